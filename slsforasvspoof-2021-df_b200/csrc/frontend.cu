@@ -1,0 +1,290 @@
+// HBM-bound front-end kernels: conv0 + LayerNorm + GELU (fused), row LayerNorm (+GELU, + centred copy), frame padding
+// for the positional conv, dtype conversion, synthetic-clip generation and the conv length formula.
+// All are coalesced / vectorised, one warp per row with shuffle reductions, fp32 statistics.
+#include "common.cuh"
+#include "kernels.h"
+#include <math.h>
+
+namespace slsb {
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// conv0: Conv1d(1 -> 512, k = 10, stride 5, bias) + Fp32LayerNorm(512) + GELU   (wav2vec2.py:795-813, first block)
+// One warp per output frame; each lane owns 16 channels (c = 64 j + 2 lane + e) whose 10 taps live in registers,
+// so a frame costs 10 broadcast loads + 160 FFMA + two shuffle reductions and one coalesced 1 KB / 2 KB store.
+// ------------------------------------------------------------------------------------------------
+constexpr int C0 = 512, K0 = 10, FRAMES_PER_WARP = 16;
+
+template <typename TO, bool EXACT>
+__global__ void __launch_bounds__(256) conv0_kernel(const float* __restrict__ wav, int S, int L0, int stride,
+                                                    const float* __restrict__ w, const float* __restrict__ bias,
+                                                    const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                                                    TO* __restrict__ out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y;
+    const int f0 = (blockIdx.x * 8 + warp) * FRAMES_PER_WARP;
+    if (f0 >= L0) return;
+    float wr[8][2][K0], br[8][2], gw[8][2], gb[8][2];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int c = 64 * j + 2 * lane + e;
+#pragma unroll
+            for (int t = 0; t < K0; ++t) wr[j][e][t] = __ldg(w + c * K0 + t);
+            br[j][e] = __ldg(bias + c); gw[j][e] = __ldg(ln_w + c); gb[j][e] = __ldg(ln_b + c);
+        }
+    const float* xb = wav + (long long)b * S;
+    const int f1 = min(f0 + FRAMES_PER_WARP, L0);
+    for (int f = f0; f < f1; ++f) {
+        float x[K0];
+#pragma unroll
+        for (int t = 0; t < K0; ++t) x[t] = __ldg(xb + f * stride + t);
+        float v[8][2];
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                float a = 0.f;
+#pragma unroll
+                for (int t = 0; t < K0; ++t) a = fmaf(wr[j][e][t], x[t], a);
+                a += br[j][e];
+                v[j][e] = a; s += a;
+            }
+        const float mean = warp_sum(s) * (1.0f / C0);
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) { const float d = v[j][e] - mean; q = fmaf(d, d, q); }
+        const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / C0) + 1e-5f);
+        TO* o = out + ((long long)b * L0 + f) * C0 + 2 * lane;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float y0 = gelu<EXACT>((v[j][0] - mean) * rstd * gw[j][0] + gb[j][0]);
+            const float y1 = gelu<EXACT>((v[j][1] - mean) * rstd * gw[j][1] + gb[j][1]);
+            if constexpr (sizeof(TO) == 2) *reinterpret_cast<uint32_t*>(o + 64 * j) = pack_bf16x2(y0, y1);
+            else *reinterpret_cast<float2*>(o + 64 * j) = make_float2(y0, y1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// row LayerNorm, one warp per row, NV = C / 128 vectors of 4 per lane
+// ------------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ void load4(const T* p, float (&v)[4]);
+template <> __device__ __forceinline__ void load4<float>(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <> __device__ __forceinline__ void load4<bf16>(const bf16* p, float (&v)[4]) {
+    const uint2 t = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&t.x), b = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+    v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+}
+template <typename T> __device__ __forceinline__ void store4(T* p, const float (&v)[4]);
+template <> __device__ __forceinline__ void store4<float>(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void store4<bf16>(bf16* p, const float (&v)[4]) {
+    uint2 t; t.x = pack_bf16x2(v[0], v[1]); t.y = pack_bf16x2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = t;
+}
+
+template <typename TI, typename TO, typename TO2, int NV, bool GELU, bool EXACT>
+__global__ void __launch_bounds__(256) ln_kernel(const TI* __restrict__ in, TO* __restrict__ out, TO2* __restrict__ out2,
+                                                 const float* __restrict__ sub, const float* __restrict__ w, const float* __restrict__ b,
+                                                 long long rows, float eps) {
+    constexpr int C = NV * 128;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const TI* x = in + row * C;
+    float v[NV][4];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        load4<TI>(x + (i * 32 + lane) * 4, v[i]);
+        s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+    }
+    const float mean = warp_sum(s) * (1.0f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float d = v[i][e] - mean; q = fmaf(d, d, q); }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / C) + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(w + c)), bb = __ldg(reinterpret_cast<const float4*>(b + c));
+        float y[4];
+        y[0] = (v[i][0] - mean) * rstd * g.x + bb.x; y[1] = (v[i][1] - mean) * rstd * g.y + bb.y;
+        y[2] = (v[i][2] - mean) * rstd * g.z + bb.z; y[3] = (v[i][3] - mean) * rstd * g.w + bb.w;
+        if constexpr (GELU) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) y[e] = gelu<EXACT>(y[e]);
+        }
+        if (out) store4<TO>(out + row * C + c, y);
+        if (out2) {
+            const float4 sv = __ldg(reinterpret_cast<const float4*>(sub + c));
+            float z[4] = {y[0] - sv.x, y[1] - sv.y, y[2] - sv.z, y[3] - sv.w};
+            store4<TO2>(out2 + row * C + c, z);
+        }
+    }
+}
+
+template <typename TI, typename TO, typename TO2, int NV>
+int ln_launch(const LnArgs& a, cudaStream_t stream) {
+    const unsigned grid = (unsigned)((a.rows + 7) / 8);
+    const TI* in = static_cast<const TI*>(a.in); TO* out = static_cast<TO*>(a.out); TO2* out2 = static_cast<TO2*>(a.out2);
+    if (a.gelu) {
+        if (a.exact_gelu) ln_kernel<TI, TO, TO2, NV, true, true><<<grid, 256, 0, stream>>>(in, out, out2, a.sub, a.w, a.b, a.rows, a.eps);
+        else ln_kernel<TI, TO, TO2, NV, true, false><<<grid, 256, 0, stream>>>(in, out, out2, a.sub, a.w, a.b, a.rows, a.eps);
+    } else {
+        ln_kernel<TI, TO, TO2, NV, false, true><<<grid, 256, 0, stream>>>(in, out, out2, a.sub, a.w, a.b, a.rows, a.eps);
+    }
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+template <typename TI, typename TO, typename TO2>
+int ln_dispatch_c(const LnArgs& a, cudaStream_t stream) {
+    if (a.C == 512) return ln_launch<TI, TO, TO2, 4>(a, stream);
+    if (a.C == 1024) return ln_launch<TI, TO, TO2, 8>(a, stream);
+    set_error("layernorm: C=%d unsupported (512 or 1024)", a.C);
+    return -1;
+}
+
+template <typename TO>
+__global__ void pad_frames_kernel(const float* __restrict__ x, TO* __restrict__ out, int T, int D, int left, int Tp, const int* __restrict__ lens) {
+    const int b = blockIdx.z, j = blockIdx.y;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (c >= D) return;
+    const int t = j - left;
+    const int len = lens ? lens[b] : T;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (t >= 0 && t < T && t < len) load4<float>(x + ((long long)b * T + t) * D + c, v);
+    store4<TO>(out + ((long long)b * Tp + j) * D + c, v);
+}
+
+__global__ void zero_padded_kernel(float* __restrict__ x, int T, int D, const int* __restrict__ lens) {
+    const int b = blockIdx.z, t = blockIdx.y;
+    if (t < lens[b]) return;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (c < D) *reinterpret_cast<float4*>(x + ((long long)b * T + t) * D + c) = make_float4(0, 0, 0, 0);
+}
+
+__global__ void cvt_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n) {
+    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const long long step = (long long)gridDim.x * blockDim.x * 4;
+    for (; i + 3 < n; i += step) {
+        float v[4];
+        load4<float>(in + i, v);
+        store4<bf16>(out + i, v);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (long long t = n & ~3ll; t < n; ++t) out[t] = __float2bfloat16_rn(in[t]);
+}
+
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void synth_kernel(float* __restrict__ out, long long first_utt, int samples, float scale) {
+    const int u = blockIdx.y;
+    const unsigned long long key = splitmix64((unsigned long long)(0x5EED0000ll + first_utt + u) * 0xD6E8FEB86659FD93ull);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < samples; i += gridDim.x * blockDim.x) {
+        const unsigned long long h = splitmix64((unsigned long long)i ^ key);
+        const unsigned s = (unsigned)(h & 0xFFFF) + (unsigned)((h >> 16) & 0xFFFF) + (unsigned)((h >> 32) & 0xFFFF) + (unsigned)(h >> 48);
+        out[(long long)u * samples + i] = __fmul_rn(__fsub_rn(__uint2float_rn(s), 131070.0f), scale);
+    }
+}
+
+struct ConvCfg { int n; int k[8]; int s[8]; };
+__global__ void frame_len_kernel(const int* __restrict__ sl, int* __restrict__ fl, int B, ConvCfg c) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int n = sl[b];
+    for (int i = 0; i < c.n; ++i) n = (n - c.k[i]) / c.s[i] + 1;
+    fl[b] = n;
+}
+
+}  // namespace
+
+int conv0_ln_gelu(const float* wav, int B, int S, int L0, int k, int stride, const float* w, const float* bias,
+                  const float* ln_w, const float* ln_b, void* out, int out_bf16, int C, bool exact_gelu, cudaStream_t stream) {
+    if (C != C0 || k != K0) { set_error("conv0: only C=512,k=10 supported (got C=%d k=%d)", C, k); return -1; }
+    dim3 grid((L0 + 8 * FRAMES_PER_WARP - 1) / (8 * FRAMES_PER_WARP), B);
+    if (out_bf16) {
+        if (exact_gelu) conv0_kernel<bf16, true><<<grid, 256, 0, stream>>>(wav, S, L0, stride, w, bias, ln_w, ln_b, static_cast<bf16*>(out));
+        else conv0_kernel<bf16, false><<<grid, 256, 0, stream>>>(wav, S, L0, stride, w, bias, ln_w, ln_b, static_cast<bf16*>(out));
+    } else {
+        if (exact_gelu) conv0_kernel<float, true><<<grid, 256, 0, stream>>>(wav, S, L0, stride, w, bias, ln_w, ln_b, static_cast<float*>(out));
+        else conv0_kernel<float, false><<<grid, 256, 0, stream>>>(wav, S, L0, stride, w, bias, ln_w, ln_b, static_cast<float*>(out));
+    }
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int layernorm(const LnArgs& a, cudaStream_t stream) {
+    if (a.rows <= 0) return 0;
+    const int sel = a.in_bf16 * 4 + a.out_bf16 * 2 + a.out2_bf16;
+    switch (sel) {
+        case 0: return ln_dispatch_c<float, float, float>(a, stream);
+        case 1: return ln_dispatch_c<float, float, bf16>(a, stream);
+        case 2: return ln_dispatch_c<float, bf16, float>(a, stream);
+        case 3: return ln_dispatch_c<float, bf16, bf16>(a, stream);
+        case 6: return ln_dispatch_c<bf16, bf16, float>(a, stream);
+        case 7: return ln_dispatch_c<bf16, bf16, bf16>(a, stream);
+        case 4: return ln_dispatch_c<bf16, float, float>(a, stream);
+        default: return ln_dispatch_c<bf16, float, bf16>(a, stream);
+    }
+}
+
+int pad_frames(const float* x, void* out, int out_bf16, int B, int T, int D, int left, int Tp, const int* lens, cudaStream_t stream) {
+    dim3 grid((D / 4 + 255) / 256, Tp, B);
+    if (out_bf16) pad_frames_kernel<bf16><<<grid, 256, 0, stream>>>(x, static_cast<bf16*>(out), T, D, left, Tp, lens);
+    else pad_frames_kernel<float><<<grid, 256, 0, stream>>>(x, static_cast<float*>(out), T, D, left, Tp, lens);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int zero_padded_frames(float* x, int B, int T, int D, const int* lens, cudaStream_t stream) {
+    if (!lens) return 0;
+    dim3 grid((D / 4 + 255) / 256, T, B);
+    zero_padded_kernel<<<grid, 256, 0, stream>>>(x, T, D, lens);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int convert_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    long long blocks = (n / 4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    cvt_kernel<<<(unsigned)blocks, 256, 0, stream>>>(in, static_cast<bf16*>(out), n);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int synth_clips(float* out, long long first_utt, int count, int samples, cudaStream_t stream) {
+    if (count <= 0) return 0;
+    const float scale = (float)(1.0 / sqrt(4.0 * (65536.0 * 65536.0 - 1.0) / 12.0));
+    dim3 grid(64, count);
+    synth_kernel<<<grid, 256, 0, stream>>>(out, first_utt, samples, scale);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int frame_lengths(const int* sample_lens, int* frame_lens, int B, int n_conv, const int* k, const int* s, cudaStream_t stream) {
+    ConvCfg c{};
+    c.n = n_conv;
+    for (int i = 0; i < n_conv && i < 8; ++i) { c.k[i] = k[i]; c.s[i] = s[i]; }
+    frame_len_kernel<<<(B + 127) / 128, 128, 0, stream>>>(sample_lens, frame_lens, B, c);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace slsb

@@ -1,0 +1,336 @@
+// bf16 tensor-core GEMM for sm_100a:  C = act(A * W^T + bias) (+ residual)
+//
+//   * operands staged by TMA (cp.async.bulk.tensor, SWIZZLE_128B) into a multi-stage smem ring,
+//   * tcgen05.mma (cta_group::1, kind::f16, 128 x BLOCK_N x 16) issued by ONE thread, fp32 accumulators in TMEM,
+//   * two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1,
+//   * persistent CTAs (grid = #SMs), static round-robin tile schedule,
+//   * 8 epilogue warps read TMEM with tcgen05.ld and fuse bias / GELU / ReLU / fp32 residual.
+//
+// Three A-operand addressing modes share the kernel (the W operand is always a plain [N, K] K-major matrix,
+// which is exactly nn.Linear's weight layout):
+//   A_PLAIN : A is [M, K] row-major.                                  (q/k/v, out_proj, fc1, fc2, proj, SAE encoder)
+//   A_CONV  : implicit GEMM for Conv1d(C->N, k taps, stride s) over channels-last activations [B, L_in, C]:
+//             output row l reads the contiguous span x[b, s*l .. s*l+k-1, :]; a 4-D tensor map
+//             (c, l_in % s, l_in / s, b) expresses every tap as a plain box -> no im2col buffer.
+//             (replaces the cuDNN call behind wav2vec2.py:795, :824-841)
+//   A_POS   : grouped positional conv (wav2vec2.py:862-875): for group g and tap t the A box is rows
+//             [m0 + t, m0 + t + 128) x channels [64 g, 64 g + 64) of the zero-padded [B, T+128, 1024] stream.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace slsb {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;       // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int kNumEpiWarps = 8;
+constexpr int kNumThreads = 128 + kNumEpiWarps * 32;   // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 spare, warps 4.. epilogue
+
+template <int BLOCK_N> struct SmemPlan {
+    static constexpr int kStageA = BLOCK_M * BLOCK_K * 2;
+    static constexpr int kStageB = BLOCK_N * BLOCK_K * 2;
+    static constexpr int kStage = kStageA + kStageB;
+    static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+    static constexpr int kBarOffset = kStages * kStage;
+    static constexpr int kBytes = kBarOffset + 256 /*barriers + tmem ptr*/ + 1024 /*alignment slack*/;
+};
+
+struct DevParams {
+    int M, N, K;
+    int batches, m_tiles, n_tiles;
+    int conv_cin, conv_stride;
+    void* out;
+    long long ldc, out_batch_stride;
+    const float* bias;
+    const float* residual;
+    long long ldr, res_batch_stride;
+    int act, out_bf16;
+};
+
+template <int ACT, bool OUT_BF16, bool HAS_RES>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], const DevParams& p, long long out_off, long long res_off,
+                                               int col0, bool row_ok) {
+    float v[32];
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float4 b = __ldg(b4 + j);
+        v[4 * j + 0] = __uint_as_float(acc[4 * j + 0]) + b.x;
+        v[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + b.y;
+        v[4 * j + 2] = __uint_as_float(acc[4 * j + 2]) + b.z;
+        v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + b.w;
+    }
+    if constexpr (ACT == ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+    } else if constexpr (ACT == ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+    }
+    if (!row_ok) return;
+    if constexpr (HAS_RES) {
+        const float4* r4 = reinterpret_cast<const float4*>(p.residual + res_off + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float4 r = __ldg(r4 + j);
+            v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+        }
+    }
+    if constexpr (OUT_BF16) {
+        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + out_off + col0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint4 w;
+            w.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+            w.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+            w.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+            w.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+            o[j] = w;
+        }
+    } else {
+        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_off + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+}
+
+template <int BLOCK_N, int A_MODE>
+__global__ void __launch_bounds__(kNumThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const DevParams p) {
+    using Plan = SmemPlan<BLOCK_N>;
+    constexpr int kStages = Plan::kStages;
+    constexpr uint32_t kTmemCols = 2 * BLOCK_N;   // two accumulator stages (power of two >= 32 for BLOCK_N in {64,128,256})
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Plan::kBarOffset);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full = empty_bar + kStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = p.batches * p.m_tiles * p.n_tiles;
+    const int num_kb = p.K / BLOCK_K;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kNumEpiWarps); }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int t = tile;
+                const int m_blk = t % p.m_tiles; t /= p.m_tiles;
+                const int n_blk = t % p.n_tiles;
+                const int b = t / p.n_tiles;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Plan::kStage;
+                    uint8_t* sb = sa + Plan::kStageA;
+                    mbar_expect_tx(&full_bar[stage], Plan::kStage);
+                    if constexpr (A_MODE == A_PLAIN) {
+                        tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+                    } else if constexpr (A_MODE == A_CONV) {
+                        const int k0 = kb * BLOCK_K;
+                        const int tap = k0 / p.conv_cin, c = k0 - tap * p.conv_cin;
+                        tma_load_4d(sa, &tmap_a, &full_bar[stage], c, tap % p.conv_stride, m_blk * BLOCK_M + tap / p.conv_stride, b);
+                    } else {
+                        tma_load_3d(sa, &tmap_a, &full_bar[stage], n_blk * BLOCK_K, m_blk * BLOCK_M + kb, b);
+                    }
+                    tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (single thread) =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Plan::kStage);
+                    const uint32_t sb = sa + Plan::kStageA;
+                    const uint64_t da = make_smem_desc_sw128(sa, 0, 1024);
+                    const uint64_t db = make_smem_desc_sw128(sb, 0, 1024);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        // advance both descriptors by k * 16 elements * 2 B = 32 B inside the 128-B swizzle row
+                        tc_mma_f16(d_tmem, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    tc_commit(&empty_bar[stage]);          // smem slot free once these MMAs have read it
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tmem_full[acc]);                // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue warps =====================
+        const int q = warp & 3;                    // TMEM lane quadrant this warp may access
+        const int half = (warp - 4) >> 2;          // column half
+        constexpr int kColsPerWarp = BLOCK_N / 2;
+        const int r = q * 32 + lane;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            int t = tile;
+            const int m_blk = t % p.m_tiles; t /= p.m_tiles;
+            const int n_blk = t % p.n_tiles;
+            const int b = t / p.n_tiles;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int row = m_blk * BLOCK_M + r;
+            const bool row_ok = row < p.M;
+            const long long out_off = (long long)b * p.out_batch_stride + (long long)row * p.ldc;
+            const long long res_off = (long long)b * p.res_batch_stride + (long long)row * p.ldr;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr0 = tmem_base + (uint32_t(q * 32) << 16) + acc * BLOCK_N + half * kColsPerWarp;
+#pragma unroll 1
+            for (int c = 0; c < kColsPerWarp; c += 32) {
+                uint32_t a[32];
+                tmem_ld_32x32b_x32(taddr0 + c, a);
+                tmem_ld_wait();
+                const int col0 = n_blk * BLOCK_N + half * kColsPerWarp + c;
+                const int sel = p.act * 4 + p.out_bf16 * 2 + (p.residual != nullptr ? 1 : 0);
+                switch (sel) {
+                    case ACT_NONE * 4 + 2 + 0: epilogue_chunk<ACT_NONE, true, false>(a, p, out_off, res_off, col0, row_ok); break;
+                    case ACT_GELU * 4 + 2 + 0: epilogue_chunk<ACT_GELU, true, false>(a, p, out_off, res_off, col0, row_ok); break;
+                    case ACT_NONE * 4 + 0 + 1: epilogue_chunk<ACT_NONE, false, true>(a, p, out_off, res_off, col0, row_ok); break;
+                    case ACT_NONE * 4 + 0 + 0: epilogue_chunk<ACT_NONE, false, false>(a, p, out_off, res_off, col0, row_ok); break;
+                    case ACT_RELU * 4 + 0 + 0: epilogue_chunk<ACT_RELU, false, false>(a, p, out_off, res_off, col0, row_ok); break;
+                    case ACT_GELU * 4 + 0 + 1: epilogue_chunk<ACT_GELU, false, true>(a, p, out_off, res_off, col0, row_ok); break;
+                    case ACT_GELU * 4 + 0 + 0: epilogue_chunk<ACT_GELU, false, false>(a, p, out_off, res_off, col0, row_ok); break;
+                    case ACT_RELU * 4 + 2 + 0: epilogue_chunk<ACT_RELU, true, false>(a, p, out_off, res_off, col0, row_ok); break;
+                    default: break;   // launcher rejects other combinations
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<kTmemCols>(tmem_base);
+    }
+}
+
+bool epilogue_supported(int act, int out_bf16, bool has_res) {
+    const int sel = act * 4 + out_bf16 * 2 + (has_res ? 1 : 0);
+    switch (sel) {
+        case ACT_NONE * 4 + 2 + 0: case ACT_GELU * 4 + 2 + 0: case ACT_NONE * 4 + 0 + 1: case ACT_NONE * 4 + 0 + 0:
+        case ACT_RELU * 4 + 0 + 0: case ACT_GELU * 4 + 0 + 1: case ACT_GELU * 4 + 0 + 0: case ACT_RELU * 4 + 2 + 0:
+            return true;
+        default: return false;
+    }
+}
+
+template <int BLOCK_N, int A_MODE>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const DevParams& dp, int num_sms, cudaStream_t stream) {
+    using Plan = SmemPlan<BLOCK_N>;
+    static bool configured = false;
+    auto kern = tc_gemm_kernel<BLOCK_N, A_MODE>;
+    if (!configured) {
+        SLSB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::kBytes));
+        configured = true;
+    }
+    const int tiles = dp.batches * dp.m_tiles * dp.n_tiles;
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    kern<<<grid, kNumThreads, Plan::kBytes, stream>>>(ta, tb, dp);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+int tc_gemm(const TcGemmArgs& g, int num_sms, cudaStream_t stream) {
+    if (g.K % BLOCK_K != 0 || g.K <= 0) { set_error("tc_gemm: K=%d must be a positive multiple of %d", g.K, BLOCK_K); return -1; }
+    if (!epilogue_supported(g.act, g.out_bf16, g.residual != nullptr)) {
+        set_error("tc_gemm: unsupported epilogue act=%d out_bf16=%d res=%d", g.act, g.out_bf16, g.residual != nullptr);
+        return -1;
+    }
+    int block_n;
+    if (g.a_mode == A_POS) block_n = 64;
+    else if (g.N % 256 == 0) block_n = 256;
+    else if (g.N % 128 == 0) block_n = 128;
+    else if (g.N % 64 == 0) block_n = 64;
+    else { set_error("tc_gemm: N=%d must be a multiple of 64", g.N); return -1; }
+    if (g.M <= 0 || g.batches <= 0) return 0;
+
+    DevParams dp{};
+    dp.M = g.M; dp.N = g.N; dp.K = g.K;
+    dp.batches = g.batches;
+    dp.m_tiles = (g.M + BLOCK_M - 1) / BLOCK_M;
+    dp.n_tiles = g.N / block_n;
+    dp.conv_cin = g.conv_cin; dp.conv_stride = g.conv_stride;
+    dp.out = g.out; dp.ldc = g.ldc; dp.out_batch_stride = g.out_batch_stride;
+    dp.bias = g.bias; dp.residual = g.residual; dp.ldr = g.ldr; dp.res_batch_stride = g.res_batch_stride;
+    dp.act = g.act; dp.out_bf16 = g.out_bf16;
+
+    CUtensorMap ta, tb;
+    {   // W: [N, K] K-major
+        uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.N};
+        uint64_t strides[1] = {(uint64_t)g.ldw * 2};
+        uint32_t box[2] = {BLOCK_K, (uint32_t)block_n};
+        if (encode_tmap_bf16(&tb, g.W, 2, dims, strides, box)) return -1;
+    }
+    if (g.a_mode == A_PLAIN) {
+        uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.M};
+        uint64_t strides[1] = {(uint64_t)g.lda * 2};
+        uint32_t box[2] = {BLOCK_K, BLOCK_M};
+        if (encode_tmap_bf16(&ta, g.A, 2, dims, strides, box)) return -1;
+    } else if (g.a_mode == A_CONV) {
+        // activations [B, L_in, C] viewed as (c, l_in % s, l_in / s, b)
+        const uint64_t C = g.conv_cin, s = g.conv_stride, Lin = g.conv_lin;
+        uint64_t dims[4] = {C, s, (Lin + s - 1) / s, (uint64_t)g.batches};
+        uint64_t strides[3] = {C * 2, s * C * 2, Lin * C * 2};
+        uint32_t box[4] = {BLOCK_K, 1, BLOCK_M, 1};
+        if (encode_tmap_bf16(&ta, g.A, 4, dims, strides, box)) return -1;
+    } else {
+        // zero-padded stream [B, Tp, D]; box = 64 channels x 128 frames
+        uint64_t dims[3] = {(uint64_t)g.pos_dim, (uint64_t)g.pos_tp, (uint64_t)g.batches};
+        uint64_t strides[2] = {(uint64_t)g.pos_dim * 2, (uint64_t)g.pos_tp * g.pos_dim * 2};
+        uint32_t box[3] = {BLOCK_K, BLOCK_M, 1};
+        if (encode_tmap_bf16(&ta, g.A, 3, dims, strides, box)) return -1;
+    }
+    if (g.a_mode == A_PLAIN) {
+        if (block_n == 256) return launch<256, A_PLAIN>(ta, tb, dp, num_sms, stream);
+        if (block_n == 128) return launch<128, A_PLAIN>(ta, tb, dp, num_sms, stream);
+        return launch<64, A_PLAIN>(ta, tb, dp, num_sms, stream);
+    } else if (g.a_mode == A_CONV) {
+        if (block_n == 256) return launch<256, A_CONV>(ta, tb, dp, num_sms, stream);
+        if (block_n == 128) return launch<128, A_CONV>(ta, tb, dp, num_sms, stream);
+        return launch<64, A_CONV>(ta, tb, dp, num_sms, stream);
+    }
+    return launch<64, A_POS>(ta, tb, dp, num_sms, stream);
+}
+
+}  // namespace slsb

@@ -1,0 +1,112 @@
+// Host-side launchers of every kernel in the library (internal header; the public C ABI is include/slsb200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace slsb {
+
+enum AMode : int { A_PLAIN = 0, A_CONV = 1, A_POS = 2 };
+
+// ---------------------------------------------------------------- tcgen05 bf16 GEMM (gemm_tc.cu)
+struct TcGemmArgs {
+    int a_mode = A_PLAIN;
+    const void* A = nullptr;      // bf16
+    long long lda = 0;            // A_PLAIN: row stride in elements
+    const void* W = nullptr;      // bf16 [N, K], row stride ldw
+    long long ldw = 0;
+    int M = 0, N = 0, K = 0;      // M = rows per batch item
+    int batches = 1;
+    // A_CONV
+    int conv_cin = 0, conv_stride = 0, conv_lin = 0;
+    // A_POS
+    int pos_dim = 0, pos_tp = 0;
+    // epilogue
+    void* out = nullptr; long long ldc = 0, out_batch_stride = 0; int out_bf16 = 0;
+    const float* bias = nullptr;
+    const float* residual = nullptr; long long ldr = 0, res_batch_stride = 0;
+    int act = 0;
+};
+int tc_gemm(const TcGemmArgs& g, int num_sms, cudaStream_t stream);
+
+// ---------------------------------------------------------------- fp32 SIMT GEMM (gemm_simt.cu)
+// C[z][m][n] = act(sum_k A[z][m][k] * W[zw][n][k] + bias[n_off + n]) (+ residual); A/W/out element types selectable.
+struct SimtGemmArgs {
+    const void* A = nullptr; int a_bf16 = 0;
+    long long lda = 0, a_batch_stride = 0;     // elements
+    int a_kinner = 0; long long a_kouter = 0;  // k -> (k / kinner) * kouter + k % kinner   (kinner = 0: contiguous)
+    const float* W = nullptr; long long ldw = 0, w_group_stride = 0;   // fp32 weights
+    int groups = 1;                             // z = batch * groups + group ; group selects W block, A column offset, out column offset
+    long long a_group_offset = 0; int n_per_group = 0;
+    int M = 0, N = 0, K = 0, batches = 1;
+    void* out = nullptr; int out_bf16 = 0; long long ldc = 0, out_batch_stride = 0;
+    const float* bias = nullptr;
+    const float* residual = nullptr; long long ldr = 0, res_batch_stride = 0;
+    int act = 0; int exact_gelu = 1;
+};
+int simt_gemm(const SimtGemmArgs& g, cudaStream_t stream);
+
+// ---------------------------------------------------------------- feature extractor / norms (frontend.cu)
+// conv0 (C_in = 1) + LayerNorm(512) + GELU fused, channels-last output [B, L0, 512]
+int conv0_ln_gelu(const float* wav, int B, int S, int L0, int k, int stride, const float* w /*[C,k]*/, const float* bias,
+                  const float* ln_w, const float* ln_b, void* out, int out_bf16, int C, bool exact_gelu, cudaStream_t stream);
+// row-wise LayerNorm over C (C in {512, 1024}), optional GELU, optional second output (y - sub[c]); in/out fp32 or bf16
+struct LnArgs {
+    const void* in = nullptr; int in_bf16 = 0;
+    void* out = nullptr; int out_bf16 = 0;
+    void* out2 = nullptr; int out2_bf16 = 0; const float* sub = nullptr;   // out2 = y - sub
+    const float* w = nullptr; const float* b = nullptr;
+    long long rows = 0; int C = 0; int gelu = 0; int exact_gelu = 1; float eps = 1e-5f;
+    // optional per-utterance masking: rows of utterance u at frame t >= lens[u] are written as zeros
+    const int* lens = nullptr; int frames_per_utt = 0;
+};
+int layernorm(const LnArgs& a, cudaStream_t stream);
+// x[B, T, D] (fp32) -> zero-padded [B, T + K, D] (fp32 or bf16), `left` zero frames in front; frames >= lens[b] zeroed
+int pad_frames(const float* x, void* out, int out_bf16, int B, int T, int D, int left, int Tp, const int* lens, cudaStream_t stream);
+// zero frames t >= lens[b] of x[B, T, D] in place (wav2vec2.py:912-913)
+int zero_padded_frames(float* x, int B, int T, int D, const int* lens, cudaStream_t stream);
+int convert_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t stream);
+// deterministic synthetic clips (same integer hash as oracle.trunk.hash_normal)
+int synth_clips(float* out, long long first_utt, int count, int samples, cudaStream_t stream);
+// frame lengths from sample lengths (wav2vec2.py:523-538)
+int frame_lengths(const int* sample_lens, int* frame_lens, int B, int n_conv, const int* k, const int* s, cudaStream_t stream);
+
+// ---------------------------------------------------------------- attention (attention.cu)
+// qkv [B*T, 3*D] (q pre-scaled), heads of 64; out [B*T, D]; keys >= lens[b] masked (lens may be null)
+int attention_simt(const void* qkv, void* out, int io_bf16, int B, int T, int H, const int* lens, cudaStream_t stream);
+int attention_tc(const void* qkv_bf16, void* out_bf16, int B, int T, int H, const int* lens, int num_sms, cudaStream_t stream);
+
+// ---------------------------------------------------------------- heads (heads.cu)
+// per-row top-k threshold of non-negative fp32 rows: writes thr[row] (k-th largest value) and tie_cut[row]
+// (entries == thr are kept only while index < tie_cut[row]) -- canonical lowest-index-wins rule
+int topk_threshold(const float* acts, long long rows, int D, int k, float* thr, int* tie_cut, cudaStream_t stream);
+// dense encoded[row][f] = keep ? acts : 0 (API parity with AutoEncoderTopK.encode, model.py:68-79)
+int topk_densify(const float* acts, const float* thr, const int* tie_cut, float* encoded, long long rows, int D, cudaStream_t stream);
+// pooled[b][f] = (1/len_b) * sum_{t < len_b} kept(acts[b,t,f])   (model.py:245), fixed summation order
+int topk_mean_pool(const float* acts, const float* thr, const int* tie_cut, float* pooled, int B, int T, int D, const int* lens, cudaStream_t stream);
+// window top-k (model_window_topk.py:118-203): window sums -> per-window top-k -> votes -> per-frame top-k
+int window_sums(const float* acts, float* sums, int B, int T, int D, int window, int stride, int nw, cudaStream_t stream);
+int window_votes(const float* acts, const float* sums, const float* thr_w, const int* cut_w, float* votes,
+                 int B, int T, int D, int window, int stride, int nw, cudaStream_t stream);
+// keep-by-votes: encoded = acts * mask(votes) ; pooled likewise
+int votes_densify(const float* acts, const float* votes, const float* thr, const int* tie_cut, float* encoded, long long rows, int D, cudaStream_t stream);
+int votes_mean_pool(const float* acts, const float* votes, const float* thr, const int* tie_cut, float* pooled, int B, int T, int D, const int* lens, cudaStream_t stream);
+// classifier: LN(D) -> Linear(D,Hd) -> ReLU -> Linear(Hd,2) -> log_softmax   (model.py:183-189, :246-247)
+int classifier_head(const float* pooled, int B, int D, int Hd, const float* ln_w, const float* ln_b, const float* w1, const float* b1,
+                    const float* w2, const float* b2, float* logprob, cudaStream_t stream);
+// mean over valid frames of a [B, T, D] fp32 stream (use_sae=False / use_sparse_features=False pooling)
+int mean_pool_frames(const float* x, float* pooled, int B, int T, int D, const int* lens, cudaStream_t stream);
+// SLS (model_backup.py:186-202 + upstream classifier)
+int sls_layer_weights(const float* const* layers, int n_layers, int B, int T, int D, const float* fc0_w, const float* fc0_b,
+                      float* layer_w /*[B, n_layers]*/, const int* lens, cudaStream_t stream);
+int sls_fuse_pool(const float* const* layers, int n_layers, const float* layer_w, int B, int T, int D, const float* bn /*w,b,rm,rv*/,
+                  float bn_eps, float* out /*[B, (T/3)*(D/3) padded to ldo]*/, int ldo, cudaStream_t stream);
+int sls_tail(const float* h /*[B, Hd] pre-activation fc1 out*/, int B, int Hd, const float* w3, const float* b3, float* logprob, cudaStream_t stream);
+// split-K skinny GEMM for SLS fc1 (M = B small, K = 22848): out[b][n] = sum_k x[b][k] w[n][k] + bias[n]; weights fp32 or bf16
+int skinny_gemm(const float* x, int ldx, const void* w, int w_bf16, int ldw, const float* bias, float* out, int B, int N, int K,
+                float* scratch, cudaStream_t stream);
+// scores = exp(logprob[:, 1])   (main.py:183-184)
+int scores_from_logprob(const float* logprob, float* scores, int B, cudaStream_t stream);
+// mse between recon and x (model.py:224-225), deterministic two-stage reduction
+int mse_loss(const float* a, const float* b, long long n, float* out_scalar, float* scratch, cudaStream_t stream);
+
+}  // namespace slsb
