@@ -1,0 +1,246 @@
+#!/usr/bin/env python
+"""Benchmark of the scoring hot path: 4-s utterances/second through XLS-R-300M + TopK-SAE head (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch of 64 synthetic 64 600-sample clips per GPU (BASELINE
+config 2, bf16).  ``value`` = whole-job utterances/s with the clips already resident in HBM; ``e2e`` = the same
+metric through ``slsb_score_host`` (pinned host clips -> H2D -> forward -> scores -> D2H every step).
+One JSON line on rank 0.  Multi-GPU: one process per GPU (torchrun), utterance-sharded, weak scaling; the only
+collective is the final all-gather of scores, outside the per-step hot path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_PER_UTT_ENC_GEMM = 121.40e9   # 24 x (qkv + out + fc1 + fc2) GEMMs per 64 600-sample clip
+FLOP_PER_UTT_TOTAL = 150.45e9      # trunk + SAE encoder + classifier
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path, timed on the box's host cores: the oracle port
+    (reference head code semantics on the restated fairseq trunk; fairseq is not shipped)."""
+    if rank != 0:
+        return
+    import torch
+    from oracle.heads import OracleModel
+    from oracle.trunk import synth_clips
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m = OracleModel(head="sae").eval()
+    bs = 4
+    x = synth_clips(0, bs)
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 2))):
+            m(x)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            m(x)
+        dt = time.perf_counter() - t0
+    v = bs * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "utterances_per_second", "value": v, "unit": "utt/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "XLS-R-300M + TopK-SAE head, 64600-sample clips (BASELINE config 2)", "sample": f"{bs} clips per step on CPU"},
+        "cpu_baseline": {"value": v, "unit": "utt/s", "cores": cores, "kind": "port", "sample": f"{args.steps} steps x {bs} clips, fp32, torch CPU"},
+        "e2e": {"value": v, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--head", default="sae", choices=["sae", "window", "sls"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    import sls_b200
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(1234)
+    B, S = args.batch, 64600
+    if args.head == "sls":
+        model = sls_b200.ModelSLS(None, dev, cp_path=None, precision=args.precision)
+        head = sls_b200.HEAD_SLS
+    else:
+        cls = sls_b200.ModelWindowTopK if args.head == "window" else sls_b200.Model
+        model = cls(None, dev, cp_path=None, precision=args.precision)
+        head = sls_b200.HEAD_WINDOW if args.head == "window" else sls_b200.HEAD_SAE
+    model = model.to(dev).eval()
+    eng = model.engine()
+    prec = sls_b200.PRECISIONS[args.precision]
+
+    # rotating pool of device-resident batches; utterances are keyed by global index so every rank scores its own shard
+    n_pool = 4
+    pool = [eng.synth_clips((rank * n_pool + i) * B, B, S) for i in range(n_pool)]
+    host = [p.cpu().pin_memory() for p in pool]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    out = None
+    for i in range(args.warmup):
+        out = eng.forward(pool[i % n_pool], head, prec)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        out = eng.forward(pool[i % n_pool], head, prec)
+    ev1.record()
+    barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = eng.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    assert torch.isfinite(out).all()
+
+    # end to end through the C ABI with host buffers (H2D + forward + D2H every step)
+    for i in range(2):
+        eng.score_host(host[i % n_pool], head, prec)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        sc = eng.score_host(host[i % n_pool], head, prec)
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+
+    # roofline of the dominant kernel (tcgen05 encoder GEMMs): per-launch CUDA events on the launch stream, separate
+    # pass over the same workload so the event records do not sit inside the headline timing
+    peaks = _peaks()
+    roof = None
+    if args.precision == "bf16":
+        eng.profile(True)
+        psteps = min(args.steps, 3)
+        for i in range(psteps):
+            eng.forward(pool[i % n_pool], head, prec)
+        g_ms, g_fl, g_n = eng.profile_read(0)
+        other = {k: eng.profile_read(i) for i, k in ((1, "conv_gemm"), (2, "pos_conv"), (3, "other_gemm"), (4, "attention"))}
+        eng.profile(False)
+        ach = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": "tc_gemm_kernel (encoder qkv/out/fc1/fc2)", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
+                "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["source"] + " (sustained)",
+                "launches": g_n, "avg_launch_ms": g_ms / max(g_n, 1), "flops_per_launch": g_fl / max(g_n, 1),
+                "share_of_step": (g_ms / psteps) / (ms / args.steps),
+                "other_kernels_ms_per_step": {k: v[0] / psteps for k, v in other.items()},
+                "other_kernels_tflops": {k: (v[1] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else 0.0) for k, v in other.items()}}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.heads import OracleModel
+        from oracle.trunk import synth_clips
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        om = OracleModel(head="sae").eval()
+        xb = synth_clips(0, 4)
+        with torch.no_grad():
+            om(xb[:1])
+            t0 = time.perf_counter()
+            n = 0
+            while time.perf_counter() - t0 < 12.0 and n < 8:
+                om(xb)
+                n += 1
+            dt = time.perf_counter() - t0
+        cpu = {"value": 4 * n / dt, "unit": "utt/s", "cores": cores, "kind": "port",
+               "sample": f"{n} batches x 4 clips of the same workload, fp32 torch CPU oracle (reference heads on restated fairseq trunk)"}
+
+    if rank == 0:
+        utt = B * world * args.steps
+        line = {
+            "metric": "utterances_per_second", "value": utt / (ms * 1e-3), "unit": "utt/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
+            "data": "synthetic",
+            "config": {"workload": f"XLS-R-300M + {args.head} head, batch={B} x 64600-sample clips per GPU (BASELINE config 2), random-init weights",
+                       "global_batch": B * world, "parallelism": f"utterance-sharded x{world}",
+                       "l2": "per-step working set (631 MB bf16 weights + >2 GB activations) exceeds the 126 MB L2; 4 rotating input batches"},
+            "e2e": {"value": utt / (e2e_ms * 1e-3), "unit": "utt/s", "h2d_bytes_per_step": B * S * 4, "d2h_bytes_per_step": B * 4},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "tflops_per_gpu_whole_step": FLOP_PER_UTT_TOTAL * B * args.steps / (ms * 1e-3) / 1e12,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

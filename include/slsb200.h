@@ -1,0 +1,141 @@
+/* slsb200 -- C ABI of the B200-native XLS-R-300M + {TopK-SAE | window-TopK | SLS} scoring path.
+ *
+ * This is the drop-in boundary for the reference's `Model(args, device).forward(x) -> log-probs`
+ * (SLSforASVspoof-2021-DF, citations relative to /root/reference):
+ *
+ *   slsb_forward        <->  model.py:195-260  Model.forward            (H-SAE, what main.py --is_eval runs)
+ *                            model_window_topk.py:324-393               (H-WIN, --use_window_topk)
+ *                            model_backup.py:167-202 + upstream SLS     (H-SLS)
+ *   slsb_extract_feat   <->  model.py:128-141  SSLModel.extract_feat    (fairseq Wav2Vec2Model.forward(mask=False,
+ *                            features_only=True)['x'], wav2vec/wav2vec2.py:540-647)
+ *   slsb_get_tensor     <->  ...['layer_results'] (wav2vec2.py:958), sae activations (model.py:236-240)
+ *   slsb_sae_encode     <->  model.py:68-79 / model_window_topk.py:68-116  AutoEncoderTopK.encode
+ *   slsb_sae_decode     <->  model.py:81-83  AutoEncoderTopK.decode
+ *   slsb_score_host     <->  main.py:172-193  produce_evaluation_file's per-batch body
+ *                            (batch_x.to(device); model(...); exp(out)[:,1].cpu())
+ *
+ * Conventions: plain pointers and sizes only; every *_dev pointer is device memory owned by the CALLER;
+ * the engine owns its weight arena and workspace; `stream` is a cudaStream_t passed as void*;
+ * no call synchronises the host except slsb_score_host (which returns host scores) and slsb_create/destroy;
+ * one engine per GPU per process, not thread-safe per engine.  Every function returns 0 on success and a
+ * negative code on failure; slsb_last_error() gives the message (thread-local).  There is no CPU fallback:
+ * without a CUDA device slsb_create fails.
+ */
+#ifndef SLSB200_H
+#define SLSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLSB_ABI_VERSION 1
+
+enum { SLSB_HEAD_NONE = 0, SLSB_HEAD_SAE = 1, SLSB_HEAD_WINDOW = 2, SLSB_HEAD_SLS = 3 };
+enum { SLSB_PREC_FP32 = 0, SLSB_PREC_BF16 = 1 };
+enum { SLSB_ATTN_AUTO = 0, SLSB_ATTN_SIMT = 1, SLSB_ATTN_TC = 2 };
+
+typedef struct slsb_config {
+    int32_t n_conv;              /* 7 */
+    int32_t conv_dim;            /* 512 */
+    int32_t conv_kernel[8];      /* 10,3,3,3,3,2,2 */
+    int32_t conv_stride[8];      /* 5,2,2,2,2,2,2 */
+    int32_t embed_dim;           /* 1024 */
+    int32_t ffn_dim;             /* 4096 */
+    int32_t n_heads;             /* 16 (head dim must be 64) */
+    int32_t n_layers;            /* 24 */
+    int32_t pos_kernel;          /* 128 */
+    int32_t pos_groups;          /* 16 (group width must be 64) */
+    int32_t sae_dict;            /* 4096; 0 = no SAE head weights */
+    int32_t sae_k;               /* 128 */
+    int32_t sae_window;          /* 8 for H-WIN, 1 otherwise */
+    int32_t cls_in;              /* classifier input dim: sae_dict (sparse features) or embed_dim */
+    int32_t cls_hidden;          /* 256 */
+    int32_t sls_frames;          /* 201: frame count the SLS fc1 was sized for; 0 = no SLS head weights */
+    int32_t sls_hidden;          /* 1024 */
+    int32_t attn_impl;           /* SLSB_ATTN_* */
+    int32_t reserved[8];
+} slsb_config;
+
+typedef struct slsb_engine slsb_engine;
+
+int slsb_abi_version(void);
+const char* slsb_last_error(void);
+
+/* life cycle */
+int slsb_create(const slsb_config* cfg, int device, slsb_engine** out);
+int slsb_destroy(slsb_engine* e);
+
+/* weights: `name` is one of the packed tensor names listed in INTEGRATION.md ("conv1.w", "L3.qkv.w", ...);
+ * `src` is fp32, host or device memory (cudaMemcpyDefault); `numel` must match the engine's expectation.
+ * slsb_finalize_weights builds the bf16 copies the tensor-core path reads. */
+int slsb_set_weight(slsb_engine* e, const char* name, const float* src, int64_t numel, void* stream);
+int slsb_finalize_weights(slsb_engine* e, void* stream);
+int64_t slsb_weight_numel(slsb_engine* e, const char* name);   /* -1 if unknown */
+
+/* shape helper: frames produced by the conv stack for `samples` input samples (wav2vec2.py:523-538) */
+int slsb_frames_for_samples(const slsb_engine* e, int samples);
+
+/* The hot path.  wav_dev: fp32 [B, S]; sample_lens_dev: int32 [B] valid samples per clip, or NULL (all S);
+ * logprob_dev: fp32 [B, 2] (ignored for SLSB_HEAD_NONE).  Asynchronous on `stream`. */
+int slsb_forward(slsb_engine* e, const float* wav_dev, const int32_t* sample_lens_dev, int B, int S,
+                 int head, int precision, float* logprob_dev, void* stream);
+
+/* SSLModel.extract_feat: x_dev fp32 [B, T, embed_dim] (final LayerNorm applied, wav2vec2.py:905-906) */
+int slsb_extract_feat(slsb_engine* e, const float* wav_dev, const int32_t* sample_lens_dev, int B, int S,
+                      int precision, float* x_dev, void* stream);
+
+/* Tensors left in the workspace by the last forward/extract_feat, copied into caller memory (fp32):
+ *   "x" [B,T,D] | "layer_results.<i>" [B,T,D] raw residual stream after layer i | "features" [B,T,conv_dim]
+ *   "acts" [B,T,dict] post-ReLU pre-top-k | "encoded" [B,T,dict] | "pooled" [B,cls_in] | "sls_weights" [B,n_layers] */
+int slsb_get_tensor(slsb_engine* e, const char* name, float* dst_dev, int64_t numel, void* stream);
+
+/* AutoEncoderTopK.encode / decode on caller activations: x_dev fp32 [rows, embed_dim] with rows = B*T.
+ * window > 1 applies the window top-k over T frames per utterance (rows must be a multiple of T). */
+int slsb_sae_encode(slsb_engine* e, const float* x_dev, int64_t rows, int T, int window, int precision,
+                    float* encoded_dev, void* stream);
+int slsb_sae_decode(slsb_engine* e, const float* encoded_dev, int64_t rows, int precision, float* recon_dev, void* stream);
+/* mean((decode(encoded) - x)^2) of the last forward (model.py:224-225); loss_dev: fp32 [1] */
+int slsb_sae_loss(slsb_engine* e, int precision, float* loss_dev, void* stream);
+
+/* End-to-end scoring of one batch with HOST buffers (pinned or pageable): H2D copy of the clips, forward,
+ * score = exp(logprob[:,1]) (main.py:183-184), D2H copy of B floats, stream synchronised before returning. */
+int slsb_score_host(slsb_engine* e, const float* wav_host, const int32_t* sample_lens_host, int B, int S,
+                    int head, int precision, float* scores_host, void* stream);
+
+/* synthetic clips keyed by utterance index, bit-identical to oracle.trunk.synth_clips */
+int slsb_synth_clips(float* wav_dev, int64_t first_utt, int count, int samples, void* stream);
+
+/* how many kernels the engine launched since creation (bench.py's gpu_launches) */
+int64_t slsb_launch_count(const slsb_engine* e);
+
+/* Per-launch CUDA-event timing of the tensor-core kernels (events recorded on the launch stream).
+ * kind: 0 encoder GEMMs (qkv/out/fc1/fc2), 1 conv-stack implicit GEMMs, 2 positional conv, 3 other GEMMs, 4 attention.
+ * slsb_profile_read synchronises the device and sums elapsed ms / algorithmic FLOPs / launches since enable. */
+int slsb_profile_enable(slsb_engine* e, int on);
+int slsb_profile_read(slsb_engine* e, int kind, double* ms_out, double* flops_out, int64_t* launches_out);
+
+/* ---- single-op entry points (unit tests call each kernel through the same ABI) ---- */
+/* out = act(A[M,K] * W[N,K]^T + bias[N]) (+ residual[M,N]); act: 0 none, 1 gelu, 2 relu.
+ * precision fp32: A, W, out fp32 (CUDA cores).  bf16: A, W bf16 (tcgen05), out bf16 if out_bf16 else fp32. */
+int slsb_op_gemm(int precision, const void* A, const void* W, const float* bias, const float* residual, void* out,
+                 int M, int N, int K, int act, int out_bf16, void* stream);
+/* Conv1d(C->N, k, stride) over channels-last x[B, L_in, C] as implicit GEMM; W is [N, k*C] tap-major */
+int slsb_op_conv(int precision, const void* x, const void* W, const float* bias, void* out, int B, int L_in, int C, int N,
+                 int k, int stride, void* stream);
+/* grouped positional conv + GELU + residual: x fp32 [B,T,D]; W [D, K*64] (per out channel: tap-major, 64 in-channels) */
+int slsb_op_posconv(int precision, const float* x, const void* W, const float* bias, float* out, void* scratch,
+                    int B, int T, int D, int K, const int32_t* frame_lens_dev, void* stream);
+int slsb_op_conv0(int out_bf16, const float* wav, const float* w, const float* bias, const float* ln_w, const float* ln_b,
+                  void* out, int B, int S, int exact_gelu, void* stream);
+int slsb_op_layernorm(const void* in, int in_bf16, void* out, int out_bf16, const float* w, const float* b,
+                      int64_t rows, int C, int gelu, int exact_gelu, void* stream);
+int slsb_op_attention(int impl, int io_bf16, const void* qkv, void* out, int B, int T, int H,
+                      const int32_t* frame_lens_dev, void* stream);
+int slsb_op_topk(const float* x, int64_t rows, int D, int k, float* thr, int32_t* tie_cut, float* encoded_or_null, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLSB200_H */

@@ -267,6 +267,8 @@ class Wav2Vec2Trunk(nn.Module):
 # --------------------------------------------------------------------------------------------
 # Deterministic, machine-independent parameter / clip synthesis (integer hash -> float, no libm)
 # --------------------------------------------------------------------------------------------
+import zlib
+
 import numpy as np
 
 _M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
@@ -307,9 +309,10 @@ def seeded_init_(module: nn.Module, seed: int = 1234) -> nn.Module:
     LayerNorm affines so a dropped bias/affine cannot hide behind a zero init."""
     names = dict(module.named_parameters())
     names.update({k: v for k, v in module.named_buffers() if v.dtype.is_floating_point})
-    for i, (name, p) in enumerate(sorted(names.items())):
+    for name, p in sorted(names.items()):
         n = p.numel()
-        z = torch.from_numpy(hash_normal(seed * 100003 + i, n)).view(p.shape)
+        # keyed by the parameter NAME, so the trunk gets the same weights under every head
+        z = torch.from_numpy(hash_normal(seed * 100003 + zlib.crc32(name.encode()), n)).view(p.shape)
         leaf = name.split(".")[-1]
         if leaf == "weight_g":
             continue  # set below from weight_v

@@ -1,0 +1,24 @@
+"""B200-native XLS-R-300M + {TopK-SAE | window-TopK | SLS} scoring path (drop-in for the reference's
+``Model(args, device).forward(x)`` behind ``main.py --is_eval``).
+
+The directory name carries the reference's name (with hyphens), so import it through the alias module at the
+repo root::
+
+    import sls_b200
+    model = sls_b200.Model(None, "cuda", cp_path=None).to("cuda").eval()
+
+Everything numerical happens in ``libslsb200.so`` (``csrc/``, C ABI in ``include/slsb200.h``); nothing here
+imports ``oracle/``.
+"""
+from ._lib import SlsbError, LIB_PATH, EXPORTED_SYMBOLS, load as load_library
+from .engine import Engine, make_config, PRECISIONS, HEAD_NONE, HEAD_SAE, HEAD_WINDOW, HEAD_SLS, PREC_FP32, PREC_BF16
+from .weights import TrunkGeometry, TrunkParams, pack_state_dict
+from .model import Model, ModelWindowTopK, ModelSLS, SSLModel, AutoEncoderTopK, getAttenF
+from .scoring import (produce_evaluation_file, score_synthetic_shard, gather_scores, write_score_file, pad_clip,
+                      SyntheticEvalSet, shard_range)
+
+__all__ = ["Model", "ModelWindowTopK", "ModelSLS", "SSLModel", "AutoEncoderTopK", "getAttenF", "Engine", "make_config",
+           "TrunkGeometry", "TrunkParams", "pack_state_dict", "produce_evaluation_file", "score_synthetic_shard",
+           "gather_scores", "write_score_file", "pad_clip", "SyntheticEvalSet", "shard_range", "SlsbError",
+           "load_library", "LIB_PATH", "EXPORTED_SYMBOLS", "PRECISIONS", "HEAD_NONE", "HEAD_SAE", "HEAD_WINDOW",
+           "HEAD_SLS", "PREC_FP32", "PREC_BF16"]

@@ -1,0 +1,285 @@
+// Multi-head self-attention over the fused qkv activations (fairseq MultiheadAttention, eval; ctor wav2vec2.py:1009-1014,
+// call :1046-1052).  q arrives pre-scaled by d^-1/2 (folded into W_q/b_q at pack time); keys >= len_b get -inf.
+//
+//   attention_tc   : bf16, tcgen05.  One CTA per (utterance, head, 128-query tile); S = Q K^T accumulates in TMEM
+//                    (128 lanes x Tp columns), four warps (thread == query row) run the fp32 softmax straight out of TMEM,
+//                    write P (bf16) into a SWIZZLE_128B K-major smem tile that aliases the dead Q/K tiles, and a second
+//                    tcgen05.mma (V as MN-major B operand, exactly the [key][d] layout TMA delivers) produces O in the
+//                    TMEM columns S vacated.  256 TMEM columns + 96 KB smem per CTA -> two CTAs per SM overlap
+//                    softmax with the other CTA's TMA/MMA.  T <= 256.
+//   attention_simt : fp32 math, fp32 or bf16 I/O, any T (key tiles of 64, online softmax).  fp32 verification mode and
+//                    the T > 256 path.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace slsb {
+namespace {
+
+constexpr int HD = 64;   // head dim
+
+// =================================================================================================
+// SIMT
+// =================================================================================================
+constexpr int SQ_ROWS = 32;      // query rows per block (4 per warp)
+constexpr int SK_TILE = 64;
+
+template <typename T>
+__global__ void __launch_bounds__(256) attn_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, int Tn, int H, const int* __restrict__ lens) {
+    extern __shared__ float simt_smem[];
+    float (*Qs)[HD] = reinterpret_cast<float (*)[HD]>(simt_smem);
+    float (*Ks)[HD + 1] = reinterpret_cast<float (*)[HD + 1]>(simt_smem + SQ_ROWS * HD);
+    float (*Vs)[HD] = reinterpret_cast<float (*)[HD]>(simt_smem + SQ_ROWS * HD + SK_TILE * (HD + 1));
+    float (*Ps)[SK_TILE][4] = reinterpret_cast<float (*)[SK_TILE][4]>(simt_smem + SQ_ROWS * HD + SK_TILE * (HD + 1) + SK_TILE * HD);
+
+    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * SQ_ROWS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int D3 = 3 * H * HD;
+    const int len = lens ? min(lens[b], Tn) : Tn;
+    const T* base = qkv + (long long)b * Tn * D3;
+
+    for (int i = threadIdx.x; i < SQ_ROWS * HD; i += 256) {
+        const int r = i / HD, d = i % HD;
+        Qs[r][d] = (q0 + r < Tn) ? to_f32<T>(base[(long long)(q0 + r) * D3 + h * HD + d]) : 0.f;
+    }
+    float m[4], l[4], o[4][2];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { m[r] = -INFINITY; l[r] = 0.f; o[r][0] = o[r][1] = 0.f; }
+
+    for (int k0 = 0; k0 < len; k0 += SK_TILE) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < SK_TILE * HD; i += 256) {
+            const int j = i / HD, d = i % HD;
+            const bool ok = k0 + j < len;
+            Ks[j][d] = ok ? to_f32<T>(base[(long long)(k0 + j) * D3 + H * HD + h * HD + d]) : 0.f;
+            Vs[j][d] = ok ? to_f32<T>(base[(long long)(k0 + j) * D3 + 2 * H * HD + h * HD + d]) : 0.f;
+        }
+        __syncthreads();
+        float s[4][2];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) s[r][0] = s[r][1] = 0.f;
+#pragma unroll 8
+        for (int d = 0; d < HD; ++d) {
+            const float ka = Ks[lane][d], kb = Ks[lane + 32][d];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float q = Qs[warp * 4 + r][d];
+                s[r][0] = fmaf(q, ka, s[r][0]);
+                s[r][1] = fmaf(q, kb, s[r][1]);
+            }
+        }
+        const bool ok0 = k0 + lane < len, ok1 = k0 + lane + 32 < len;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float s0 = ok0 ? s[r][0] : -INFINITY, s1 = ok1 ? s[r][1] : -INFINITY;
+            const float mt = warp_max(fmaxf(s0, s1));
+            const float mn = fmaxf(m[r], mt);            // finite: every tile has >= 1 valid key
+            const float corr = __expf(m[r] - mn);
+            const float p0 = ok0 ? __expf(s0 - mn) : 0.f, p1 = ok1 ? __expf(s1 - mn) : 0.f;
+            l[r] = l[r] * corr + warp_sum(p0 + p1);
+            o[r][0] *= corr; o[r][1] *= corr;
+            m[r] = mn;
+            Ps[warp][lane][r] = p0;
+            Ps[warp][lane + 32][r] = p1;
+        }
+        __syncwarp();
+#pragma unroll 4
+        for (int j = 0; j < SK_TILE; ++j) {
+            const float4 p = *reinterpret_cast<const float4*>(&Ps[warp][j][0]);
+            const float va = Vs[j][lane], vb = Vs[j][lane + 32];
+            o[0][0] = fmaf(p.x, va, o[0][0]); o[0][1] = fmaf(p.x, vb, o[0][1]);
+            o[1][0] = fmaf(p.y, va, o[1][0]); o[1][1] = fmaf(p.y, vb, o[1][1]);
+            o[2][0] = fmaf(p.z, va, o[2][0]); o[2][1] = fmaf(p.z, vb, o[2][1]);
+            o[3][0] = fmaf(p.w, va, o[3][0]); o[3][1] = fmaf(p.w, vb, o[3][1]);
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int t = q0 + warp * 4 + r;
+        if (t >= Tn) continue;
+        const float inv = 1.0f / l[r];
+        T* op = out + ((long long)b * Tn + t) * (H * HD) + h * HD;
+        op[lane] = from_f32<T>(o[r][0] * inv);
+        op[lane + 32] = from_f32<T>(o[r][1] * inv);
+    }
+}
+
+// =================================================================================================
+// tcgen05
+// =================================================================================================
+constexpr int AQ = 128;                       // query rows per CTA
+constexpr int kSmemQ = AQ * 128;              // 16 KB
+constexpr int kSmemK = 256 * 128;             // 32 KB (Tp <= 256 keys)
+constexpr int kSmemPExtra = 16 * 1024;        // P (64 KB) aliases Q + K + this
+constexpr int kSmemV = 256 * 128;             // 32 KB
+constexpr int kAttnSmem = kSmemQ + kSmemK + kSmemPExtra + kSmemV + 64 + 1024;
+
+__global__ void __launch_bounds__(160, 2)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+               bf16* __restrict__ out, int Tn, int Tp, int H, const int* __restrict__ lens) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sK = smem + kSmemQ;
+    uint8_t* sP = smem;                                    // alias: valid once S = QK^T has completed
+    uint8_t* sV = smem + kSmemQ + kSmemK + kSmemPExtra;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kSmemV);   // [0] loads, [1] S ready, [2] P ready, [3] O ready
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AQ;
+    const int len = lens ? min(lens[b], Tn) : Tn;
+    const int D = H * HD;
+
+    if (warp == 4 && lane == 0) {
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_kv);
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 128); mbar_init(&bars[3], 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc<256>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_expect_tx(&bars[0], (uint32_t)(kSmemQ + 2 * Tp * 128));
+            tma_load_2d(sQ, &tm_q, &bars[0], h * HD, b * Tn + q0);
+            tma_load_2d(sK, &tm_kv, &bars[0], D + h * HD, b * Tn);
+            tma_load_2d(sV, &tm_kv, &bars[0], 2 * D + h * HD, b * Tn);
+            mbar_wait(&bars[0], 0);
+            tc_fence_after();
+            {   // S[128 x Tp] = Q K^T
+                const uint32_t idesc = make_idesc_bf16(AQ, Tp);
+                const uint64_t da = make_smem_desc_sw128(smem_u32(sQ), 0, 1024);
+                const uint64_t db = make_smem_desc_sw128(smem_u32(sK), 0, 1024);
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k) tc_mma_f16(tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, k != 0);
+                tc_commit(&bars[1]);
+            }
+            mbar_wait(&bars[2], 0);      // P written by the softmax warps
+            tc_fence_after();
+            {   // O[128 x 64] = P V ; V is [key][d] = MN-major B
+                const uint32_t idesc = make_idesc_bf16(AQ, HD, 0, 1);
+                const int ksteps = Tp / 16;
+                for (int kk = 0; kk < ksteps; ++kk) {
+                    const uint64_t da = make_smem_desc_sw128(smem_u32(sP) + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024);
+                    const uint64_t db = make_smem_desc_sw128(smem_u32(sV) + kk * 2048, 32768, 1024);
+                    tc_mma_f16(tmem, da, db, idesc, kk != 0);
+                }
+                tc_commit(&bars[3]);
+            }
+        }
+    } else {
+        // softmax + epilogue: thread == query row == TMEM lane
+        const int r = warp * 32 + lane;
+        const uint32_t trow = tmem + (uint32_t(warp * 32) << 16);
+        mbar_wait(&bars[1], 0);
+        tc_fence_after();
+        const int nchunk = Tp / 16;
+        float mx = -INFINITY;
+        for (int c = 0; c < nchunk; ++c) {
+            uint32_t a[16];
+            tmem_ld_32x32b_x16(trow + c * 16, a);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (c * 16 + j < len) mx = fmaxf(mx, __uint_as_float(a[j]));
+        }
+        const float mxl = mx * 1.4426950408889634f;
+        float sum = 0.f;
+        for (int c = 0; c < nchunk; ++c) {
+            uint32_t a[16];
+            tmem_ld_32x32b_x16(trow + c * 16, a);
+            tmem_ld_wait();
+            float p[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                p[j] = (c * 16 + j < len) ? exp2f(fmaf(__uint_as_float(a[j]), 1.4426950408889634f, -mxl)) : 0.f;
+                sum += p[j];
+            }
+            uint8_t* blk = sP + (c >> 2) * 16384 + r * 128;
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                uint4 w;
+                w.x = pack_bf16x2(p[8 * v + 0], p[8 * v + 1]); w.y = pack_bf16x2(p[8 * v + 2], p[8 * v + 3]);
+                w.z = pack_bf16x2(p[8 * v + 4], p[8 * v + 5]); w.w = pack_bf16x2(p[8 * v + 6], p[8 * v + 7]);
+                const int c8 = (c & 3) * 2 + v;
+                *reinterpret_cast<uint4*>(blk + ((c8 ^ (r & 7)) << 4)) = w;
+            }
+        }
+        fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        tc_fence_before();
+        mbar_arrive(&bars[2]);
+        mbar_wait(&bars[3], 0);
+        tc_fence_after();
+        const float inv = 1.0f / sum;
+        const int t = q0 + r;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t a[32];
+            tmem_ld_32x32b_x32(trow + c * 32, a);
+            tmem_ld_wait();
+            if (t < Tn) {
+                uint4* op = reinterpret_cast<uint4*>(out + ((long long)b * Tn + t) * D + h * HD + c * 32);
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    uint4 w;
+                    w.x = pack_bf16x2(__uint_as_float(a[8 * v + 0]) * inv, __uint_as_float(a[8 * v + 1]) * inv);
+                    w.y = pack_bf16x2(__uint_as_float(a[8 * v + 2]) * inv, __uint_as_float(a[8 * v + 3]) * inv);
+                    w.z = pack_bf16x2(__uint_as_float(a[8 * v + 4]) * inv, __uint_as_float(a[8 * v + 5]) * inv);
+                    w.w = pack_bf16x2(__uint_as_float(a[8 * v + 6]) * inv, __uint_as_float(a[8 * v + 7]) * inv);
+                    op[v] = w;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc<256>(tmem);
+    }
+}
+
+}  // namespace
+
+int attention_simt(const void* qkv, void* out, int io_bf16, int B, int T, int H, const int* lens, cudaStream_t stream) {
+    dim3 grid((T + SQ_ROWS - 1) / SQ_ROWS, H, B);
+    constexpr int kSmem = (SQ_ROWS * HD + SK_TILE * (HD + 1) + SK_TILE * HD + 8 * SK_TILE * 4) * (int)sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        SLSB_CUDA_CHECK(cudaFuncSetAttribute(attn_simt_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        SLSB_CUDA_CHECK(cudaFuncSetAttribute(attn_simt_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        configured = true;
+    }
+    if (io_bf16) attn_simt_kernel<bf16><<<grid, 256, kSmem, stream>>>(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), T, H, lens);
+    else attn_simt_kernel<float><<<grid, 256, kSmem, stream>>>(static_cast<const float*>(qkv), static_cast<float*>(out), T, H, lens);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int attention_tc(const void* qkv, void* out, int B, int T, int H, const int* lens, int num_sms, cudaStream_t stream) {
+    (void)num_sms;
+    const int Tp = (T + 15) / 16 * 16;
+    if (Tp > 256) { set_error("attention_tc: T=%d > 256 (use attention_simt)", T); return -1; }
+    const int D = H * HD;
+    CUtensorMap tq, tkv;
+    uint64_t dims[2] = {(uint64_t)(3 * D), (uint64_t)B * T};
+    uint64_t strides[1] = {(uint64_t)(3 * D) * 2};
+    uint32_t boxq[2] = {HD, AQ}, boxkv[2] = {HD, (uint32_t)Tp};
+    if (encode_tmap_bf16(&tq, qkv, 2, dims, strides, boxq)) return -1;
+    if (encode_tmap_bf16(&tkv, qkv, 2, dims, strides, boxkv)) return -1;
+    static bool configured = false;
+    if (!configured) {
+        SLSB_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+        configured = true;
+    }
+    dim3 grid((T + AQ - 1) / AQ, H, B);
+    attn_tc_kernel<<<grid, 160, kAttnSmem, stream>>>(tq, tkv, static_cast<bf16*>(out), T, Tp, H, lens);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace slsb

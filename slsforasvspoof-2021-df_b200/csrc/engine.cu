@@ -1,0 +1,767 @@
+// Engine: weight arena, workspace, the forward schedule of the scoring path, and the C ABI (include/slsb200.h).
+// Host code only orchestrates launches on the caller's stream; it never synchronises inside slsb_forward.
+#include "common.cuh"
+#include "kernels.h"
+#include "../../include/slsb200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace slsb {
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// tensor-map encode via the driver entry point (resolved lazily; no libcuda link dependency)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+static int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
+                       const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
+    EncodeTiledFn fn = get_encode();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return -1; }
+    cuuint64_t d[5], s[4];
+    cuuint32_t b[5], es[5];
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+    CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): rank=%d dims=[%llu,%llu,%llu,%llu] stride0=%llu box=[%u,%u,%u,%u] base=%p", (int)r, rank,
+                  (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0), (unsigned long long)(rank > 2 ? dims[2] : 0),
+                  (unsigned long long)(rank > 3 ? dims[3] : 0), (unsigned long long)(rank > 1 ? strides_bytes[0] : 0), box[0], rank > 1 ? box[1] : 0,
+                  rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, base);
+        return -1;
+    }
+    return 0;
+}
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, bool sw) {
+    return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, sw);
+}
+int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, bool sw) {
+    return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box, sw);
+}
+
+// small elementwise helper kernels private to the engine
+__global__ void center_rows_kernel(const float* __restrict__ x, const float* __restrict__ sub, float* __restrict__ of, bf16* __restrict__ ob, long long n, int C) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = x[i] - sub[i % C];
+    if (of) of[i] = v;
+    if (ob) ob[i] = __float2bfloat16_rn(v);
+}
+__global__ void bf16_to_f32_kernel(const bf16* __restrict__ in, float* __restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __bfloat162float(in[i]);
+}
+
+}  // namespace slsb
+
+using namespace slsb;
+
+// ------------------------------------------------------------------------------------------------
+// engine
+// ------------------------------------------------------------------------------------------------
+struct Weight {
+    int64_t numel = 0;
+    float* f32 = nullptr;
+    bf16* b16 = nullptr;
+    bool gemm = false;   // gets a bf16 copy
+    bool set = false;
+};
+
+struct Buf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t need) {
+        if (need <= bytes) return 0;
+        if (p) { cudaDeviceSynchronize(); cudaFree(p); p = nullptr; bytes = 0; }
+        need = (need + (size_t(4) << 20)) & ~size_t(255);      // slack: TMA boxes may touch one partial tile past the end
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e)); return -1; }
+        cudaMemset(p, 0, need);
+        bytes = need;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct slsb_engine {
+    slsb_config cfg{};
+    int device = 0, num_sms = 148;
+    std::map<std::string, Weight> w;
+    bool finalized = false;
+    int64_t launches = 0;
+    // workspace
+    Buf fe[2], lnbuf, qkv, attn, ffn, xmid, xfinal, xc, xpad, acts, encoded, sums, votes, thr, cut, thr_w, cut_w, pooled, logprob,
+        sls_w, sls_in, sls_part, zeros, scratch, flens, wav_stage, lens_stage, score_stage, recon, tmp_bf16;
+    std::vector<Buf> X;
+    // last call
+    int B = 0, S = 0, T = 0, prec = 0, head = 0;
+    bool have_lens = false, have_acts = false, have_sel = false;
+    int sls_ks = 17, sls_kp = 0;
+    // optional per-launch CUDA-event timing of the tensor-core kernels (bench.py roofline)
+    bool profiling = false;
+    struct ProfRec { cudaEvent_t a, b; double flops; int kind; };
+    std::vector<ProfRec> prof;
+};
+
+enum ProfKind { PK_ENC_GEMM = 0, PK_CONV_GEMM = 1, PK_POS_GEMM = 2, PK_OTHER_GEMM = 3, PK_ATTN = 4, PK_COUNT = 5 };
+
+struct ProfScope {
+    slsb_engine* e; cudaStream_t st; int idx = -1;
+    ProfScope(slsb_engine* e_, cudaStream_t st_, int kind, double flops) : e(e_), st(st_) {
+        if (!e->profiling) return;
+        slsb_engine::ProfRec r{};
+        cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+        r.flops = flops; r.kind = kind;
+        cudaEventRecord(r.a, st);
+        e->prof.push_back(r);
+        idx = (int)e->prof.size() - 1;
+    }
+    ~ProfScope() { if (idx >= 0) cudaEventRecord(e->prof[idx].b, st); }
+};
+
+static int conv_len(const slsb_config& c, int n, int upto = -1) {
+    const int last = upto < 0 ? c.n_conv : upto;
+    for (int i = 0; i < last; ++i) n = (n - c.conv_kernel[i]) / c.conv_stride[i] + 1;
+    return n;
+}
+
+static void add_weight(slsb_engine* e, const std::string& name, int64_t numel, bool gemm = false) {
+    Weight wt;
+    wt.numel = numel;
+    wt.gemm = gemm;
+    e->w[name] = wt;
+}
+
+static int build_weight_table(slsb_engine* e) {
+    const slsb_config& c = e->cfg;
+    const int C = c.conv_dim, D = c.embed_dim, F = c.ffn_dim;
+    add_weight(e, "conv0.w", (int64_t)C * c.conv_kernel[0]);
+    for (int i = 0; i < c.n_conv; ++i) {
+        const std::string p = "conv" + std::to_string(i);
+        if (i > 0) add_weight(e, p + ".w", (int64_t)C * c.conv_kernel[i] * C, true);
+        add_weight(e, p + ".b", C);
+        add_weight(e, p + ".ln.w", C);
+        add_weight(e, p + ".ln.b", C);
+    }
+    add_weight(e, "feat_ln.w", C); add_weight(e, "feat_ln.b", C);
+    add_weight(e, "proj.w", (int64_t)D * C, true); add_weight(e, "proj.b", D);
+    add_weight(e, "pos.w", (int64_t)D * c.pos_kernel * (D / c.pos_groups), true); add_weight(e, "pos.b", D);
+    for (int l = 0; l < c.n_layers; ++l) {
+        const std::string p = "L" + std::to_string(l);
+        add_weight(e, p + ".ln1.w", D); add_weight(e, p + ".ln1.b", D);
+        add_weight(e, p + ".qkv.w", (int64_t)3 * D * D, true); add_weight(e, p + ".qkv.b", 3 * D);
+        add_weight(e, p + ".out.w", (int64_t)D * D, true); add_weight(e, p + ".out.b", D);
+        add_weight(e, p + ".ln2.w", D); add_weight(e, p + ".ln2.b", D);
+        add_weight(e, p + ".fc1.w", (int64_t)F * D, true); add_weight(e, p + ".fc1.b", F);
+        add_weight(e, p + ".fc2.w", (int64_t)D * F, true); add_weight(e, p + ".fc2.b", D);
+    }
+    add_weight(e, "enc_ln.w", D); add_weight(e, "enc_ln.b", D);
+    if (c.sae_dict > 0) {
+        add_weight(e, "sae.enc.w", (int64_t)c.sae_dict * D, true); add_weight(e, "sae.enc.b", c.sae_dict);
+        add_weight(e, "sae.b_dec", D);
+        add_weight(e, "sae.dec.w", (int64_t)D * c.sae_dict, true);
+    }
+    if (c.cls_in > 0) {
+        add_weight(e, "cls.ln.w", c.cls_in); add_weight(e, "cls.ln.b", c.cls_in);
+        add_weight(e, "cls.fc1.w", (int64_t)c.cls_hidden * c.cls_in); add_weight(e, "cls.fc1.b", c.cls_hidden);
+        add_weight(e, "cls.fc2.w", (int64_t)2 * c.cls_hidden); add_weight(e, "cls.fc2.b", 2);
+    }
+    if (c.sls_frames > 0) {
+        const int kraw = (c.sls_frames / 3) * (D / 3);
+        const int q = 16 * e->sls_ks;
+        e->sls_kp = (kraw + q - 1) / q * q;
+        add_weight(e, "sls.fc0.w", D); add_weight(e, "sls.fc0.b", 1);
+        add_weight(e, "sls.bn", 4);
+        add_weight(e, "sls.fc1.w", (int64_t)c.sls_hidden * e->sls_kp); add_weight(e, "sls.fc1.b", c.sls_hidden);
+        add_weight(e, "sls.fc3.w", (int64_t)2 * c.sls_hidden); add_weight(e, "sls.fc3.b", 2);
+    }
+    for (auto& kv : e->w) {
+        cudaError_t err = cudaMalloc(&kv.second.f32, kv.second.numel * sizeof(float));
+        if (err == cudaSuccess && kv.second.gemm) err = cudaMalloc(&kv.second.b16, kv.second.numel * sizeof(bf16));
+        if (err != cudaSuccess) { set_error("weight arena cudaMalloc failed for %s: %s", kv.first.c_str(), cudaGetErrorString(err)); return -1; }
+    }
+    return 0;
+}
+
+#define W32(name) (e->w.at(name).f32)
+#define W16(name) (e->w.at(name).b16)
+#define LAUNCH(call) do { ++e->launches; if ((call) != 0) return -1; } while (0)
+
+// C = act(A W^T + b) (+res): fp32 path -> CUDA cores, bf16 path -> tcgen05
+static int linear(slsb_engine* e, bool bf, const void* A, long long lda, const std::string& wname, int N, int K, long long M,
+                  const float* bias, const float* residual, long long ldr, void* out, long long ldc, int out_bf16, int act, cudaStream_t st,
+                  int kind = PK_OTHER_GEMM) {
+    ProfScope ps(e, st, kind, 2.0 * (double)M * N * K);
+    if (bf) {
+        TcGemmArgs g;
+        g.a_mode = A_PLAIN; g.A = A; g.lda = lda; g.W = W16(wname); g.ldw = K; g.M = (int)M; g.N = N; g.K = K; g.batches = 1;
+        g.out = out; g.ldc = ldc; g.out_bf16 = out_bf16; g.bias = bias; g.residual = residual; g.ldr = ldr; g.act = act;
+        LAUNCH(tc_gemm(g, e->num_sms, st));
+    } else {
+        SimtGemmArgs g;
+        g.A = A; g.lda = lda; g.W = W32(wname); g.ldw = K; g.M = (int)M; g.N = N; g.K = K; g.batches = 1;
+        g.out = out; g.ldc = ldc; g.bias = bias; g.residual = residual; g.ldr = ldr; g.act = act; g.exact_gelu = 1;
+        LAUNCH(simt_gemm(g, st));
+    }
+    return 0;
+}
+
+static int conv_layer(slsb_engine* e, bool bf, const void* x, const void* Wp, const float* bias, void* out, int B, int Lin, int C, int N,
+                      int k, int s, cudaStream_t st) {
+    const int Lout = (Lin - k) / s + 1;
+    ProfScope ps(e, st, PK_CONV_GEMM, 2.0 * (double)B * Lout * N * k * C);
+    if (bf) {
+        TcGemmArgs g;
+        g.a_mode = A_CONV; g.A = x; g.W = Wp; g.ldw = (long long)k * C; g.M = Lout; g.N = N; g.K = k * C; g.batches = B;
+        g.conv_cin = C; g.conv_stride = s; g.conv_lin = Lin;
+        g.out = out; g.ldc = N; g.out_batch_stride = (long long)Lout * N; g.out_bf16 = 1; g.bias = bias; g.act = ACT_NONE;
+        LAUNCH(tc_gemm(g, e->num_sms, st));
+    } else {
+        SimtGemmArgs g;
+        g.A = x; g.lda = (long long)s * C; g.a_batch_stride = (long long)Lin * C; g.W = static_cast<const float*>(Wp); g.ldw = (long long)k * C;
+        g.M = Lout; g.N = N; g.K = k * C; g.batches = B;
+        g.out = out; g.ldc = N; g.out_batch_stride = (long long)Lout * N; g.bias = bias; g.act = ACT_NONE;
+        LAUNCH(simt_gemm(g, st));
+    }
+    return 0;
+}
+
+// x_out = x + gelu(pos_conv(x) + b)  (wav2vec2.py:915-917); xpad is scratch [B, T + K, D]
+static int pos_conv(slsb_engine* e, bool bf, const float* x, const void* Wp, const float* bias, float* out, void* xpad, int B, int T, int D,
+                    int K, int groups, const int* flens, cudaStream_t st) {
+    const int Tp = T + K, gw = D / groups;
+    LAUNCH(pad_frames(x, xpad, bf ? 1 : 0, B, T, D, K / 2, Tp, flens, st));
+    ProfScope ps(e, st, PK_POS_GEMM, 2.0 * (double)B * T * D * K * gw);
+    if (bf) {
+        if (gw != 64) { set_error("pos_conv (tcgen05): group width %d != 64", gw); return -1; }
+        TcGemmArgs g;
+        g.a_mode = A_POS; g.A = xpad; g.W = Wp; g.ldw = (long long)K * gw; g.M = T; g.N = D; g.K = K * gw; g.batches = B;
+        g.pos_dim = D; g.pos_tp = Tp;
+        g.out = out; g.ldc = D; g.out_batch_stride = (long long)T * D; g.out_bf16 = 0; g.bias = bias;
+        g.residual = x; g.ldr = D; g.res_batch_stride = (long long)T * D; g.act = ACT_GELU;
+        LAUNCH(tc_gemm(g, e->num_sms, st));
+    } else {
+        SimtGemmArgs g;
+        g.A = xpad; g.lda = D; g.a_batch_stride = (long long)Tp * D; g.a_kinner = gw; g.a_kouter = D;
+        g.W = static_cast<const float*>(Wp); g.ldw = (long long)K * gw; g.w_group_stride = (long long)gw * K * gw;
+        g.groups = groups; g.a_group_offset = gw; g.n_per_group = gw;
+        g.M = T; g.N = gw; g.K = K * gw; g.batches = B;
+        g.out = out; g.ldc = D; g.out_batch_stride = (long long)T * D; g.bias = bias;
+        g.residual = x; g.ldr = D; g.res_batch_stride = (long long)T * D; g.act = ACT_GELU; g.exact_gelu = 1;
+        LAUNCH(simt_gemm(g, st));
+    }
+    return 0;
+}
+
+static int attention(slsb_engine* e, bool bf, const void* qkv, void* out, int B, int T, int H, const int* flens, cudaStream_t st) {
+    ProfScope ps(e, st, PK_ATTN, 4.0 * (double)B * H * T * T * 64);
+    int impl = e->cfg.attn_impl;
+    if (impl == SLSB_ATTN_AUTO) impl = (bf && T <= 256) ? SLSB_ATTN_TC : SLSB_ATTN_SIMT;
+    if (impl == SLSB_ATTN_TC && bf) LAUNCH(attention_tc(qkv, out, B, T, H, flens, e->num_sms, st));
+    else LAUNCH(attention_simt(qkv, out, bf ? 1 : 0, B, T, H, flens, st));
+    return 0;
+}
+
+static int check_ready(slsb_engine* e) {
+    if (!e) { set_error("null engine"); return -1; }
+    if (!e->finalized) { set_error("weights not finalized: call slsb_set_weight for every tensor, then slsb_finalize_weights"); return -1; }
+    return 0;
+}
+
+// ---- the trunk: wav -> X[0..n_layers], xfinal (+ xc = xfinal - b_dec) ---------------------------
+static int run_trunk(slsb_engine* e, const float* wav, const int* slens, int B, int S, int prec, bool want_xc, cudaStream_t st) {
+    const slsb_config& c = e->cfg;
+    const bool bf = prec == SLSB_PREC_BF16;
+    const size_t es = bf ? 2 : 4;
+    const int C = c.conv_dim, D = c.embed_dim, F = c.ffn_dim, H = c.n_heads;
+    if (B <= 0 || S <= 0) { set_error("empty batch (B=%d, S=%d)", B, S); return -1; }
+    std::vector<int> L(c.n_conv);
+    for (int i = 0; i < c.n_conv; ++i) L[i] = conv_len(c, S, i + 1);
+    const int T = L[c.n_conv - 1];
+    if (T < 1) { set_error("clip too short: %d samples give %d frames", S, T); return -1; }
+    const long long M = (long long)B * T;
+    const int Tp = T + c.pos_kernel;
+
+    if (e->fe[0].reserve((size_t)B * L[0] * C * es)) return -1;
+    if (e->fe[1].reserve((size_t)B * (c.n_conv > 1 ? L[1] : 1) * C * es)) return -1;
+    if (e->lnbuf.reserve((size_t)M * D * es) || e->qkv.reserve((size_t)M * 3 * D * es) || e->attn.reserve((size_t)M * D * es) ||
+        e->ffn.reserve((size_t)M * F * es) || e->xmid.reserve((size_t)M * D * 4) || e->xfinal.reserve((size_t)M * D * 4) ||
+        e->xc.reserve((size_t)M * D * es) || e->xpad.reserve((size_t)B * Tp * D * es) || e->flens.reserve((size_t)B * 4)) return -1;
+    if ((int)e->X.size() < c.n_layers + 1) e->X.resize(c.n_layers + 1);
+    for (int l = 0; l <= c.n_layers; ++l) if (e->X[l].reserve((size_t)M * D * 4)) return -1;
+
+    int* flens = nullptr;
+    if (slens) {
+        flens = e->flens.as<int>();
+        LAUNCH(frame_lengths(slens, flens, B, c.n_conv, c.conv_kernel, c.conv_stride, st));
+    }
+    e->B = B; e->S = S; e->T = T; e->prec = prec; e->have_lens = slens != nullptr; e->have_acts = false; e->have_sel = false;
+
+    // 1. feature extractor (wav2vec2.py:843-851)
+    LAUNCH(conv0_ln_gelu(wav, B, S, L[0], c.conv_kernel[0], c.conv_stride[0], W32("conv0.w"), W32("conv0.b"), W32("conv0.ln.w"),
+                         W32("conv0.ln.b"), e->fe[0].p, bf ? 1 : 0, C, !bf, st));
+    for (int i = 1; i < c.n_conv; ++i) {
+        const std::string p = "conv" + std::to_string(i);
+        void* in = e->fe[(i - 1) & 1].p;
+        void* out = e->fe[i & 1].p;
+        if (conv_layer(e, bf, in, bf ? (const void*)W16(p + ".w") : (const void*)W32(p + ".w"), W32(p + ".b"), out, B, L[i - 1], C, C,
+                       c.conv_kernel[i], c.conv_stride[i], st)) return -1;
+        LnArgs a;
+        a.in = out; a.in_bf16 = bf; a.out = out; a.out_bf16 = bf; a.w = W32(p + ".ln.w"); a.b = W32(p + ".ln.b");
+        a.rows = (long long)B * L[i]; a.C = C; a.gelu = 1; a.exact_gelu = !bf;
+        LAUNCH(layernorm(a, st));
+    }
+    // 2. LayerNorm(512) + post_extract_proj (wav2vec2.py:563-564, :595-596)
+    {
+        LnArgs a;
+        a.in = e->fe[(c.n_conv - 1) & 1].p; a.in_bf16 = bf; a.out = e->lnbuf.p; a.out_bf16 = bf; a.w = W32("feat_ln.w"); a.b = W32("feat_ln.b");
+        a.rows = M; a.C = C;
+        LAUNCH(layernorm(a, st));
+        if (linear(e, bf, e->lnbuf.p, C, "proj.w", D, C, M, W32("proj.b"), nullptr, 0, e->xmid.p, D, 0, ACT_NONE, st)) return -1;
+    }
+    // 3. positional conv + GELU + residual (wav2vec2.py:910-917)
+    if (pos_conv(e, bf, e->xmid.as<float>(), bf ? (const void*)W16("pos.w") : (const void*)W32("pos.w"), W32("pos.b"), e->X[0].as<float>(),
+                 e->xpad.p, B, T, D, c.pos_kernel, c.pos_groups, flens, st)) return -1;
+    // 4. transformer layers, pre-LN (wav2vec2.py:1044-1062)
+    for (int l = 0; l < c.n_layers; ++l) {
+        const std::string p = "L" + std::to_string(l);
+        float* xin = e->X[l].as<float>();
+        float* xout = e->X[l + 1].as<float>();
+        LnArgs a;
+        a.in = xin; a.out = e->lnbuf.p; a.out_bf16 = bf; a.w = W32(p + ".ln1.w"); a.b = W32(p + ".ln1.b"); a.rows = M; a.C = D;
+        LAUNCH(layernorm(a, st));
+        if (linear(e, bf, e->lnbuf.p, D, p + ".qkv.w", 3 * D, D, M, W32(p + ".qkv.b"), nullptr, 0, e->qkv.p, 3 * D, bf, ACT_NONE, st, PK_ENC_GEMM)) return -1;
+        if (attention(e, bf, e->qkv.p, e->attn.p, B, T, H, flens, st)) return -1;
+        if (linear(e, bf, e->attn.p, D, p + ".out.w", D, D, M, W32(p + ".out.b"), xin, D, e->xmid.p, D, 0, ACT_NONE, st, PK_ENC_GEMM)) return -1;
+        LnArgs a2;
+        a2.in = e->xmid.p; a2.out = e->lnbuf.p; a2.out_bf16 = bf; a2.w = W32(p + ".ln2.w"); a2.b = W32(p + ".ln2.b"); a2.rows = M; a2.C = D;
+        LAUNCH(layernorm(a2, st));
+        if (linear(e, bf, e->lnbuf.p, D, p + ".fc1.w", F, D, M, W32(p + ".fc1.b"), nullptr, 0, e->ffn.p, F, bf, ACT_GELU, st, PK_ENC_GEMM)) return -1;
+        if (linear(e, bf, e->ffn.p, F, p + ".fc2.w", D, F, M, W32(p + ".fc2.b"), e->xmid.as<float>(), D, xout, D, 0, ACT_NONE, st, PK_ENC_GEMM)) return -1;
+    }
+    // 5. final LayerNorm on x only (wav2vec2.py:905-906); xc = x - b_dec feeds the SAE encoder (model.py:70)
+    {
+        LnArgs a;
+        a.in = e->X[c.n_layers].p; a.out = e->xfinal.p; a.w = W32("enc_ln.w"); a.b = W32("enc_ln.b"); a.rows = M; a.C = D;
+        if (want_xc && c.sae_dict > 0) { a.out2 = e->xc.p; a.out2_bf16 = bf; a.sub = W32("sae.b_dec"); }
+        LAUNCH(layernorm(a, st));
+    }
+    return 0;
+}
+
+// acts = relu(xc W_enc^T + b_enc) [rows, dict]   (model.py:70)
+static int sae_acts(slsb_engine* e, bool bf, const void* xc, long long rows, cudaStream_t st) {
+    const slsb_config& c = e->cfg;
+    if (e->acts.reserve((size_t)rows * c.sae_dict * 4)) return -1;
+    return linear(e, bf, xc, c.embed_dim, "sae.enc.w", c.sae_dict, c.embed_dim, rows, W32("sae.enc.b"), nullptr, 0, e->acts.p, c.sae_dict, 0, ACT_RELU, st);
+}
+
+// selection pass: fills thr/cut (and votes for the window variant); `sel` is what the keep-rule looks at
+static int sae_select(slsb_engine* e, long long rows, int T, int window, const float** sel_out, cudaStream_t st) {
+    const slsb_config& c = e->cfg;
+    const int Dd = c.sae_dict, k = c.sae_k;
+    if (e->thr.reserve((size_t)rows * 4) || e->cut.reserve((size_t)rows * 4)) return -1;
+    const float* acts = e->acts.as<float>();
+    if (window <= 1) {
+        LAUNCH(topk_threshold(acts, rows, Dd, k, e->thr.as<float>(), e->cut.as<int>(), st));
+        *sel_out = acts;
+        return 0;
+    }
+    const int stride = window / 2 > 0 ? window / 2 : 1;
+    if (rows % T != 0) { set_error("window top-k: rows=%lld is not a multiple of T=%d", rows, T); return -1; }
+    if (T < window || stride >= T) { set_error("window top-k: T=%d shorter than window %d", T, window); return -1; }
+    const int B = (int)(rows / T);
+    const int nw = (T - window) / stride + 1;                                  // model_window_topk.py:141
+    if (e->sums.reserve((size_t)B * nw * Dd * 4) || e->votes.reserve((size_t)rows * Dd * 4) ||
+        e->thr_w.reserve((size_t)B * nw * 4) || e->cut_w.reserve((size_t)B * nw * 4)) return -1;
+    LAUNCH(window_sums(acts, e->sums.as<float>(), B, T, Dd, window, stride, nw, st));
+    LAUNCH(topk_threshold(e->sums.as<float>(), (long long)B * nw, Dd, k, e->thr_w.as<float>(), e->cut_w.as<int>(), st));
+    LAUNCH(window_votes(acts, e->sums.as<float>(), e->thr_w.as<float>(), e->cut_w.as<int>(), e->votes.as<float>(), B, T, Dd, window, stride, nw, st));
+    LAUNCH(topk_threshold(e->votes.as<float>(), rows, Dd, k, e->thr.as<float>(), e->cut.as<int>(), st));
+    *sel_out = e->votes.as<float>();
+    return 0;
+}
+
+static int run_head(slsb_engine* e, int head, int prec, float* logprob, cudaStream_t st) {
+    const slsb_config& c = e->cfg;
+    const bool bf = prec == SLSB_PREC_BF16;
+    const int B = e->B, T = e->T, D = c.embed_dim;
+    const long long M = (long long)B * T;
+    const int* flens = e->have_lens ? e->flens.as<int>() : nullptr;
+    if (head == SLSB_HEAD_SAE || head == SLSB_HEAD_WINDOW) {
+        if (c.cls_in <= 0) { set_error("engine was created without classifier weights"); return -1; }
+        if (e->pooled.reserve((size_t)B * c.cls_in * 4)) return -1;
+        if (c.sae_dict > 0) {
+            const int window = head == SLSB_HEAD_WINDOW ? c.sae_window : 1;
+            if (window > 1 && flens) { set_error("window top-k with per-utterance lengths is not defined by the reference"); return -1; }
+            if (sae_acts(e, bf, e->xc.p, M, st)) return -1;
+            const float* sel = nullptr;
+            if (sae_select(e, M, T, window, &sel, st)) return -1;
+            e->have_acts = true; e->have_sel = true;
+            if (c.cls_in == c.sae_dict) {
+                LAUNCH(votes_mean_pool(e->acts.as<float>(), sel, e->thr.as<float>(), e->cut.as<int>(), e->pooled.as<float>(), B, T, c.sae_dict, flens, st));
+            } else {
+                // use_sparse_features=False: classifier sees the reconstruction (model.py:231-233)
+                if (e->encoded.reserve((size_t)M * c.sae_dict * 4) || e->recon.reserve((size_t)M * D * 4)) return -1;
+                LAUNCH(votes_densify(e->acts.as<float>(), sel, e->thr.as<float>(), e->cut.as<int>(), e->encoded.as<float>(), M, c.sae_dict, st));
+                const void* A = e->encoded.p;
+                if (bf) {
+                    if (e->tmp_bf16.reserve((size_t)M * c.sae_dict * 2)) return -1;
+                    LAUNCH(convert_f32_to_bf16(e->encoded.as<float>(), e->tmp_bf16.p, M * c.sae_dict, st));
+                    A = e->tmp_bf16.p;
+                }
+                if (linear(e, bf, A, c.sae_dict, "sae.dec.w", D, c.sae_dict, M, W32("sae.b_dec"), nullptr, 0, e->recon.p, D, 0, ACT_NONE, st)) return -1;
+                LAUNCH(mean_pool_frames(e->recon.as<float>(), e->pooled.as<float>(), B, T, D, flens, st));
+            }
+        } else {
+            LAUNCH(mean_pool_frames(e->xfinal.as<float>(), e->pooled.as<float>(), B, T, D, flens, st));   // use_sae=False
+        }
+        LAUNCH(classifier_head(e->pooled.as<float>(), B, c.cls_in, c.cls_hidden, W32("cls.ln.w"), W32("cls.ln.b"), W32("cls.fc1.w"), W32("cls.fc1.b"),
+                               W32("cls.fc2.w"), W32("cls.fc2.b"), logprob, st));
+        return 0;
+    }
+    if (head == SLSB_HEAD_SLS) {
+        if (c.sls_frames <= 0) { set_error("engine was created without SLS weights"); return -1; }
+        if (T != c.sls_frames) { set_error("SLS head: fc1 is sized for %d frames, got %d", c.sls_frames, T); return -1; }
+        if (flens) { set_error("SLS head with per-utterance lengths is not defined by the reference"); return -1; }
+        const int KS = e->sls_ks, Kp = e->sls_kp, Hs = c.sls_hidden;
+        if (e->sls_w.reserve((size_t)B * c.n_layers * 4) || e->sls_in.reserve((size_t)B * Kp * 4) ||
+            e->sls_part.reserve((size_t)B * KS * Hs * 4) || e->zeros.reserve((size_t)KS * Hs * 4)) return -1;
+        std::vector<const float*> layers(c.n_layers);
+        for (int l = 0; l < c.n_layers; ++l) layers[l] = e->X[l + 1].as<float>();
+        LAUNCH(sls_layer_weights(layers.data(), c.n_layers, B, T, D, W32("sls.fc0.w"), W32("sls.fc0.b"), e->sls_w.as<float>(), nullptr, st));
+        LAUNCH(sls_fuse_pool(layers.data(), c.n_layers, e->sls_w.as<float>(), B, T, D, W32("sls.bn"), 1e-5f, e->sls_in.as<float>(), Kp, st));
+        SimtGemmArgs g;      // split-K: group ks handles columns [ks*Kp/KS, (ks+1)*Kp/KS) of both operands
+        g.A = e->sls_in.p; g.lda = Kp; g.a_group_offset = Kp / KS; g.W = W32("sls.fc1.w"); g.ldw = Kp; g.w_group_stride = Kp / KS;
+        g.groups = KS; g.n_per_group = Hs; g.M = B; g.N = Hs; g.K = Kp / KS; g.batches = 1;
+        g.out = e->sls_part.p; g.ldc = (long long)KS * Hs; g.bias = e->zeros.as<float>(); g.act = ACT_NONE;
+        LAUNCH(simt_gemm(g, st));
+        LAUNCH(sls_tail(e->sls_part.as<float>(), KS, B, Hs, W32("sls.fc1.b"), W32("sls.fc3.w"), W32("sls.fc3.b"), logprob, st));
+        return 0;
+    }
+    set_error("unknown head %d", head);
+    return -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int slsb_abi_version(void) { return SLSB_ABI_VERSION; }
+const char* slsb_last_error(void) { return g_err; }
+
+int slsb_create(const slsb_config* cfg, int device, slsb_engine** out) {
+    if (!cfg || !out) { set_error("slsb_create: null argument"); return -1; }
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { set_error("slsb_create: no CUDA device (this library has no CPU fallback)"); return -2; }
+    if (device < 0 || device >= n) { set_error("slsb_create: device %d out of range (%d devices)", device, n); return -1; }
+    cudaDeviceProp prop;
+    SLSB_CUDA_CHECK(cudaSetDevice(device));
+    SLSB_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) { set_error("slsb_create: device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor); return -2; }
+    if (cfg->n_conv < 1 || cfg->n_conv > 8 || cfg->embed_dim % 128 || cfg->embed_dim / cfg->n_heads != 64 || cfg->conv_dim != 512 ||
+        cfg->embed_dim / cfg->pos_groups != 64 || cfg->ffn_dim % 256 || cfg->n_layers < 1 || cfg->n_layers > 31) {
+        set_error("slsb_create: unsupported geometry (need conv_dim 512, head dim 64, pos group width 64, ffn %% 256 == 0, <= 31 layers)");
+        return -1;
+    }
+    slsb_engine* e = new slsb_engine();
+    e->cfg = *cfg;
+    e->device = device;
+    e->num_sms = prop.multiProcessorCount;
+    if (build_weight_table(e)) { slsb_destroy(e); return -1; }
+    *out = e;
+    return 0;
+}
+
+int slsb_destroy(slsb_engine* e) {
+    if (!e) return 0;
+    cudaDeviceSynchronize();
+    for (auto& kv : e->w) { if (kv.second.f32) cudaFree(kv.second.f32); if (kv.second.b16) cudaFree(kv.second.b16); }
+    Buf* bufs[] = {&e->fe[0], &e->fe[1], &e->lnbuf, &e->qkv, &e->attn, &e->ffn, &e->xmid, &e->xfinal, &e->xc, &e->xpad, &e->acts, &e->encoded,
+                   &e->sums, &e->votes, &e->thr, &e->cut, &e->thr_w, &e->cut_w, &e->pooled, &e->logprob, &e->sls_w, &e->sls_in, &e->sls_part,
+                   &e->zeros, &e->scratch, &e->flens, &e->wav_stage, &e->lens_stage, &e->score_stage, &e->recon, &e->tmp_bf16};
+    for (Buf* b : bufs) b->release();
+    for (auto& b : e->X) b.release();
+    delete e;
+    return 0;
+}
+
+int64_t slsb_weight_numel(slsb_engine* e, const char* name) {
+    if (!e || !name) return -1;
+    auto it = e->w.find(name);
+    return it == e->w.end() ? -1 : it->second.numel;
+}
+
+int slsb_set_weight(slsb_engine* e, const char* name, const float* src, int64_t numel, void* stream) {
+    if (!e || !name || !src) { set_error("slsb_set_weight: null argument"); return -1; }
+    auto it = e->w.find(name);
+    if (it == e->w.end()) { set_error("slsb_set_weight: unknown tensor '%s'", name); return -1; }
+    if (it->second.numel != numel) { set_error("slsb_set_weight: '%s' expects %lld elements, got %lld", name, (long long)it->second.numel, (long long)numel); return -1; }
+    SLSB_CUDA_CHECK(cudaMemcpyAsync(it->second.f32, src, numel * sizeof(float), cudaMemcpyDefault, static_cast<cudaStream_t>(stream)));
+    it->second.set = true;
+    e->finalized = false;
+    return 0;
+}
+
+int slsb_finalize_weights(slsb_engine* e, void* stream) {
+    if (!e) { set_error("null engine"); return -1; }
+    for (auto& kv : e->w) {
+        if (!kv.second.set) { set_error("slsb_finalize_weights: tensor '%s' was never set", kv.first.c_str()); return -1; }
+        if (kv.second.gemm) LAUNCH(convert_f32_to_bf16(kv.second.f32, kv.second.b16, kv.second.numel, static_cast<cudaStream_t>(stream)));
+    }
+    e->finalized = true;
+    return 0;
+}
+
+int slsb_frames_for_samples(const slsb_engine* e, int samples) { return e ? conv_len(e->cfg, samples) : -1; }
+int64_t slsb_launch_count(const slsb_engine* e) { return e ? e->launches : -1; }
+
+int slsb_forward(slsb_engine* e, const float* wav_dev, const int32_t* sample_lens_dev, int B, int S, int head, int precision,
+                 float* logprob_dev, void* stream) {
+    if (check_ready(e)) return -1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (run_trunk(e, wav_dev, sample_lens_dev, B, S, precision, head == SLSB_HEAD_SAE || head == SLSB_HEAD_WINDOW, st)) return -1;
+    e->head = head;
+    if (head == SLSB_HEAD_NONE) return 0;
+    if (!logprob_dev) { set_error("slsb_forward: logprob_dev is null"); return -1; }
+    return run_head(e, head, precision, logprob_dev, st);
+}
+
+int slsb_extract_feat(slsb_engine* e, const float* wav_dev, const int32_t* sample_lens_dev, int B, int S, int precision, float* x_dev, void* stream) {
+    if (check_ready(e)) return -1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (run_trunk(e, wav_dev, sample_lens_dev, B, S, precision, false, st)) return -1;
+    e->head = SLSB_HEAD_NONE;
+    if (x_dev) SLSB_CUDA_CHECK(cudaMemcpyAsync(x_dev, e->xfinal.p, (size_t)B * e->T * e->cfg.embed_dim * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int slsb_get_tensor(slsb_engine* e, const char* name, float* dst, int64_t numel, void* stream) {
+    if (!e || !name || !dst) { set_error("slsb_get_tensor: null argument"); return -1; }
+    if (e->B == 0) { set_error("slsb_get_tensor: no forward has run yet"); return -1; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const slsb_config& c = e->cfg;
+    const long long M = (long long)e->B * e->T;
+    const std::string n(name);
+    const void* src = nullptr;
+    int64_t want = 0;
+    if (n == "x") { src = e->xfinal.p; want = M * c.embed_dim; }
+    else if (n.rfind("layer_results.", 0) == 0) {
+        const int i = atoi(n.c_str() + 14);
+        if (i < 0 || i >= c.n_layers) { set_error("slsb_get_tensor: layer %d out of range", i); return -1; }
+        src = e->X[i + 1].p; want = M * c.embed_dim;
+    } else if (n == "pos_out") { src = e->X[0].p; want = M * c.embed_dim; }
+    else if (n == "acts") { if (!e->have_acts) { set_error("no SAE activations: last forward ran no SAE head"); return -1; } src = e->acts.p; want = M * c.sae_dict; }
+    else if (n == "pooled") { src = e->pooled.p; want = (int64_t)e->B * c.cls_in; }
+    else if (n == "sls_weights") { src = e->sls_w.p; want = (int64_t)e->B * c.n_layers; }
+    else if (n == "encoded") {
+        if (!e->have_sel) { set_error("no SAE selection: last forward ran no SAE head"); return -1; }
+        want = M * c.sae_dict;
+        if (numel != want) { set_error("slsb_get_tensor: '%s' has %lld elements, caller gave %lld", name, (long long)want, (long long)numel); return -1; }
+        const float* sel = (e->head == SLSB_HEAD_WINDOW && c.sae_window > 1) ? e->votes.as<float>() : e->acts.as<float>();
+        LAUNCH(votes_densify(e->acts.as<float>(), sel, e->thr.as<float>(), e->cut.as<int>(), dst, M, c.sae_dict, st));
+        return 0;
+    } else if (n == "features") {
+        want = M * c.conv_dim;
+        if (numel != want) { set_error("slsb_get_tensor: '%s' has %lld elements, caller gave %lld", name, (long long)want, (long long)numel); return -1; }
+        set_error("slsb_get_tensor: 'features' is overwritten by the encoder's LayerNorm scratch; not retained");
+        return -1;
+    } else { set_error("slsb_get_tensor: unknown tensor '%s'", name); return -1; }
+    if (numel != want) { set_error("slsb_get_tensor: '%s' has %lld elements, caller gave %lld", name, (long long)want, (long long)numel); return -1; }
+    SLSB_CUDA_CHECK(cudaMemcpyAsync(dst, src, (size_t)want * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int slsb_sae_encode(slsb_engine* e, const float* x_dev, int64_t rows, int T, int window, int precision, float* encoded_dev, void* stream) {
+    if (check_ready(e)) return -1;
+    const slsb_config& c = e->cfg;
+    if (c.sae_dict <= 0) { set_error("engine has no SAE weights"); return -1; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool bf = precision == SLSB_PREC_BF16;
+    if (rows <= 0) return 0;
+    if (e->xc.reserve((size_t)rows * c.embed_dim * (bf ? 2 : 4))) return -1;
+    const long long n = rows * c.embed_dim;
+    ++e->launches;
+    center_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x_dev, W32("sae.b_dec"), bf ? nullptr : e->xc.as<float>(), bf ? e->xc.as<bf16>() : nullptr, n, c.embed_dim);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    if (sae_acts(e, bf, e->xc.p, rows, st)) return -1;
+    const float* sel = nullptr;
+    if (sae_select(e, rows, T > 0 ? T : 1, window, &sel, st)) return -1;
+    LAUNCH(votes_densify(e->acts.as<float>(), sel, e->thr.as<float>(), e->cut.as<int>(), encoded_dev, rows, c.sae_dict, st));
+    return 0;
+}
+
+int slsb_sae_decode(slsb_engine* e, const float* encoded_dev, int64_t rows, int precision, float* recon_dev, void* stream) {
+    if (check_ready(e)) return -1;
+    const slsb_config& c = e->cfg;
+    if (c.sae_dict <= 0) { set_error("engine has no SAE weights"); return -1; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool bf = precision == SLSB_PREC_BF16;
+    if (rows <= 0) return 0;
+    const void* A = encoded_dev;
+    if (bf) {
+        if (e->tmp_bf16.reserve((size_t)rows * c.sae_dict * 2)) return -1;
+        LAUNCH(convert_f32_to_bf16(encoded_dev, e->tmp_bf16.p, rows * c.sae_dict, st));
+        A = e->tmp_bf16.p;
+    }
+    return linear(e, bf, A, c.sae_dict, "sae.dec.w", c.embed_dim, c.sae_dict, rows, W32("sae.b_dec"), nullptr, 0, recon_dev, c.embed_dim, 0, ACT_NONE, st);
+}
+
+int slsb_sae_loss(slsb_engine* e, int precision, float* loss_dev, void* stream) {
+    if (check_ready(e)) return -1;
+    const slsb_config& c = e->cfg;
+    if (!e->have_sel) { set_error("slsb_sae_loss: last forward ran no SAE head"); return -1; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long M = (long long)e->B * e->T;
+    if (e->encoded.reserve((size_t)M * c.sae_dict * 4) || e->recon.reserve((size_t)M * c.embed_dim * 4) || e->scratch.reserve(1024 * 4)) return -1;
+    const float* sel = (e->head == SLSB_HEAD_WINDOW && c.sae_window > 1) ? e->votes.as<float>() : e->acts.as<float>();
+    LAUNCH(votes_densify(e->acts.as<float>(), sel, e->thr.as<float>(), e->cut.as<int>(), e->encoded.as<float>(), M, c.sae_dict, st));
+    if (slsb_sae_decode(e, e->encoded.as<float>(), M, precision, e->recon.as<float>(), stream)) return -1;
+    e->launches += 1;
+    LAUNCH(mse_loss(e->recon.as<float>(), e->xfinal.as<float>(), M * c.embed_dim, loss_dev, e->scratch.as<float>(), st));
+    return 0;
+}
+
+int slsb_score_host(slsb_engine* e, const float* wav_host, const int32_t* lens_host, int B, int S, int head, int precision, float* scores_host, void* stream) {
+    if (check_ready(e)) return -1;
+    if (!wav_host || !scores_host) { set_error("slsb_score_host: null buffer"); return -1; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (e->wav_stage.reserve((size_t)B * S * 4) || e->logprob.reserve((size_t)B * 2 * 4) || e->score_stage.reserve((size_t)B * 4) ||
+        e->lens_stage.reserve((size_t)B * 4)) return -1;
+    SLSB_CUDA_CHECK(cudaMemcpyAsync(e->wav_stage.p, wav_host, (size_t)B * S * 4, cudaMemcpyHostToDevice, st));
+    const int32_t* lens_dev = nullptr;
+    if (lens_host) {
+        SLSB_CUDA_CHECK(cudaMemcpyAsync(e->lens_stage.p, lens_host, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+        lens_dev = e->lens_stage.as<int32_t>();
+    }
+    if (slsb_forward(e, e->wav_stage.as<float>(), lens_dev, B, S, head, precision, e->logprob.as<float>(), stream)) return -1;
+    LAUNCH(scores_from_logprob(e->logprob.as<float>(), e->score_stage.as<float>(), B, st));
+    SLSB_CUDA_CHECK(cudaMemcpyAsync(scores_host, e->score_stage.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    SLSB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int slsb_profile_enable(slsb_engine* e, int on) {
+    if (!e) { set_error("null engine"); return -1; }
+    for (auto& r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    e->prof.clear();
+    e->profiling = on != 0;
+    return 0;
+}
+
+int slsb_profile_read(slsb_engine* e, int kind, double* ms_out, double* flops_out, int64_t* launches_out) {
+    if (!e) { set_error("null engine"); return -1; }
+    SLSB_CUDA_CHECK(cudaDeviceSynchronize());
+    double ms = 0.0, fl = 0.0; int64_t n = 0;
+    for (auto& r : e->prof) {
+        if (r.kind != kind) continue;
+        float t = 0.f;
+        SLSB_CUDA_CHECK(cudaEventElapsedTime(&t, r.a, r.b));
+        ms += t; fl += r.flops; ++n;
+    }
+    if (ms_out) *ms_out = ms;
+    if (flops_out) *flops_out = fl;
+    if (launches_out) *launches_out = n;
+    return 0;
+}
+
+int slsb_synth_clips(float* wav_dev, int64_t first_utt, int count, int samples, void* stream) {
+    return synth_clips(wav_dev, first_utt, count, samples, static_cast<cudaStream_t>(stream));
+}
+
+// ---- single-op entry points -------------------------------------------------------------------
+static int device_sms() {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+
+int slsb_op_gemm(int precision, const void* A, const void* W, const float* bias, const float* residual, void* out, int M, int N, int K,
+                 int act, int out_bf16, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (precision == SLSB_PREC_BF16) {
+        TcGemmArgs g;
+        g.A = A; g.lda = K; g.W = W; g.ldw = K; g.M = M; g.N = N; g.K = K; g.out = out; g.ldc = N; g.out_bf16 = out_bf16;
+        g.bias = bias; g.residual = residual; g.ldr = N; g.act = act;
+        return tc_gemm(g, device_sms(), st);
+    }
+    SimtGemmArgs g;
+    g.A = A; g.lda = K; g.W = static_cast<const float*>(W); g.ldw = K; g.M = M; g.N = N; g.K = K; g.out = out; g.ldc = N; g.out_bf16 = out_bf16;
+    g.bias = bias; g.residual = residual; g.ldr = N; g.act = act;
+    return simt_gemm(g, st);
+}
+
+int slsb_op_conv(int precision, const void* x, const void* W, const float* bias, void* out, int B, int L_in, int C, int N, int k, int stride, void* stream) {
+    slsb_engine tmp;      // only num_sms / launches are touched
+    tmp.num_sms = device_sms();
+    return conv_layer(&tmp, precision == SLSB_PREC_BF16, x, W, bias, out, B, L_in, C, N, k, stride, static_cast<cudaStream_t>(stream));
+}
+
+int slsb_op_posconv(int precision, const float* x, const void* W, const float* bias, float* out, void* scratch, int B, int T, int D, int K,
+                    const int32_t* frame_lens_dev, void* stream) {
+    slsb_engine tmp;
+    tmp.num_sms = device_sms();
+    return pos_conv(&tmp, precision == SLSB_PREC_BF16, x, W, bias, out, scratch, B, T, D, K, D / 64, frame_lens_dev, static_cast<cudaStream_t>(stream));
+}
+
+int slsb_op_conv0(int out_bf16, const float* wav, const float* w, const float* bias, const float* ln_w, const float* ln_b, void* out, int B, int S,
+                  int exact_gelu, void* stream) {
+    const int L0 = (S - 10) / 5 + 1;
+    return conv0_ln_gelu(wav, B, S, L0, 10, 5, w, bias, ln_w, ln_b, out, out_bf16, 512, exact_gelu != 0, static_cast<cudaStream_t>(stream));
+}
+
+int slsb_op_layernorm(const void* in, int in_bf16, void* out, int out_bf16, const float* w, const float* b, int64_t rows, int C, int gelu,
+                      int exact_gelu, void* stream) {
+    LnArgs a;
+    a.in = in; a.in_bf16 = in_bf16; a.out = out; a.out_bf16 = out_bf16; a.w = w; a.b = b; a.rows = rows; a.C = C; a.gelu = gelu; a.exact_gelu = exact_gelu;
+    return layernorm(a, static_cast<cudaStream_t>(stream));
+}
+
+int slsb_op_attention(int impl, int io_bf16, const void* qkv, void* out, int B, int T, int H, const int32_t* frame_lens_dev, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (impl == SLSB_ATTN_TC) {
+        if (!io_bf16) { set_error("attention_tc is bf16 only"); return -1; }
+        return attention_tc(qkv, out, B, T, H, frame_lens_dev, device_sms(), st);
+    }
+    return attention_simt(qkv, out, io_bf16, B, T, H, frame_lens_dev, st);
+}
+
+int slsb_op_topk(const float* x, int64_t rows, int D, int k, float* thr, int32_t* tie_cut, float* encoded_or_null, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (topk_threshold(x, rows, D, k, thr, tie_cut, st)) return -1;
+    if (encoded_or_null) return topk_densify(x, thr, tie_cut, encoded_or_null, rows, D, st);
+    return 0;
+}
+
+}  // extern "C"

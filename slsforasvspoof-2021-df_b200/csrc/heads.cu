@@ -1,0 +1,433 @@
+// Classifier-head kernels (HBM-bound, integer/selection work stays on CUDA cores):
+//   * exact per-row top-k by 4-pass radix select (threshold + canonical lowest-index tie cut), never sorting;
+//   * streaming mean-pool of the kept activations in a fixed order (bit-stable, no atomics);
+//   * window top-k (model_window_topk.py:118-203) as window sums -> select -> votes -> select;
+//   * LayerNorm + MLP + log-softmax classifier (model.py:183-189);
+//   * SLS layer weighting / fused weighted sum + BN + SELU + 3x3 max-pool / tail (model_backup.py:186-202 + upstream).
+#include "common.cuh"
+#include "kernels.h"
+#include <math.h>
+
+namespace slsb {
+namespace {
+
+__device__ __forceinline__ uint32_t order_key(float v) {
+    const uint32_t u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
+// inclusive suffix sum over 256 per-thread values (thread t gets sum_{d >= t} v[d]); scratch: 8 ints
+__device__ __forceinline__ int block_suffix_sum_256(int v, int* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int s = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_down_sync(0xffffffffu, s, o);
+        if (lane + o < 32) s += n;
+    }
+    if (lane == 0) scratch[warp] = s;
+    __syncthreads();
+    int add = 0;
+    for (int w = warp + 1; w < 8; ++w) add += scratch[w];
+    __syncthreads();
+    return s + add;
+}
+// exclusive prefix sum over 256 per-thread values
+__device__ __forceinline__ int block_prefix_excl_256(int v, int* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int s = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, s, o);
+        if (lane >= o) s += n;
+    }
+    if (lane == 31) scratch[warp] = s;
+    __syncthreads();
+    int add = 0;
+    for (int w = 0; w < warp; ++w) add += scratch[w];
+    __syncthreads();
+    return s + add - v;
+}
+
+// One block (256 threads) per row; thread t owns the contiguous slice [t * EPT, (t + 1) * EPT).
+template <int EPT>
+__global__ void __launch_bounds__(256) topk_threshold_kernel(const float* __restrict__ x, int D, int k, float* __restrict__ thr, int* __restrict__ tie_cut) {
+    __shared__ int hist[256];
+    __shared__ int scratch[8];
+    __shared__ uint32_t s_prefix;
+    __shared__ int s_krem;
+    const long long row = blockIdx.x;
+    const float* xr = x + row * D;
+    uint32_t key[EPT];
+#pragma unroll
+    for (int i = 0; i < EPT; i += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + threadIdx.x * EPT + i);
+        key[i] = order_key(v.x); key[i + 1] = order_key(v.y); key[i + 2] = order_key(v.z); key[i + 3] = order_key(v.w);
+    }
+    uint32_t prefix = 0, mask = 0;
+    int krem = k;
+#pragma unroll 1
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        hist[threadIdx.x] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < EPT; ++i)
+            if ((key[i] & mask) == prefix) atomicAdd(&hist[(key[i] >> shift) & 255], 1);
+        __syncthreads();
+        const int h = hist[threadIdx.x];
+        const int suf = block_suffix_sum_256(h, scratch);      // elements with digit >= t
+        if (suf >= krem && suf - h < krem) {                    // exactly one thread
+            s_prefix = prefix | (uint32_t(threadIdx.x) << shift);
+            s_krem = krem - (suf - h);
+        }
+        __syncthreads();
+        prefix = s_prefix; krem = s_krem;
+        mask |= 255u << shift;
+        __syncthreads();
+    }
+    // prefix == key of the k-th largest value; krem (>= 1) of the entries equal to it are kept, lowest indices first
+    int eq = 0;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) eq += (key[i] == prefix);
+    const int before = block_prefix_excl_256(eq, scratch);
+    if (before < krem && before + eq >= krem) {
+        int need = krem - before, cut = 0;
+#pragma unroll
+        for (int i = 0; i < EPT; ++i)
+            if (key[i] == prefix && need > 0) { --need; cut = threadIdx.x * EPT + i + 1; }
+        thr[row] = key_to_float(prefix);
+        tie_cut[row] = cut;
+    }
+}
+
+__device__ __forceinline__ bool kept(float sel, int idx, float thr, int cut) { return sel > thr || (sel == thr && idx < cut); }
+
+__global__ void densify_kernel(const float* __restrict__ acts, const float* __restrict__ sel, const float* __restrict__ thr,
+                               const int* __restrict__ cut, float* __restrict__ out, long long rows, int D) {
+    const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 >= rows * D) return;
+    const long long row = i4 / D;
+    const int c = (int)(i4 - row * D);
+    const float t = thr[row]; const int ct = cut[row];
+    const float4 a = *reinterpret_cast<const float4*>(acts + i4);
+    const float4 s = *reinterpret_cast<const float4*>(sel + i4);
+    float4 o;
+    o.x = kept(s.x, c, t, ct) ? a.x : 0.f; o.y = kept(s.y, c + 1, t, ct) ? a.y : 0.f;
+    o.z = kept(s.z, c + 2, t, ct) ? a.z : 0.f; o.w = kept(s.w, c + 3, t, ct) ? a.w : 0.f;
+    *reinterpret_cast<float4*>(out + i4) = o;
+}
+
+__global__ void mean_pool_kept_kernel(const float* __restrict__ acts, const float* __restrict__ sel, const float* __restrict__ thr,
+                                      const int* __restrict__ cut, float* __restrict__ pooled, int T, int D, const int* __restrict__ lens) {
+    const int b = blockIdx.y;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= D) return;
+    const int len = lens ? min(lens[b], T) : T;
+    float s = 0.f;
+    for (int t = 0; t < len; ++t) {
+        const long long row = (long long)b * T + t;
+        const float v = sel[row * D + f];
+        if (kept(v, f, thr[row], cut[row])) s += acts[row * D + f];
+    }
+    pooled[(long long)b * D + f] = s / (float)len;
+}
+
+__global__ void mean_pool_kernel(const float* __restrict__ x, float* __restrict__ pooled, int T, int D, const int* __restrict__ lens) {
+    const int b = blockIdx.y;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= D) return;
+    const int len = lens ? min(lens[b], T) : T;
+    float s = 0.f;
+    for (int t = 0; t < len; ++t) s += x[((long long)b * T + t) * D + f];
+    pooled[(long long)b * D + f] = s / (float)len;
+}
+
+__global__ void window_sums_kernel(const float* __restrict__ acts, float* __restrict__ sums, int T, int D, int window, int stride, int nw) {
+    const int b = blockIdx.z, w = blockIdx.y;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= D) return;
+    float s = 0.f;
+    for (int j = 0; j < window; ++j) s += acts[((long long)b * T + w * stride + j) * D + f];
+    sums[((long long)b * nw + w) * D + f] = s;
+}
+
+__global__ void window_votes_kernel(const float* __restrict__ acts, const float* __restrict__ sums, const float* __restrict__ thr_w,
+                                    const int* __restrict__ cut_w, float* __restrict__ votes, int T, int D, int window, int stride, int nw) {
+    const int b = blockIdx.z, t = blockIdx.y;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= D) return;
+    const float a = acts[((long long)b * T + t) * D + f];
+    float v = 0.f;
+    const int w_hi = min(t / stride, nw - 1);
+    const int w_lo = (t - window + 1 > 0) ? (t - window + stride) / stride : 0;
+    for (int w = w_lo; w <= w_hi; ++w) {         // ascending window order, as the reference accumulates (:175-185)
+        const long long wr = (long long)b * nw + w;
+        if (kept(sums[wr * D + f], f, thr_w[wr], cut_w[wr])) v += a;
+    }
+    votes[((long long)b * T + t) * D + f] = v;
+}
+
+// ---- classifier: LN(D) -> Linear(D, Hd) -> ReLU -> Linear(Hd, 2) -> log_softmax ; one block per utterance
+__global__ void __launch_bounds__(256) classifier_kernel(const float* __restrict__ pooled, int D, int Hd, const float* __restrict__ ln_w,
+                                                         const float* __restrict__ ln_b, const float* __restrict__ w1, const float* __restrict__ b1,
+                                                         const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ logprob) {
+    extern __shared__ float cls_smem[];
+    float* xs = cls_smem;            // D
+    float* hs = cls_smem + D;        // Hd
+    __shared__ float red[8];
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* x = pooled + (long long)b * D;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < D; i += 256) { const float v = x[i]; xs[i] = v; s += v; }
+    s = warp_sum(s);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    float mean = 0.f;
+    for (int w = 0; w < 8; ++w) mean += red[w];
+    mean /= (float)D;
+    __syncthreads();
+    float q = 0.f;
+    for (int i = threadIdx.x; i < D; i += 256) { const float d = xs[i] - mean; q = fmaf(d, d, q); }
+    q = warp_sum(q);
+    if (lane == 0) red[warp] = q;
+    __syncthreads();
+    float var = 0.f;
+    for (int w = 0; w < 8; ++w) var += red[w];
+    const float rstd = 1.0f / sqrtf(var / (float)D + 1e-5f);
+    for (int i = threadIdx.x; i < D; i += 256) xs[i] = (xs[i] - mean) * rstd * ln_w[i] + ln_b[i];
+    __syncthreads();
+    for (int u = warp; u < Hd; u += 8) {
+        const float* wr = w1 + (long long)u * D;
+        float a = 0.f;
+        for (int i = lane * 4; i < D; i += 128) {
+            const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + i));
+            const float4 xv = *reinterpret_cast<const float4*>(xs + i);
+            a = fmaf(wv.x, xv.x, a); a = fmaf(wv.y, xv.y, a); a = fmaf(wv.z, xv.z, a); a = fmaf(wv.w, xv.w, a);
+        }
+        a = warp_sum(a);
+        if (lane == 0) hs[u] = fmaxf(a + b1[u], 0.f);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float l0 = 0.f, l1 = 0.f;
+        for (int i = lane; i < Hd; i += 32) { l0 = fmaf(w2[i], hs[i], l0); l1 = fmaf(w2[Hd + i], hs[i], l1); }
+        l0 = warp_sum(l0) + b2[0]; l1 = warp_sum(l1) + b2[1];
+        if (lane == 0) {
+            const float m = fmaxf(l0, l1);
+            const float lse = m + logf(expf(l0 - m) + expf(l1 - m));
+            logprob[b * 2 + 0] = l0 - lse; logprob[b * 2 + 1] = l1 - lse;
+        }
+    }
+}
+
+// ---- SLS
+struct LayerPtrs { const float* p[32]; };
+
+// grid (n_layers, B), 256 threads x 4 channels: layer mean over frames, dot with fc0, sigmoid
+__global__ void __launch_bounds__(256) sls_weights_kernel(LayerPtrs L, int T, int D, const float* __restrict__ fc0_w, const float* __restrict__ fc0_b,
+                                                          float* __restrict__ layer_w, int n_layers, const int* __restrict__ lens) {
+    __shared__ float red[8];
+    const int l = blockIdx.x, b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int len = lens ? min(lens[b], T) : T;
+    const float* x = L.p[l] + (long long)b * T * D;
+    float dot = 0.f;
+    for (int c = threadIdx.x * 4; c < D; c += 1024) {
+        float4 s = make_float4(0, 0, 0, 0);
+        for (int t = 0; t < len; ++t) {
+            const float4 v = *reinterpret_cast<const float4*>(x + (long long)t * D + c);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        const float inv = 1.0f / (float)len;
+        const float4 w = *reinterpret_cast<const float4*>(fc0_w + c);
+        dot = fmaf(s.x * inv, w.x, dot); dot = fmaf(s.y * inv, w.y, dot); dot = fmaf(s.z * inv, w.z, dot); dot = fmaf(s.w * inv, w.w, dot);
+    }
+    dot = warp_sum(dot);
+    if (lane == 0) red[warp] = dot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float z = fc0_b[0];
+        for (int w = 0; w < 8; ++w) z += red[w];
+        layer_w[b * n_layers + l] = 1.0f / (1.0f + expf(-z));
+    }
+}
+
+__device__ __forceinline__ float selu(float x) {
+    const float alpha = 1.6732632423543772848170429916717f, scale = 1.0507009873554804934193349852946f;
+    return scale * (x > 0.f ? x : alpha * (expf(x) - 1.0f));
+}
+
+// grid (T/3, B), D threads: weighted layer sum for 3 frames, BN (eval affine) + SELU, then 3x3 max pool -> out[b][i*(D/3)+j]
+__global__ void sls_fuse_pool_kernel(LayerPtrs L, int n_layers, const float* __restrict__ layer_w, int T, int D, const float* __restrict__ bn, float bn_eps,
+                                     float* __restrict__ out, int ldo) {
+    extern __shared__ float fp_smem[];   // [3][D]
+    __shared__ float lw[32];
+    const int i = blockIdx.x, b = blockIdx.y, c = threadIdx.x;
+    if (c < n_layers) lw[c] = layer_w[b * n_layers + c];
+    __syncthreads();
+    const float g = bn[0] / sqrtf(bn[3] + bn_eps), beta = bn[1], rm = bn[2];
+    if (c < D) {
+#pragma unroll
+        for (int di = 0; di < 3; ++di) {
+            const long long off = ((long long)b * T + 3 * i + di) * D + c;
+            float s = 0.f;
+            for (int l = 0; l < n_layers; ++l) s = fmaf(L.p[l][off], lw[l], s);
+            fp_smem[di * D + c] = selu((s - rm) * g + beta);
+        }
+    }
+    __syncthreads();
+    const int J = D / 3;
+    if (c < J) {
+        float m = -INFINITY;
+#pragma unroll
+        for (int di = 0; di < 3; ++di)
+#pragma unroll
+            for (int dj = 0; dj < 3; ++dj) m = fmaxf(m, fp_smem[di * D + 3 * c + dj]);
+        out[(long long)b * ldo + i * J + c] = m;
+    }
+}
+
+// partial sums [B][KS][N] -> h = selu(sum + bias) -> fc3 -> selu -> log_softmax ; one block per utterance
+__global__ void __launch_bounds__(256) sls_tail_kernel(const float* __restrict__ partial, int KS, int Hd, const float* __restrict__ b1,
+                                                       const float* __restrict__ w3, const float* __restrict__ b3, float* __restrict__ logprob) {
+    __shared__ float red0[8], red1[8];
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float l0 = 0.f, l1 = 0.f;
+    for (int n = threadIdx.x; n < Hd; n += 256) {
+        float s = 0.f;
+        for (int ks = 0; ks < KS; ++ks) s += partial[((long long)b * KS + ks) * Hd + n];
+        const float h = selu(s + b1[n]);
+        l0 = fmaf(w3[n], h, l0); l1 = fmaf(w3[Hd + n], h, l1);
+    }
+    l0 = warp_sum(l0); l1 = warp_sum(l1);
+    if (lane == 0) { red0[warp] = l0; red1[warp] = l1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = b3[0], c = b3[1];
+        for (int w = 0; w < 8; ++w) { a += red0[w]; c += red1[w]; }
+        a = selu(a); c = selu(c);
+        const float m = fmaxf(a, c);
+        const float lse = m + logf(expf(a - m) + expf(c - m));
+        logprob[b * 2] = a - lse; logprob[b * 2 + 1] = c - lse;
+    }
+}
+
+__global__ void scores_kernel(const float* __restrict__ logprob, float* __restrict__ scores, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) scores[b] = expf(logprob[b * 2 + 1]);
+}
+
+__global__ void __launch_bounds__(256) sqdiff_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, float* __restrict__ partial) {
+    __shared__ float red[8];
+    float s = 0.f;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) { const float d = a[i] - b[i]; s = fmaf(d, d, s); }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { float t = 0.f; for (int w = 0; w < 8; ++w) t += red[w]; partial[blockIdx.x] = t; }
+}
+__global__ void sqdiff_final_kernel(const float* __restrict__ partial, int np, long long n, float* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) { double t = 0.0; for (int i = 0; i < np; ++i) t += partial[i]; out[0] = (float)(t / (double)n); }
+}
+
+}  // namespace
+
+int topk_threshold(const float* x, long long rows, int D, int k, float* thr, int* tie_cut, cudaStream_t stream) {
+    if (rows <= 0) return 0;
+    if (k < 1 || k > D) { set_error("topk: k=%d out of range for D=%d", k, D); return -1; }
+    switch (D) {
+        case 4096: topk_threshold_kernel<16><<<(unsigned)rows, 256, 0, stream>>>(x, D, k, thr, tie_cut); break;
+        case 2048: topk_threshold_kernel<8><<<(unsigned)rows, 256, 0, stream>>>(x, D, k, thr, tie_cut); break;
+        case 1024: topk_threshold_kernel<4><<<(unsigned)rows, 256, 0, stream>>>(x, D, k, thr, tie_cut); break;
+        case 8192: topk_threshold_kernel<32><<<(unsigned)rows, 256, 0, stream>>>(x, D, k, thr, tie_cut); break;
+        default: set_error("topk: dict size %d unsupported (1024/2048/4096/8192)", D); return -1;
+    }
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+int topk_densify(const float* acts, const float* thr, const int* tie_cut, float* encoded, long long rows, int D, cudaStream_t stream) {
+    return votes_densify(acts, acts, thr, tie_cut, encoded, rows, D, stream);
+}
+int votes_densify(const float* acts, const float* votes, const float* thr, const int* tie_cut, float* encoded, long long rows, int D, cudaStream_t stream) {
+    if (rows <= 0) return 0;
+    const long long n4 = rows * D / 4;
+    densify_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(acts, votes, thr, tie_cut, encoded, rows, D);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+int topk_mean_pool(const float* acts, const float* thr, const int* tie_cut, float* pooled, int B, int T, int D, const int* lens, cudaStream_t stream) {
+    return votes_mean_pool(acts, acts, thr, tie_cut, pooled, B, T, D, lens, stream);
+}
+int votes_mean_pool(const float* acts, const float* votes, const float* thr, const int* tie_cut, float* pooled, int B, int T, int D, const int* lens, cudaStream_t stream) {
+    dim3 grid((D + 127) / 128, B);
+    mean_pool_kept_kernel<<<grid, 128, 0, stream>>>(acts, votes, thr, tie_cut, pooled, T, D, lens);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+int mean_pool_frames(const float* x, float* pooled, int B, int T, int D, const int* lens, cudaStream_t stream) {
+    dim3 grid((D + 127) / 128, B);
+    mean_pool_kernel<<<grid, 128, 0, stream>>>(x, pooled, T, D, lens);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+int window_sums(const float* acts, float* sums, int B, int T, int D, int window, int stride, int nw, cudaStream_t stream) {
+    dim3 grid((D + 255) / 256, nw, B);
+    window_sums_kernel<<<grid, 256, 0, stream>>>(acts, sums, T, D, window, stride, nw);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+int window_votes(const float* acts, const float* sums, const float* thr_w, const int* cut_w, float* votes,
+                 int B, int T, int D, int window, int stride, int nw, cudaStream_t stream) {
+    dim3 grid((D + 255) / 256, T, B);
+    window_votes_kernel<<<grid, 256, 0, stream>>>(acts, sums, thr_w, cut_w, votes, T, D, window, stride, nw);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+int classifier_head(const float* pooled, int B, int D, int Hd, const float* ln_w, const float* ln_b, const float* w1, const float* b1,
+                    const float* w2, const float* b2, float* logprob, cudaStream_t stream) {
+    if (D % 128 != 0) { set_error("classifier: D=%d must be a multiple of 128", D); return -1; }
+    classifier_kernel<<<B, 256, (D + Hd) * sizeof(float), stream>>>(pooled, D, Hd, ln_w, ln_b, w1, b1, w2, b2, logprob);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+int sls_layer_weights(const float* const* layers, int n_layers, int B, int T, int D, const float* fc0_w, const float* fc0_b,
+                      float* layer_w, const int* lens, cudaStream_t stream) {
+    if (n_layers > 32) { set_error("sls: at most 32 layers"); return -1; }
+    LayerPtrs L{};
+    for (int i = 0; i < n_layers; ++i) L.p[i] = layers[i];
+    dim3 grid(n_layers, B);
+    sls_weights_kernel<<<grid, 256, 0, stream>>>(L, T, D, fc0_w, fc0_b, layer_w, n_layers, lens);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+int sls_fuse_pool(const float* const* layers, int n_layers, const float* layer_w, int B, int T, int D, const float* bn, float bn_eps,
+                  float* out, int ldo, cudaStream_t stream) {
+    if (n_layers > 32 || D > 1024) { set_error("sls_fuse_pool: n_layers<=32, D<=1024"); return -1; }
+    LayerPtrs L{};
+    for (int i = 0; i < n_layers; ++i) L.p[i] = layers[i];
+    dim3 grid(T / 3, B);
+    sls_fuse_pool_kernel<<<grid, D, 3 * D * sizeof(float), stream>>>(L, n_layers, layer_w, T, D, bn, bn_eps, out, ldo);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+int sls_tail(const float* partial, int KS, int B, int Hd, const float* b1, const float* w3, const float* b3, float* logprob, cudaStream_t stream) {
+    sls_tail_kernel<<<B, 256, 0, stream>>>(partial, KS, Hd, b1, w3, b3, logprob);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+int scores_from_logprob(const float* logprob, float* scores, int B, cudaStream_t stream) {
+    scores_kernel<<<(B + 127) / 128, 128, 0, stream>>>(logprob, scores, B);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+int mse_loss(const float* a, const float* b, long long n, float* out_scalar, float* scratch, cudaStream_t stream) {
+    const int np = 1024;
+    sqdiff_partial_kernel<<<np, 256, 0, stream>>>(a, b, n, scratch);
+    sqdiff_final_kernel<<<1, 32, 0, stream>>>(scratch, np, n, out_scalar);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace slsb

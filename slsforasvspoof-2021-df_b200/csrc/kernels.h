@@ -56,8 +56,6 @@ struct LnArgs {
     void* out2 = nullptr; int out2_bf16 = 0; const float* sub = nullptr;   // out2 = y - sub
     const float* w = nullptr; const float* b = nullptr;
     long long rows = 0; int C = 0; int gelu = 0; int exact_gelu = 1; float eps = 1e-5f;
-    // optional per-utterance masking: rows of utterance u at frame t >= lens[u] are written as zeros
-    const int* lens = nullptr; int frames_per_utt = 0;
 };
 int layernorm(const LnArgs& a, cudaStream_t stream);
 // x[B, T, D] (fp32) -> zero-padded [B, T + K, D] (fp32 or bf16), `left` zero frames in front; frames >= lens[b] zeroed
@@ -100,10 +98,8 @@ int sls_layer_weights(const float* const* layers, int n_layers, int B, int T, in
                       float* layer_w /*[B, n_layers]*/, const int* lens, cudaStream_t stream);
 int sls_fuse_pool(const float* const* layers, int n_layers, const float* layer_w, int B, int T, int D, const float* bn /*w,b,rm,rv*/,
                   float bn_eps, float* out /*[B, (T/3)*(D/3) padded to ldo]*/, int ldo, cudaStream_t stream);
-int sls_tail(const float* h /*[B, Hd] pre-activation fc1 out*/, int B, int Hd, const float* w3, const float* b3, float* logprob, cudaStream_t stream);
-// split-K skinny GEMM for SLS fc1 (M = B small, K = 22848): out[b][n] = sum_k x[b][k] w[n][k] + bias[n]; weights fp32 or bf16
-int skinny_gemm(const float* x, int ldx, const void* w, int w_bf16, int ldw, const float* bias, float* out, int B, int N, int K,
-                float* scratch, cudaStream_t stream);
+// fc1 split-K partials [B][KS][Hd] -> selu(sum + b1) -> fc3 -> selu -> log_softmax
+int sls_tail(const float* partial, int KS, int B, int Hd, const float* b1, const float* w3, const float* b3, float* logprob, cudaStream_t stream);
 // scores = exp(logprob[:, 1])   (main.py:183-184)
 int scores_from_logprob(const float* logprob, float* scores, int B, cudaStream_t stream);
 // mse between recon and x (model.py:224-225), deterministic two-stage reduction

@@ -1,0 +1,160 @@
+"""CPU tests of the host side: C-ABI library loads and exports what include/slsb200.h declares, the drop-in
+``Model`` has the reference's surface and state_dict keys, packing shapes, score-file format, sharding and the
+world_size-2 gather (gloo).  No compute entry point is called here (there is no GPU in the build container)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(sls, lib):
+    header = open(os.path.join(ROOT, "include", "slsb200.h")).read()
+    declared = set(re.findall(r"\b(slsb_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(sls.EXPORTED_SYMBOLS), declared ^ set(sls.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.slsb_abi_version() == 1
+
+
+def test_no_cpu_fallback(sls):
+    m = sls.Model(None, "cpu", cp_path=None, geometry=sls.TrunkGeometry(layers=1))
+    with pytest.raises(sls.SlsbError):
+        m(torch.zeros(1, 64600))
+    if not torch.cuda.is_available():
+        import ctypes as C
+        from importlib import import_module
+        cfg = sls.make_config(sls.TrunkGeometry(layers=1))
+        h = C.c_void_p()
+        rc = sls.load_library().slsb_create(C.byref(cfg), 0, C.byref(h))
+        assert rc != 0 and b"no CUDA device" in sls.load_library().slsb_last_error()
+
+
+def test_missing_checkpoint_raises_like_reference(sls):
+    with pytest.raises(RuntimeError):
+        sls.Model(None, "cpu", cp_path="/nonexistent/xlsr2_300m.pt", geometry=sls.TrunkGeometry(layers=1))
+
+
+def test_state_dict_keys_match_reference_naming(sls):
+    m = sls.Model(None, "cpu", cp_path=None, geometry=sls.TrunkGeometry(layers=2))
+    keys = set(m.state_dict())
+    for k in ["ssl_model.model.feature_extractor.conv_layers.0.0.weight", "ssl_model.model.feature_extractor.conv_layers.6.2.1.bias",
+              "ssl_model.model.post_extract_proj.weight", "ssl_model.model.mask_emb", "ssl_model.model.layer_norm.weight",
+              "ssl_model.model.encoder.pos_conv.0.weight_g", "ssl_model.model.encoder.pos_conv.0.weight_v",
+              "ssl_model.model.encoder.pos_conv.0.bias", "ssl_model.model.encoder.layers.1.self_attn.q_proj.weight",
+              "ssl_model.model.encoder.layers.1.self_attn.out_proj.bias", "ssl_model.model.encoder.layers.0.fc1.weight",
+              "ssl_model.model.encoder.layers.0.final_layer_norm.weight", "ssl_model.model.encoder.layer_norm.bias",
+              "sae.k", "sae.encoder.weight", "sae.encoder.bias", "sae.decoder.weight", "sae.b_dec",
+              "classifier.0.weight", "classifier.1.weight", "classifier.4.bias"]:
+        assert k in keys, k
+    assert m.state_dict()["sae.encoder.weight"].shape == (4096, 1024)
+    assert m.state_dict()["ssl_model.model.encoder.pos_conv.0.weight_g"].shape == (1, 1, 128)
+    # oracle (== reference naming, verified against /root/reference/model.py by strict load in oracle/make_golden.py)
+    from oracle.heads import OracleModel
+    from oracle.trunk import TrunkConfig
+    o = OracleModel(head="sae", trunk_cfg=TrunkConfig(layers=2))
+    missing, unexpected = m.load_state_dict(o.state_dict(), strict=False)
+    assert not unexpected and all("quantizer" in k for k in missing)
+    # module. prefix round trip (main.py:542-560)
+    wrapped = torch.nn.DataParallel(m) if torch.cuda.is_available() else None
+    sd = {"module." + k: v for k, v in m.state_dict().items()}
+    assert all(k.startswith("module.ssl_model") or k.startswith("module.sae") or k.startswith("module.classifier") for k in sd)
+
+
+def test_pack_shapes_and_folds(sls):
+    geo = sls.TrunkGeometry(layers=1)
+    m = sls.Model(None, "cpu", cp_path=None, geometry=geo)
+    packed = sls.pack_state_dict(m.state_dict(), geo)
+    assert packed["conv0.w"].shape == (512, 10) and packed["conv1.w"].shape == (512, 1536) and packed["conv6.w"].shape == (512, 1024)
+    assert packed["pos.w"].shape == (1024, 128 * 64) and packed["L0.qkv.w"].shape == (3072, 1024)
+    sd = m.state_dict()
+    # conv weights are tap-major: packed[o, t*C + c] == w[o, c, t]
+    w = sd["ssl_model.model.feature_extractor.conv_layers.2.0.weight"]
+    assert torch.equal(packed["conv2.w"][7, 2 * 512 + 5], w[7, 5, 2])
+    # q rows pre-scaled by 64**-0.5, k/v untouched
+    q = sd["ssl_model.model.encoder.layers.0.self_attn.q_proj.weight"]
+    assert torch.equal(packed["L0.qkv.w"][:1024], q * 0.125)
+    assert torch.equal(packed["L0.qkv.w"][1024:2048], sd["ssl_model.model.encoder.layers.0.self_attn.k_proj.weight"])
+    # weight-norm fold equals torch's own weight_norm forward
+    conv = m.ssl_model.model.encoder.pos_conv[0]
+    x = torch.randn(1, 1024, 50)
+    ref_w = torch._weight_norm(conv.weight_v, conv.weight_g, 2)
+    assert torch.allclose(packed["pos.w"].reshape(1024, 128, 64).permute(0, 2, 1), ref_w, atol=1e-7)
+    s = sls.ModelSLS(None, "cpu", cp_path=None, geometry=geo)
+    ps = sls.pack_state_dict(s.state_dict(), geo, sls_kp=s._sls_kp())
+    assert s.fc1.in_features == 22847 and ps["sls.fc1.w"].shape == (1024, 22848) and ps["sls.bn"].shape == (4,)
+    assert float(ps["sls.fc1.w"][:, 22847:].abs().max()) == 0.0
+
+
+def test_frames_formula(sls):
+    geo = sls.TrunkGeometry()
+    assert geo.frames(64600) == 201 and geo.frames(16000) == 49 and geo.frames(160000) == 499
+
+
+def test_pad_clip_matches_reference_semantics(sls):
+    x = np.arange(5, dtype=np.float32)
+    assert sls.pad_clip(x, 12).tolist() == [0, 1, 2, 3, 4, 0, 1, 2, 3, 4, 0, 1]      # data_utils_SSL.py:58-65 tile-repeat
+    assert sls.pad_clip(np.arange(20, dtype=np.float32), 12).tolist() == list(range(12))  # truncate head
+    assert sls.pad_clip(x, 5).tolist() == x.tolist()
+    if os.path.isdir("/root/reference"):
+        import importlib.util, types
+        src = open("/root/reference/data_utils_SSL.py").read()
+        fn = src[src.index("def pad("):src.index("class Dataset_ASVspoof2019_train")]
+        ns = {"np": np}
+        exec(fn, ns)                                                                  # the reference's own pad()
+        for n in (1, 7, 64599, 64600, 70000):
+            y = np.random.RandomState(n).randn(n).astype(np.float32)
+            assert np.array_equal(ns["pad"](y, 64600), sls.pad_clip(y, 64600))
+
+
+def test_score_file_format(sls, tmp_path):
+    p = str(tmp_path / "s.txt")
+    sls.write_score_file(p, ["LA_E_1", "LA_E_2"], [0.5, 1.25e-07])
+    assert open(p).read() == "LA_E_1 0.5\nLA_E_2 1.25e-07\n"                      # main.py:190-192: python float repr
+    sls.write_score_file(p, ["a"], [0.123456789], fmt="6f")
+    assert open(p).read() == "a 0.123457\n"
+    import pandas
+    sls.write_score_file(p, ["u1", "u2", "u3"], [0.1, 0.2, 0.3])
+    df = pandas.read_csv(p, sep=" ", header=None, skipinitialspace=True)           # evaluate_2021_DF.py:24
+    assert df.shape == (3, 2)
+
+
+def test_shard_ranges_cover_exactly(sls):
+    for n, w in [(611829, 8), (10, 4), (3, 8), (0, 2)]:
+        r = [sls.shard_range(n, k, w) for k in range(w)]
+        assert r[0][0] == 0 and r[-1][1] == n and all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+        assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+
+
+_GLOO_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+import sls_b200
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank, n = dist.get_rank(), 11
+lo, hi = sls_b200.shard_range(n, rank, 2)
+local = torch.arange(lo, hi, dtype=torch.float32) * 0.5       # stands in for this rank's scores
+full = sls_b200.gather_scores(local, n, rank, 2)
+assert torch.equal(full, torch.arange(n, dtype=torch.float32) * 0.5), full
+if rank == 0:
+    sls_b200.write_score_file(sys.argv[4], ["u%d" % i for i in range(n)], full.tolist())
+dist.barrier(); dist.destroy_process_group()
+'''
+
+
+def test_world_size_2_gather_gloo(tmp_path):
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    out = str(tmp_path / "scores.txt")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r), out]) for r in range(2)]
+    assert all(p.wait(timeout=240) == 0 for p in procs)
+    lines = open(out).read().splitlines()
+    assert len(lines) == 11 and lines[3] == "u3 1.5"

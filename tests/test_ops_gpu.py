@@ -1,0 +1,210 @@
+"""Kernel-level parity: every CUDA kernel, called through the C ABI, against a plain PyTorch fp32
+reference of the same op on the same seeded inputs.  Tolerances are written next to each check."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import P, ok, report, stream
+
+pytestmark = pytest.mark.gpu
+
+FP32, BF16 = 0, 1
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+
+
+def _rand(shape, seed, scale=1.0, device="cuda"):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(device)
+
+
+def _act(x, act):
+    return F.gelu(x) if act == ACT_GELU else (F.relu(x) if act == ACT_RELU else x)
+
+
+# ------------------------------------------------------------------------------------------ SIMT GEMM
+@pytest.mark.parametrize("M,N,K,act,res", [(300, 200, 64, ACT_NONE, False), (257, 1024, 512, ACT_GELU, False),
+                                           (1000, 512, 1024, ACT_NONE, True), (128, 4096, 1024, ACT_RELU, False)])
+def test_gemm_fp32(lib, cuda, M, N, K, act, res):
+    A, W, b = _rand((M, K), 1), _rand((N, K), 2, 0.05), _rand((N,), 3)
+    R = _rand((M, N), 4) if res else None
+    out = torch.empty(M, N, device=cuda)
+    ok(lib, lib.slsb_op_gemm(FP32, P(A), P(W), P(b), P(R), P(out), M, N, K, act, 0, stream()), "gemm fp32")
+    ref = _act(A.double() @ W.double().T + b.double(), act)
+    if res:
+        ref = ref + R.double()
+    report(f"gemm_fp32 {M}x{N}x{K}", out, ref.float(), atol=2e-5, rtol=2e-5)   # fp32 accumulate over K <= 1024
+
+
+# ------------------------------------------------------------------------------------------ tcgen05 GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 256), (256, 512, 1024), (1000, 1024, 1024), (777, 3072, 1024),
+                                   (640, 1024, 4096), (300, 384, 128), (300, 192, 512), (12864, 1024, 1024)])
+def test_gemm_bf16_tc_bias(lib, cuda, M, N, K):
+    A, W, b = _rand((M, K), 1).bfloat16(), _rand((N, K), 2, 0.05).bfloat16(), _rand((N,), 3)
+    out = torch.empty(M, N, device=cuda, dtype=torch.bfloat16)
+    ok(lib, lib.slsb_op_gemm(BF16, P(A), P(W), P(b), None, P(out), M, N, K, ACT_NONE, 1, stream()), "gemm tc")
+    ref = A.float() @ W.float().T + b
+    report(f"gemm_tc {M}x{N}x{K}", out, ref, atol=2e-3, rtol=8e-3)      # output rounded to bf16 (2^-8 rel)
+
+
+@pytest.mark.parametrize("act,out_bf16,res", [(ACT_GELU, 1, False), (ACT_NONE, 0, True), (ACT_NONE, 0, False),
+                                              (ACT_RELU, 0, False), (ACT_GELU, 0, True)])
+def test_gemm_bf16_tc_epilogues(lib, cuda, act, out_bf16, res):
+    M, N, K = 1000, 1024, 512
+    A, W, b = _rand((M, K), 5).bfloat16(), _rand((N, K), 6, 0.05).bfloat16(), _rand((N,), 7)
+    R = _rand((M, N), 8) if res else None
+    out = torch.empty(M, N, device=cuda, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    ok(lib, lib.slsb_op_gemm(BF16, P(A), P(W), P(b), P(R), P(out), M, N, K, act, out_bf16, stream()), "gemm tc epi")
+    ref = _act(A.float() @ W.float().T + b, act)
+    if res:
+        ref = ref + R
+    report(f"gemm_tc epi act={act} bf16={out_bf16} res={res}", out, ref, atol=2e-3 if out_bf16 else 2e-4, rtol=8e-3 if out_bf16 else 1e-4)
+
+
+def test_gemm_bf16_tc_deterministic(lib, cuda):
+    M, N, K = 2000, 1024, 1024
+    A, W, b = _rand((M, K), 9).bfloat16(), _rand((N, K), 10, 0.05).bfloat16(), _rand((N,), 11)
+    outs = []
+    for _ in range(3):
+        out = torch.empty(M, N, device=cuda, dtype=torch.bfloat16)
+        ok(lib, lib.slsb_op_gemm(BF16, P(A), P(W), P(b), None, P(out), M, N, K, ACT_NONE, 1, stream()), "gemm tc")
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])   # bit-stable
+
+
+# ------------------------------------------------------------------------------------------ strided convs as implicit GEMM
+@pytest.mark.parametrize("prec", [FP32, BF16])
+@pytest.mark.parametrize("B,Lin,k,s", [(2, 1291, 3, 2), (3, 403, 2, 2), (1, 806, 2, 2), (2, 6459, 3, 2)])
+def test_conv_implicit_gemm(lib, cuda, prec, B, Lin, k, s):
+    C = N = 512
+    dt = torch.bfloat16 if prec == BF16 else torch.float32
+    x = _rand((B, Lin, C), 20).to(dt)
+    w = _rand((N, C, k), 21, 1.0 / math.sqrt(C * k)).to(dt)
+    b = _rand((N,), 22)
+    Lout = (Lin - k) // s + 1
+    wp = w.permute(0, 2, 1).reshape(N, k * C).contiguous()
+    out = torch.empty(B, Lout, N, device=cuda, dtype=dt)
+    ok(lib, lib.slsb_op_conv(prec, P(x), P(wp), P(b), P(out), B, Lin, C, N, k, s, stream()), "conv")
+    ref = F.conv1d(x.float().transpose(1, 2), w.float(), b, stride=s).transpose(1, 2)
+    report(f"conv prec={prec} B={B} Lin={Lin} k={k}", out, ref, atol=2e-3 if prec == BF16 else 2e-5, rtol=8e-3 if prec == BF16 else 2e-5)
+
+
+# ------------------------------------------------------------------------------------------ positional conv
+@pytest.mark.parametrize("prec", [FP32, BF16])
+@pytest.mark.parametrize("B,T,lens", [(2, 201, None), (3, 97, [97, 50, 80])])
+def test_posconv(lib, cuda, prec, B, T, lens):
+    D, K, G = 1024, 128, 16
+    x = _rand((B, T, D), 30)
+    w = _rand((D, D // G, K), 31, math.sqrt(4.0 / (K * D)) * 3)
+    b = _rand((D,), 32, 0.05)
+    wp = w.permute(0, 2, 1).reshape(D, K * (D // G)).contiguous()
+    es = 2 if prec == BF16 else 4
+    scratch = torch.zeros(B * (T + K) * D * es + (8 << 20), device=cuda, dtype=torch.uint8)
+    lens_t = torch.tensor(lens, dtype=torch.int32, device=cuda) if lens else None
+    out = torch.empty(B, T, D, device=cuda)
+    wdev = wp.bfloat16() if prec == BF16 else wp
+    ok(lib, lib.slsb_op_posconv(prec, P(x), P(wdev), P(b), P(out), P(scratch), B, T, D, K, P(lens_t), stream()), "posconv")
+    xin = x.clone()
+    if lens:
+        for i, n in enumerate(lens):
+            xin[i, n:] = 0
+    if prec == BF16:
+        xc, wc = xin.bfloat16().float(), w.bfloat16().float()
+    else:
+        xc, wc = xin, w
+    y = F.conv1d(xc.transpose(1, 2), wc, b, padding=K // 2, groups=G)[:, :, :-1]
+    ref = x + F.gelu(y).transpose(1, 2)
+    if lens:   # only valid frames are defined
+        for i, n in enumerate(lens):
+            out[i, n:] = 0
+            ref[i, n:] = 0
+    report(f"posconv prec={prec}", out, ref, atol=3e-3 if prec == BF16 else 3e-5, rtol=1e-3 if prec == BF16 else 1e-5)
+
+
+# ------------------------------------------------------------------------------------------ conv0 + LN + GELU
+@pytest.mark.parametrize("out_bf16", [0, 1])
+def test_conv0_ln_gelu(lib, cuda, out_bf16):
+    B, S, C = 3, 4000, 512
+    wav = _rand((B, S), 40)
+    w, b = _rand((C, 10), 41, math.sqrt(2.0 / 10)), _rand((C,), 42, 0.05)
+    g, be = 1 + _rand((C,), 43, 0.1), _rand((C,), 44, 0.05)
+    L0 = (S - 10) // 5 + 1
+    out = torch.empty(B, L0, C, device=cuda, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    ok(lib, lib.slsb_op_conv0(out_bf16, P(wav), P(w), P(b), P(g), P(be), P(out), B, S, 0 if out_bf16 else 1, stream()), "conv0")
+    y = F.conv1d(wav.unsqueeze(1), w.unsqueeze(1), b, stride=5).transpose(1, 2)
+    ref = F.gelu(F.layer_norm(y, (C,), g, be, 1e-5))
+    report(f"conv0 bf16={out_bf16}", out, ref, atol=1e-2 if out_bf16 else 2e-5, rtol=8e-3 if out_bf16 else 1e-5)
+
+
+@pytest.mark.parametrize("C", [512, 1024])
+@pytest.mark.parametrize("in_bf16,out_bf16,gelu", [(0, 0, 0), (0, 1, 0), (1, 1, 1), (0, 0, 1)])
+def test_layernorm(lib, cuda, C, in_bf16, out_bf16, gelu):
+    rows = 1003
+    x = _rand((rows, C), 50, 2.0) + 0.5
+    x = x.bfloat16() if in_bf16 else x
+    g, b = 1 + _rand((C,), 51, 0.1), _rand((C,), 52, 0.05)
+    out = torch.empty(rows, C, device=cuda, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    ok(lib, lib.slsb_op_layernorm(P(x), in_bf16, P(out), out_bf16, P(g), P(b), rows, C, gelu, 1, stream()), "ln")
+    ref = F.layer_norm(x.float(), (C,), g, b, 1e-5)
+    if gelu:
+        ref = F.gelu(ref)
+    report(f"ln C={C}", out, ref, atol=2e-2 if out_bf16 else 1e-5, rtol=8e-3 if out_bf16 else 1e-5)
+
+
+# ------------------------------------------------------------------------------------------ attention
+def _attn_ref(qkv, B, T, H, lens):
+    D = H * 64
+    q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2)
+    if lens is not None:
+        mask = torch.arange(T, device=qkv.device)[None, :] >= torch.tensor(lens, device=qkv.device)[:, None]
+        s = s.masked_fill(mask[:, None, None, :], float("-inf"))
+    o = torch.softmax(s, -1) @ v
+    return o.permute(0, 2, 1, 3).reshape(B, T, D)
+
+
+@pytest.mark.parametrize("impl,bf16", [(1, 0), (1, 1), (2, 1)])
+@pytest.mark.parametrize("B,T,lens", [(2, 201, None), (3, 137, [137, 60, 1]), (1, 256, None), (2, 49, None)])
+def test_attention(lib, cuda, impl, bf16, B, T, lens):
+    H = 16
+    qkv = _rand((B, T, 3 * H * 64), 60, 0.5)
+    qkv[..., :H * 64] *= 0.125 * 4      # q pre-scaled (keeps the softmax reasonably peaked)
+    qkv = qkv.bfloat16() if bf16 else qkv
+    out = torch.zeros(B, T, H * 64, device=cuda, dtype=qkv.dtype)
+    lens_t = torch.tensor(lens, dtype=torch.int32, device=cuda) if lens else None
+    ok(lib, lib.slsb_op_attention(impl, bf16, P(qkv), P(out), B, T, H, P(lens_t), stream()), "attention")
+    ref = _attn_ref(qkv, B, T, H, lens)
+    if lens:
+        for i, n in enumerate(lens):
+            out[i, n:] = 0
+            ref[i, n:] = 0
+    report(f"attention impl={impl} bf16={bf16} T={T}", out, ref, atol=1.5e-2 if bf16 else 2e-5, rtol=1e-2 if bf16 else 1e-5)
+
+
+def test_attention_long_simt(lib, cuda):
+    B, T, H = 1, 499, 16
+    qkv = _rand((B, T, 3 * H * 64), 61, 0.5)
+    out = torch.zeros(B, T, H * 64, device=cuda)
+    ok(lib, lib.slsb_op_attention(1, 0, P(qkv), P(out), B, T, H, None, stream()), "attention long")
+    report("attention simt T=499", out, _attn_ref(qkv, B, T, H, None), atol=2e-5, rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------ top-k select
+@pytest.mark.parametrize("D,k", [(4096, 128), (1024, 64), (2048, 7)])
+def test_topk_matches_canonical_rule(lib, cuda, D, k):
+    rows = 300
+    x = F.relu(_rand((rows, D), 70))
+    x[5] = 0.0                       # all-zero row: k zeros kept, output all zero
+    x[6, :] = 1.0                    # all-equal row: lowest k indices win
+    x[7, : D // 2] = x[7, D // 2:]   # duplicated values -> real ties at the threshold
+    x[8, 10:] = 0.0                  # fewer than k positives
+    thr = torch.empty(rows, device=cuda)
+    cut = torch.empty(rows, device=cuda, dtype=torch.int32)
+    enc = torch.empty(rows, D, device=cuda)
+    ok(lib, lib.slsb_op_topk(P(x), rows, D, k, P(thr), P(cut), P(enc), stream()), "topk")
+    order = torch.sort(x, dim=-1, descending=True, stable=True).indices[:, :k]
+    ref = torch.zeros_like(x).scatter_(-1, order, x.gather(-1, order))
+    assert torch.equal(enc, ref)     # bit-exact selection, canonical lowest-index tie rule
+    assert torch.equal(thr, x.gather(-1, order[:, -1:]).squeeze(-1))
+    assert int((enc[6] != 0).nonzero().max()) == k - 1
