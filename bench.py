@@ -194,8 +194,10 @@ def main():
         psteps = min(args.steps, 3)
         for i in range(psteps):
             eng.forward(pool[i % n_pool], head, prec)
-        g_ms, g_fl, g_n = eng.profile_read(0)
-        other = {k: eng.profile_read(i) for i, k in ((1, "conv_gemm"), (2, "pos_conv"), (3, "other_gemm"), (4, "attention"))}
+        enc = {k: eng.profile_read(i) for i, k in ((0, "qkv"), (1, "out_proj"), (2, "fc1"), (3, "fc2"))}
+        g_ms, g_fl, g_n = (sum(v[j] for v in enc.values()) for j in range(3))
+        other = {k: eng.profile_read(i) for i, k in ((4, "conv_gemm"), (5, "pos_conv"), (6, "other_gemm"), (7, "attention"))}
+        other.update(enc)
         eng.profile(False)
         ach = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "tc_gemm_kernel (encoder qkv/out/fc1/fc2)", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],

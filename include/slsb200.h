@@ -111,7 +111,7 @@ int slsb_synth_clips(float* wav_dev, int64_t first_utt, int count, int samples, 
 int64_t slsb_launch_count(const slsb_engine* e);
 
 /* Per-launch CUDA-event timing of the tensor-core kernels (events recorded on the launch stream).
- * kind: 0 encoder GEMMs (qkv/out/fc1/fc2), 1 conv-stack implicit GEMMs, 2 positional conv, 3 other GEMMs, 4 attention.
+ * kind: 0 qkv, 1 out_proj, 2 fc1, 3 fc2 (encoder GEMMs), 4 conv-stack implicit GEMMs, 5 positional conv, 6 other GEMMs, 7 attention.
  * slsb_profile_read synchronises the device and sums elapsed ms / algorithmic FLOPs / launches since enable. */
 int slsb_profile_enable(slsb_engine* e, int on);
 int slsb_profile_read(slsb_engine* e, int kind, double* ms_out, double* flops_out, int64_t* launches_out);
@@ -124,6 +124,12 @@ int slsb_op_gemm(int precision, const void* A, const void* W, const float* bias,
 /* Conv1d(C->N, k, stride) over channels-last x[B, L_in, C] as implicit GEMM; W is [N, k*C] tap-major */
 int slsb_op_conv(int precision, const void* x, const void* W, const float* bias, void* out, int B, int L_in, int C, int N,
                  int k, int stride, void* stream);
+/* bf16 tensor-core feature-extractor layer: GELU(LayerNorm_512(Conv1d(x))) in one kernel; x bf16 [B, L_in, 512], out bf16 */
+int slsb_op_conv_ln_gelu(const void* x, const void* W, const float* bias, const float* ln_w, const float* ln_b, void* out,
+                         int B, int L_in, int C, int k, int stride, void* stream);
+/* conv0 (raw audio, k = 10, stride 5) on tensor cores via a hi/lo bf16 split; scratch >= 64 KB + B*L0*128 bytes; out bf16 */
+int slsb_op_conv0_tc(const float* wav, const float* w, const float* bias, const float* ln_w, const float* ln_b, void* out,
+                     void* scratch, int B, int S, void* stream);
 /* grouped positional conv + GELU + residual: x fp32 [B,T,D]; W [D, K*64] (per out channel: tap-major, 64 in-channels) */
 int slsb_op_posconv(int precision, const float* x, const void* W, const float* bias, float* out, void* scratch,
                     int B, int T, int D, int K, const int32_t* frame_lens_dev, void* stream);

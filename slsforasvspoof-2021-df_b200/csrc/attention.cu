@@ -178,25 +178,46 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         const uint32_t trow = tmem + (uint32_t(warp * 32) << 16);
         mbar_wait(&bars[1], 0);
         tc_fence_after();
+        // Scores are read from TMEM in 16-column chunks, double-buffered in registers so the next tcgen05.ld is in
+        // flight while the current chunk is processed.  Pass 1: row max.  Pass 2: p = exp2(s*log2e - max*log2e).
         const int nchunk = Tp / 16;
         float mx = -INFINITY;
-        for (int c = 0; c < nchunk; ++c) {
-            uint32_t a[16];
-            tmem_ld_32x32b_x16(trow + c * 16, a);
+        {
+            uint32_t a[2][16];
+            tmem_ld_32x32b_x16(trow, a[0]);
             tmem_ld_wait();
+#pragma unroll 1
+            for (int c = 0; c < nchunk; c += 2) {
+                if (c + 1 < nchunk) tmem_ld_32x32b_x16(trow + (c + 1) * 16, a[1]);
+                if (c * 16 + 16 <= len) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) if (c * 16 + j < len) mx = fmaxf(mx, __uint_as_float(a[j]));
+                    for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(a[0][j]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (c * 16 + j < len) mx = fmaxf(mx, __uint_as_float(a[0][j]));
+                }
+                tmem_ld_wait();
+                if (c + 1 >= nchunk) break;
+                if (c + 2 < nchunk) tmem_ld_32x32b_x16(trow + (c + 2) * 16, a[0]);
+                if (c * 16 + 32 <= len) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(a[1][j]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (c * 16 + 16 + j < len) mx = fmaxf(mx, __uint_as_float(a[1][j]));
+                }
+                tmem_ld_wait();
+            }
         }
         const float mxl = mx * 1.4426950408889634f;
         float sum = 0.f;
-        for (int c = 0; c < nchunk; ++c) {
-            uint32_t a[16];
-            tmem_ld_32x32b_x16(trow + c * 16, a);
-            tmem_ld_wait();
+        auto emit = [&](const uint32_t (&a)[16], int c) {
             float p[16];
+            const bool full = c * 16 + 16 <= len;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                p[j] = (c * 16 + j < len) ? exp2f(fmaf(__uint_as_float(a[j]), 1.4426950408889634f, -mxl)) : 0.f;
+                const float e = ex2_approx(fmaf(__uint_as_float(a[j]), 1.4426950408889634f, -mxl));
+                p[j] = (full || c * 16 + j < len) ? e : 0.f;
                 sum += p[j];
             }
             uint8_t* blk = sP + (c >> 2) * 16384 + r * 128;
@@ -207,6 +228,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                 w.z = pack_bf16x2(p[8 * v + 4], p[8 * v + 5]); w.w = pack_bf16x2(p[8 * v + 6], p[8 * v + 7]);
                 const int c8 = (c & 3) * 2 + v;
                 *reinterpret_cast<uint4*>(blk + ((c8 ^ (r & 7)) << 4)) = w;
+            }
+        };
+        {
+            uint32_t a[2][16];
+            tmem_ld_32x32b_x16(trow, a[0]);
+            tmem_ld_wait();
+#pragma unroll 1
+            for (int c = 0; c < nchunk; c += 2) {
+                if (c + 1 < nchunk) tmem_ld_32x32b_x16(trow + (c + 1) * 16, a[1]);
+                emit(a[0], c);
+                tmem_ld_wait();
+                if (c + 1 >= nchunk) break;
+                if (c + 2 < nchunk) tmem_ld_32x32b_x16(trow + (c + 2) * 16, a[0]);
+                emit(a[1], c + 1);
+                tmem_ld_wait();
             }
         }
         fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the tensor core (async proxy)

@@ -120,7 +120,7 @@ struct slsb_engine {
     int64_t launches = 0;
     // workspace
     Buf fe[2], lnbuf, qkv, attn, ffn, xmid, xfinal, xc, xpad, acts, encoded, sums, votes, thr, cut, thr_w, cut_w, pooled, logprob,
-        sls_w, sls_in, sls_part, zeros, scratch, flens, wav_stage, lens_stage, score_stage, recon, tmp_bf16;
+        sls_w, sls_in, sls_part, zeros, scratch, flens, wav_stage, lens_stage, score_stage, recon, tmp_bf16, im2col, conv0_w64;
     std::vector<Buf> X;
     // last call
     int B = 0, S = 0, T = 0, prec = 0, head = 0;
@@ -132,7 +132,7 @@ struct slsb_engine {
     std::vector<ProfRec> prof;
 };
 
-enum ProfKind { PK_ENC_GEMM = 0, PK_CONV_GEMM = 1, PK_POS_GEMM = 2, PK_OTHER_GEMM = 3, PK_ATTN = 4, PK_COUNT = 5 };
+enum ProfKind { PK_ENC_QKV = 0, PK_ENC_OUT = 1, PK_ENC_FC1 = 2, PK_ENC_FC2 = 3, PK_CONV_GEMM = 4, PK_POS_GEMM = 5, PK_OTHER_GEMM = 6, PK_ATTN = 7, PK_COUNT = 8 };
 
 struct ProfScope {
     slsb_engine* e; cudaStream_t st; int idx = -1;
@@ -327,18 +327,42 @@ static int run_trunk(slsb_engine* e, const float* wav, const int* slens, int B, 
     e->B = B; e->S = S; e->T = T; e->prec = prec; e->have_lens = slens != nullptr; e->have_acts = false; e->have_sel = false;
 
     // 1. feature extractor (wav2vec2.py:843-851)
-    LAUNCH(conv0_ln_gelu(wav, B, S, L[0], c.conv_kernel[0], c.conv_stride[0], W32("conv0.w"), W32("conv0.b"), W32("conv0.ln.w"),
-                         W32("conv0.ln.b"), e->fe[0].p, bf ? 1 : 0, C, !bf, st));
-    for (int i = 1; i < c.n_conv; ++i) {
-        const std::string p = "conv" + std::to_string(i);
-        void* in = e->fe[(i - 1) & 1].p;
-        void* out = e->fe[i & 1].p;
-        if (conv_layer(e, bf, in, bf ? (const void*)W16(p + ".w") : (const void*)W32(p + ".w"), W32(p + ".b"), out, B, L[i - 1], C, C,
-                       c.conv_kernel[i], c.conv_stride[i], st)) return -1;
-        LnArgs a;
-        a.in = out; a.in_bf16 = bf; a.out = out; a.out_bf16 = bf; a.w = W32(p + ".ln.w"); a.b = W32(p + ".ln.b");
-        a.rows = (long long)B * L[i]; a.C = C; a.gelu = 1; a.exact_gelu = !bf;
-        LAUNCH(layernorm(a, st));
+    const bool fused_ln = bf && c.reserved[0] == 0;     // reserved[0] = 1 disables the fused conv+LN+GELU tensor-core kernel
+    if (fused_ln) {
+        // bf16: every layer is one tcgen05 kernel with the LayerNorm + GELU in its epilogue
+        if (e->im2col.reserve((size_t)B * L[0] * 64 * 2)) return -1;
+        LAUNCH(conv0_im2col(wav, e->im2col.p, B, S, L[0], c.conv_kernel[0], c.conv_stride[0], st));
+        {
+            ProfScope ps(e, st, PK_CONV_GEMM, 2.0 * (double)B * L[0] * C * c.conv_kernel[0]);
+            TcLnGemmArgs g;
+            g.a_mode = A_PLAIN; g.A = e->im2col.p; g.lda = 64; g.W = e->conv0_w64.p; g.M = B * L[0]; g.K = 64; g.batches = 1;
+            g.out = e->fe[0].p; g.bias = W32("conv0.b"); g.ln_w = W32("conv0.ln.w"); g.ln_b = W32("conv0.ln.b");
+            LAUNCH(tc_gemm_ln_gelu(g, e->num_sms, st));
+        }
+        for (int i = 1; i < c.n_conv; ++i) {
+            const std::string p = "conv" + std::to_string(i);
+            ProfScope ps(e, st, PK_CONV_GEMM, 2.0 * (double)B * L[i] * C * c.conv_kernel[i] * C);
+            TcLnGemmArgs g;
+            g.a_mode = A_CONV; g.A = e->fe[(i - 1) & 1].p; g.W = W16(p + ".w"); g.M = L[i]; g.K = c.conv_kernel[i] * C; g.batches = B;
+            g.conv_cin = C; g.conv_stride = c.conv_stride[i]; g.conv_lin = L[i - 1];
+            g.out = e->fe[i & 1].p; g.out_batch_stride = (long long)L[i] * C;
+            g.bias = W32(p + ".b"); g.ln_w = W32(p + ".ln.w"); g.ln_b = W32(p + ".ln.b");
+            LAUNCH(tc_gemm_ln_gelu(g, e->num_sms, st));
+        }
+    } else {
+        LAUNCH(conv0_ln_gelu(wav, B, S, L[0], c.conv_kernel[0], c.conv_stride[0], W32("conv0.w"), W32("conv0.b"), W32("conv0.ln.w"),
+                             W32("conv0.ln.b"), e->fe[0].p, bf ? 1 : 0, C, !bf, st));
+        for (int i = 1; i < c.n_conv; ++i) {
+            const std::string p = "conv" + std::to_string(i);
+            void* in = e->fe[(i - 1) & 1].p;
+            void* out = e->fe[i & 1].p;
+            if (conv_layer(e, bf, in, bf ? (const void*)W16(p + ".w") : (const void*)W32(p + ".w"), W32(p + ".b"), out, B, L[i - 1], C, C,
+                           c.conv_kernel[i], c.conv_stride[i], st)) return -1;
+            LnArgs a;
+            a.in = out; a.in_bf16 = bf; a.out = out; a.out_bf16 = bf; a.w = W32(p + ".ln.w"); a.b = W32(p + ".ln.b");
+            a.rows = (long long)B * L[i]; a.C = C; a.gelu = 1; a.exact_gelu = !bf;
+            LAUNCH(layernorm(a, st));
+        }
     }
     // 2. LayerNorm(512) + post_extract_proj (wav2vec2.py:563-564, :595-596)
     {
@@ -359,14 +383,14 @@ static int run_trunk(slsb_engine* e, const float* wav, const int* slens, int B, 
         LnArgs a;
         a.in = xin; a.out = e->lnbuf.p; a.out_bf16 = bf; a.w = W32(p + ".ln1.w"); a.b = W32(p + ".ln1.b"); a.rows = M; a.C = D;
         LAUNCH(layernorm(a, st));
-        if (linear(e, bf, e->lnbuf.p, D, p + ".qkv.w", 3 * D, D, M, W32(p + ".qkv.b"), nullptr, 0, e->qkv.p, 3 * D, bf, ACT_NONE, st, PK_ENC_GEMM)) return -1;
+        if (linear(e, bf, e->lnbuf.p, D, p + ".qkv.w", 3 * D, D, M, W32(p + ".qkv.b"), nullptr, 0, e->qkv.p, 3 * D, bf, ACT_NONE, st, PK_ENC_QKV)) return -1;
         if (attention(e, bf, e->qkv.p, e->attn.p, B, T, H, flens, st)) return -1;
-        if (linear(e, bf, e->attn.p, D, p + ".out.w", D, D, M, W32(p + ".out.b"), xin, D, e->xmid.p, D, 0, ACT_NONE, st, PK_ENC_GEMM)) return -1;
+        if (linear(e, bf, e->attn.p, D, p + ".out.w", D, D, M, W32(p + ".out.b"), xin, D, e->xmid.p, D, 0, ACT_NONE, st, PK_ENC_OUT)) return -1;
         LnArgs a2;
         a2.in = e->xmid.p; a2.out = e->lnbuf.p; a2.out_bf16 = bf; a2.w = W32(p + ".ln2.w"); a2.b = W32(p + ".ln2.b"); a2.rows = M; a2.C = D;
         LAUNCH(layernorm(a2, st));
-        if (linear(e, bf, e->lnbuf.p, D, p + ".fc1.w", F, D, M, W32(p + ".fc1.b"), nullptr, 0, e->ffn.p, F, bf, ACT_GELU, st, PK_ENC_GEMM)) return -1;
-        if (linear(e, bf, e->ffn.p, F, p + ".fc2.w", D, F, M, W32(p + ".fc2.b"), e->xmid.as<float>(), D, xout, D, 0, ACT_NONE, st, PK_ENC_GEMM)) return -1;
+        if (linear(e, bf, e->lnbuf.p, D, p + ".fc1.w", F, D, M, W32(p + ".fc1.b"), nullptr, 0, e->ffn.p, F, bf, ACT_GELU, st, PK_ENC_FC1)) return -1;
+        if (linear(e, bf, e->ffn.p, F, p + ".fc2.w", D, F, M, W32(p + ".fc2.b"), e->xmid.as<float>(), D, xout, D, 0, ACT_NONE, st, PK_ENC_FC2)) return -1;
     }
     // 5. final LayerNorm on x only (wav2vec2.py:905-906); xc = x - b_dec feeds the SAE encoder (model.py:70)
     {
@@ -445,8 +469,10 @@ static int run_head(slsb_engine* e, int head, int prec, float* logprob, cudaStre
         } else {
             LAUNCH(mean_pool_frames(e->xfinal.as<float>(), e->pooled.as<float>(), B, T, D, flens, st));   // use_sae=False
         }
+        if (e->scratch.reserve((size_t)(B * c.cls_hidden + 1024) * 4)) return -1;
+        ++e->launches;
         LAUNCH(classifier_head(e->pooled.as<float>(), B, c.cls_in, c.cls_hidden, W32("cls.ln.w"), W32("cls.ln.b"), W32("cls.fc1.w"), W32("cls.fc1.b"),
-                               W32("cls.fc2.w"), W32("cls.fc2.b"), logprob, st));
+                               W32("cls.fc2.w"), W32("cls.fc2.b"), e->scratch.as<float>(), logprob, st));
         return 0;
     }
     if (head == SLSB_HEAD_SLS) {
@@ -509,7 +535,7 @@ int slsb_destroy(slsb_engine* e) {
     for (auto& kv : e->w) { if (kv.second.f32) cudaFree(kv.second.f32); if (kv.second.b16) cudaFree(kv.second.b16); }
     Buf* bufs[] = {&e->fe[0], &e->fe[1], &e->lnbuf, &e->qkv, &e->attn, &e->ffn, &e->xmid, &e->xfinal, &e->xc, &e->xpad, &e->acts, &e->encoded,
                    &e->sums, &e->votes, &e->thr, &e->cut, &e->thr_w, &e->cut_w, &e->pooled, &e->logprob, &e->sls_w, &e->sls_in, &e->sls_part,
-                   &e->zeros, &e->scratch, &e->flens, &e->wav_stage, &e->lens_stage, &e->score_stage, &e->recon, &e->tmp_bf16};
+                   &e->zeros, &e->scratch, &e->flens, &e->wav_stage, &e->lens_stage, &e->score_stage, &e->recon, &e->tmp_bf16, &e->im2col, &e->conv0_w64};
     for (Buf* b : bufs) b->release();
     for (auto& b : e->X) b.release();
     delete e;
@@ -539,6 +565,8 @@ int slsb_finalize_weights(slsb_engine* e, void* stream) {
         if (!kv.second.set) { set_error("slsb_finalize_weights: tensor '%s' was never set", kv.first.c_str()); return -1; }
         if (kv.second.gemm) LAUNCH(convert_f32_to_bf16(kv.second.f32, kv.second.b16, kv.second.numel, static_cast<cudaStream_t>(stream)));
     }
+    if (e->conv0_w64.reserve((size_t)e->cfg.conv_dim * 64 * 2)) return -1;
+    LAUNCH(conv0_pack_weights(e->w.at("conv0.w").f32, e->conv0_w64.p, e->cfg.conv_dim, e->cfg.conv_kernel[0], static_cast<cudaStream_t>(stream)));
     e->finalized = true;
     return 0;
 }
@@ -643,7 +671,7 @@ int slsb_sae_loss(slsb_engine* e, int precision, float* loss_dev, void* stream) 
     if (!e->have_sel) { set_error("slsb_sae_loss: last forward ran no SAE head"); return -1; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long M = (long long)e->B * e->T;
-    if (e->encoded.reserve((size_t)M * c.sae_dict * 4) || e->recon.reserve((size_t)M * c.embed_dim * 4) || e->scratch.reserve(1024 * 4)) return -1;
+    if (e->encoded.reserve((size_t)M * c.sae_dict * 4) || e->recon.reserve((size_t)M * c.embed_dim * 4) || e->scratch.reserve((size_t)(e->B * c.cls_hidden + 1024) * 4)) return -1;
     const float* sel = (e->head == SLSB_HEAD_WINDOW && c.sae_window > 1) ? e->votes.as<float>() : e->acts.as<float>();
     LAUNCH(votes_densify(e->acts.as<float>(), sel, e->thr.as<float>(), e->cut.as<int>(), e->encoded.as<float>(), M, c.sae_dict, st));
     if (slsb_sae_decode(e, e->encoded.as<float>(), M, precision, e->recon.as<float>(), stream)) return -1;
@@ -726,6 +754,29 @@ int slsb_op_conv(int precision, const void* x, const void* W, const float* bias,
     slsb_engine tmp;      // only num_sms / launches are touched
     tmp.num_sms = device_sms();
     return conv_layer(&tmp, precision == SLSB_PREC_BF16, x, W, bias, out, B, L_in, C, N, k, stride, static_cast<cudaStream_t>(stream));
+}
+
+int slsb_op_conv_ln_gelu(const void* x, const void* W, const float* bias, const float* ln_w, const float* ln_b, void* out, int B, int L_in,
+                         int C, int k, int stride, void* stream) {
+    TcLnGemmArgs g;
+    const int Lout = (L_in - k) / stride + 1;
+    g.a_mode = A_CONV; g.A = x; g.W = W; g.M = Lout; g.K = k * C; g.batches = B; g.conv_cin = C; g.conv_stride = stride; g.conv_lin = L_in;
+    g.out = out; g.out_batch_stride = (long long)Lout * 512; g.bias = bias; g.ln_w = ln_w; g.ln_b = ln_b;
+    return tc_gemm_ln_gelu(g, device_sms(), static_cast<cudaStream_t>(stream));
+}
+
+int slsb_op_conv0_tc(const float* wav, const float* w, const float* bias, const float* ln_w, const float* ln_b, void* out, void* scratch,
+                     int B, int S, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int L0 = (S - 10) / 5 + 1;
+    char* w64 = static_cast<char*>(scratch);                       // [512, 64] bf16
+    char* cols = w64 + 512 * 64 * 2;                               // [B*L0, 64] bf16
+    if (conv0_pack_weights(w, w64, 512, 10, st)) return -1;
+    if (conv0_im2col(wav, cols, B, S, L0, 10, 5, st)) return -1;
+    TcLnGemmArgs g;
+    g.a_mode = A_PLAIN; g.A = cols; g.lda = 64; g.W = w64; g.M = B * L0; g.K = 64; g.batches = 1;
+    g.out = out; g.bias = bias; g.ln_w = ln_w; g.ln_b = ln_b;
+    return tc_gemm_ln_gelu(g, device_sms(), st);
 }
 
 int slsb_op_posconv(int precision, const float* x, const void* W, const float* bias, float* out, void* scratch, int B, int T, int D, int K,

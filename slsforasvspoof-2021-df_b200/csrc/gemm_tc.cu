@@ -49,50 +49,80 @@ struct DevParams {
     int act, out_bf16;
 };
 
-template <int ACT, bool OUT_BF16, bool HAS_RES>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], const DevParams& p, long long out_off, long long res_off,
-                                               int col0, bool row_ok) {
-    float v[32];
-    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        float4 b = __ldg(b4 + j);
-        v[4 * j + 0] = __uint_as_float(acc[4 * j + 0]) + b.x;
-        v[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + b.y;
-        v[4 * j + 2] = __uint_as_float(acc[4 * j + 2]) + b.z;
-        v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + b.w;
-    }
-    if constexpr (ACT == ACT_GELU) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
-    } else if constexpr (ACT == ACT_RELU) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-    }
-    if (!row_ok) return;
+// One warp's share of a tile: kCols accumulator columns of its 32 TMEM lanes (thread == output row).
+// The fp32 residual of chunk c+1 is fetched into registers while chunk c is converted and stored (the strided
+// row-per-thread global reads are latency-, not bandwidth-limited), and the first chunk's residual is requested
+// before the accumulator is even complete.
+template <int ACT, bool OUT_BF16, bool HAS_RES, int kCols>
+__device__ __forceinline__ void epilogue_tile(const DevParams& p, uint32_t taddr, long long out_off, long long res_off, int col_base,
+                                              bool row_ok, uint64_t* full_bar, uint32_t full_parity) {
+    constexpr int kChunks = kCols / 32;
+    float4 rnext[8];
     if constexpr (HAS_RES) {
-        const float4* r4 = reinterpret_cast<const float4*>(p.residual + res_off + col0);
+        if (row_ok) {
+            const float4* r4 = reinterpret_cast<const float4*>(p.residual + res_off + col_base);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rnext[j] = __ldg(r4 + j);
+        }
+    }
+    mbar_wait(full_bar, full_parity);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < kChunks; ++c) {
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(taddr + c * 32, acc);
+        float4 rcur[8];
+        if constexpr (HAS_RES) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rcur[j] = rnext[j];
+            if (row_ok && c + 1 < kChunks) {
+                const float4* r4 = reinterpret_cast<const float4*>(p.residual + res_off + col_base + (c + 1) * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rnext[j] = __ldg(r4 + j);
+            }
+        }
+        const int col0 = col_base + c * 32;
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+        tmem_ld_wait();
+        float v[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            float4 r = __ldg(r4 + j);
-            v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+            const float4 b = __ldg(b4 + j);
+            v[4 * j + 0] = __uint_as_float(acc[4 * j + 0]) + b.x;
+            v[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + b.y;
+            v[4 * j + 2] = __uint_as_float(acc[4 * j + 2]) + b.z;
+            v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + b.w;
         }
-    }
-    if constexpr (OUT_BF16) {
-        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + out_off + col0);
+        if constexpr (ACT == ACT_GELU) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            uint4 w;
-            w.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-            w.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-            w.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-            w.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-            o[j] = w;
+            for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+        } else if constexpr (ACT == ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
         }
-    } else {
-        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_off + col0);
+        if (!row_ok) continue;
+        if constexpr (HAS_RES) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 8; ++j) {
+                v[4 * j + 0] += rcur[j].x; v[4 * j + 1] += rcur[j].y; v[4 * j + 2] += rcur[j].z; v[4 * j + 3] += rcur[j].w;
+            }
+        }
+        if constexpr (OUT_BF16) {
+            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + out_off + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint4 w;
+                w.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                w.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                w.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                w.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                o[j] = w;
+            }
+        } else {
+            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_off + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
     }
 }
 
@@ -137,9 +167,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 int t = tile;
-                const int m_blk = t % p.m_tiles; t /= p.m_tiles;
-                const int n_blk = t % p.n_tiles;
-                const int b = t / p.n_tiles;
+                const int n_blk = t % p.n_tiles; t /= p.n_tiles;      // n fastest: the CTAs running together share one band of A
+                const int m_blk = t % p.m_tiles;
+                const int b = t / p.m_tiles;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Plan::kStage;
@@ -198,37 +228,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             int t = tile;
-            const int m_blk = t % p.m_tiles; t /= p.m_tiles;
-            const int n_blk = t % p.n_tiles;
-            const int b = t / p.n_tiles;
+            const int n_blk = t % p.n_tiles; t /= p.n_tiles;
+            const int m_blk = t % p.m_tiles;
+            const int b = t / p.m_tiles;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int row = m_blk * BLOCK_M + r;
             const bool row_ok = row < p.M;
             const long long out_off = (long long)b * p.out_batch_stride + (long long)row * p.ldc;
             const long long res_off = (long long)b * p.res_batch_stride + (long long)row * p.ldr;
-            mbar_wait(&tmem_full[acc], acc_phase);
-            tc_fence_after();
             const uint32_t taddr0 = tmem_base + (uint32_t(q * 32) << 16) + acc * BLOCK_N + half * kColsPerWarp;
-#pragma unroll 1
-            for (int c = 0; c < kColsPerWarp; c += 32) {
-                uint32_t a[32];
-                tmem_ld_32x32b_x32(taddr0 + c, a);
-                tmem_ld_wait();
-                const int col0 = n_blk * BLOCK_N + half * kColsPerWarp + c;
-                const int sel = p.act * 4 + p.out_bf16 * 2 + (p.residual != nullptr ? 1 : 0);
-                switch (sel) {
-                    case ACT_NONE * 4 + 2 + 0: epilogue_chunk<ACT_NONE, true, false>(a, p, out_off, res_off, col0, row_ok); break;
-                    case ACT_GELU * 4 + 2 + 0: epilogue_chunk<ACT_GELU, true, false>(a, p, out_off, res_off, col0, row_ok); break;
-                    case ACT_NONE * 4 + 0 + 1: epilogue_chunk<ACT_NONE, false, true>(a, p, out_off, res_off, col0, row_ok); break;
-                    case ACT_NONE * 4 + 0 + 0: epilogue_chunk<ACT_NONE, false, false>(a, p, out_off, res_off, col0, row_ok); break;
-                    case ACT_RELU * 4 + 0 + 0: epilogue_chunk<ACT_RELU, false, false>(a, p, out_off, res_off, col0, row_ok); break;
-                    case ACT_GELU * 4 + 0 + 1: epilogue_chunk<ACT_GELU, false, true>(a, p, out_off, res_off, col0, row_ok); break;
-                    case ACT_GELU * 4 + 0 + 0: epilogue_chunk<ACT_GELU, false, false>(a, p, out_off, res_off, col0, row_ok); break;
-                    case ACT_RELU * 4 + 2 + 0: epilogue_chunk<ACT_RELU, true, false>(a, p, out_off, res_off, col0, row_ok); break;
-                    default: break;   // launcher rejects other combinations
-                }
+            const int col_base = n_blk * BLOCK_N + half * kColsPerWarp;
+            const int sel = p.act * 4 + p.out_bf16 * 2 + (p.residual != nullptr ? 1 : 0);
+#define SLSB_EPI(A_, O_, R_) epilogue_tile<A_, O_, R_, kColsPerWarp>(p, taddr0, out_off, res_off, col_base, row_ok, &tmem_full[acc], acc_phase)
+            switch (sel) {
+                case ACT_NONE * 4 + 2 + 0: SLSB_EPI(ACT_NONE, true, false); break;
+                case ACT_GELU * 4 + 2 + 0: SLSB_EPI(ACT_GELU, true, false); break;
+                case ACT_NONE * 4 + 0 + 1: SLSB_EPI(ACT_NONE, false, true); break;
+                case ACT_NONE * 4 + 0 + 0: SLSB_EPI(ACT_NONE, false, false); break;
+                case ACT_RELU * 4 + 0 + 0: SLSB_EPI(ACT_RELU, false, false); break;
+                case ACT_GELU * 4 + 0 + 1: SLSB_EPI(ACT_GELU, false, true); break;
+                case ACT_GELU * 4 + 0 + 0: SLSB_EPI(ACT_GELU, false, false); break;
+                case ACT_RELU * 4 + 2 + 0: SLSB_EPI(ACT_RELU, true, false); break;
+                default: mbar_wait(&tmem_full[acc], acc_phase); break;   // launcher rejects other combinations
             }
+#undef SLSB_EPI
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);

@@ -1,0 +1,290 @@
+// Feature-extractor layer as ONE tensor-core kernel:  out = GELU(LayerNorm_512(A * W^T + bias))  (bf16 out)
+// (wav2vec2.py:785-822: Conv1d -> Fp32LayerNorm over the 512 channels -> GELU, extractor_mode="layer_norm").
+//
+// The CTA tile is 128 rows x all 512 channels, so a whole LayerNorm row lives in one CTA's TMEM (128 lanes x 512 fp32
+// columns = the full 256 KB) and the normalisation + GELU run in the epilogue straight out of TMEM: the pre-norm
+// activations never touch HBM (saves one write + one read of every conv output and six stand-alone LN launches).
+//   * A operand: A_PLAIN ([M, K] bf16; used for conv0 after a hi/lo bf16 split of the raw audio, see frontend.cu)
+//                or A_CONV (implicit GEMM over channels-last activations through a 4-D tensor map, see gemm_tc.cu).
+//   * B operand: W [512, K] bf16, loaded as two 256-row TMA boxes per k-block; two tcgen05.mma (N = 256) per UMMA_K step.
+//   * 2-stage smem ring (80 KB / stage); the single 512-column accumulator means MMA and epilogue of one CTA alternate.
+//   * epilogue: 8 warps, thread == row; pass 1 reads TMEM for sum / sum-of-squares (two column halves combine through
+//     smem), pass 2 re-reads TMEM, normalises, applies affine + GELU and stores bf16.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace slsb {
+namespace {
+
+constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16, NCH = 512;
+constexpr int kStages = 2;
+constexpr int kStageA = BLOCK_M * BLOCK_K * 2;          // 16 KB
+constexpr int kStageB = NCH * BLOCK_K * 2;              // 64 KB
+constexpr int kStage = kStageA + kStageB;
+constexpr int kPartOffset = kStages * kStage;           // float2 part[2 buffers][2 halves][128 rows]
+constexpr int kBarOffset = kPartOffset + 2 * 2 * 128 * 8;
+constexpr int kSmemBytes = kBarOffset + 128 + 1024;
+constexpr int kThreads = 384;
+
+struct LnDev {
+    int M, K, batches, m_tiles;
+    int conv_cin, conv_stride;
+    bf16* out; long long out_batch_stride;
+    const float* bias; const float* ln_w; const float* ln_b;
+    float eps;
+};
+
+template <int A_MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const LnDev p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float2* part = reinterpret_cast<float2*>(smem + kPartOffset);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kBarOffset);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full = empty_bar + kStages;
+    uint64_t* tmem_empty = tmem_full + 1;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = p.batches * p.m_tiles;
+    const int num_kb = p.K / BLOCK_K;
+
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full, 1); mbar_init(tmem_empty, 8);
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc<512>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile % p.m_tiles, b = tile / p.m_tiles;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * kStage;
+                    uint8_t* sb = sa + kStageA;
+                    mbar_expect_tx(&full_bar[stage], kStage);
+                    if constexpr (A_MODE == A_PLAIN) {
+                        tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+                    } else {
+                        const int k0 = kb * BLOCK_K;
+                        const int tap = k0 / p.conv_cin, c = k0 - tap * p.conv_cin;
+                        tma_load_4d(sa, &tmap_a, &full_bar[stage], c, tap % p.conv_stride, m_blk * BLOCK_M + tap / p.conv_stride, b);
+                    }
+                    tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, 0);
+                    tma_load_2d(sb + kStageB / 2, &tmap_b, &full_bar[stage], kb * BLOCK_K, 256);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, 256);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                mbar_wait(tmem_empty, (it & 1) ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * kStage);
+                    const uint32_t sb = sa + kStageA;
+                    const uint64_t da = make_smem_desc_sw128(sa, 0, 1024);
+                    const uint64_t db0 = make_smem_desc_sw128(sb, 0, 1024);
+                    const uint64_t db1 = make_smem_desc_sw128(sb + kStageB / 2, 0, 1024);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+                        tc_mma_f16(tmem_base, da + uint64_t(k * 2), db0 + uint64_t(k * 2), idesc, accum);
+                        tc_mma_f16(tmem_base + 256, da + uint64_t(k * 2), db1 + uint64_t(k * 2), idesc, accum);
+                    }
+                    tc_commit(&empty_bar[stage]);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tmem_full);
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3, half = (warp - 4) >> 2;
+        const int r = q * 32 + lane;
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + half * 256;
+        const int col_base = half * 256;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int m_blk = tile % p.m_tiles, b = tile / p.m_tiles;
+            const int row = m_blk * BLOCK_M + r;
+            const bool row_ok = row < p.M;
+            mbar_wait(tmem_full, it & 1);
+            tc_fence_after();
+            // pass 1: statistics over this warp's 256 columns
+            float s = 0.f, ss = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 8; ++c) {
+                uint32_t acc[32];
+                tmem_ld_32x32b_x32(taddr + c * 32, acc);
+                const float4* b4 = reinterpret_cast<const float4*>(p.bias + col_base + c * 32);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 bb = __ldg(b4 + j);
+                    const float v0 = __uint_as_float(acc[4 * j + 0]) + bb.x, v1 = __uint_as_float(acc[4 * j + 1]) + bb.y;
+                    const float v2 = __uint_as_float(acc[4 * j + 2]) + bb.z, v3 = __uint_as_float(acc[4 * j + 3]) + bb.w;
+                    s += (v0 + v1) + (v2 + v3);
+                    ss = fmaf(v0, v0, ss); ss = fmaf(v1, v1, ss); ss = fmaf(v2, v2, ss); ss = fmaf(v3, v3, ss);
+                }
+            }
+            float2* pbuf = part + (it & 1) * 256;
+            pbuf[half * 128 + r] = make_float2(s, ss);
+            asm volatile("bar.sync 1, 256;" ::: "memory");            // the 8 epilogue warps only
+            const float2 other = pbuf[(half ^ 1) * 128 + r];
+            const float mean = (s + other.x) * (1.0f / NCH);
+            const float var = fmaxf((ss + other.y) * (1.0f / NCH) - mean * mean, 0.0f);
+            const float rstd = rsqrtf(var + p.eps);
+            // pass 2: normalise + affine + GELU + store
+            bf16* orow = p.out + (long long)b * p.out_batch_stride + (long long)row * NCH + col_base;
+#pragma unroll 1
+            for (int c = 0; c < 8; ++c) {
+                uint32_t acc[32];
+                tmem_ld_32x32b_x32(taddr + c * 32, acc);
+                const float4* b4 = reinterpret_cast<const float4*>(p.bias + col_base + c * 32);
+                const float4* g4 = reinterpret_cast<const float4*>(p.ln_w + col_base + c * 32);
+                const float4* h4 = reinterpret_cast<const float4*>(p.ln_b + col_base + c * 32);
+                tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 bb = __ldg(b4 + j), g = __ldg(g4 + j), h = __ldg(h4 + j);
+                    v[4 * j + 0] = gelu_fast(fmaf((__uint_as_float(acc[4 * j + 0]) + bb.x - mean) * rstd, g.x, h.x));
+                    v[4 * j + 1] = gelu_fast(fmaf((__uint_as_float(acc[4 * j + 1]) + bb.y - mean) * rstd, g.y, h.y));
+                    v[4 * j + 2] = gelu_fast(fmaf((__uint_as_float(acc[4 * j + 2]) + bb.z - mean) * rstd, g.z, h.z));
+                    v[4 * j + 3] = gelu_fast(fmaf((__uint_as_float(acc[4 * j + 3]) + bb.w - mean) * rstd, g.w, h.w));
+                }
+                if (row_ok) {
+                    uint4* o = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 w;
+                        w.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]); w.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                        w.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); w.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                        o[j] = w;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+template <int A_MODE>
+int launch_ln(const CUtensorMap& ta, const CUtensorMap& tb, const LnDev& dp, int num_sms, cudaStream_t stream) {
+    static bool configured = false;
+    auto kern = tc_gemm_ln_kernel<A_MODE>;
+    if (!configured) {
+        SLSB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        configured = true;
+    }
+    const int tiles = dp.batches * dp.m_tiles;
+    kern<<<tiles < num_sms ? tiles : num_sms, kThreads, kSmemBytes, stream>>>(ta, tb, dp);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// raw audio -> hi/lo bf16 im2col rows for conv0: [x_hi(10) 0.. | x_hi(10) 0.. | x_lo(10) 0.. | 0 (16)]
+__global__ void conv0_im2col_kernel(const float* __restrict__ wav, bf16* __restrict__ out, int S, int L0, int k, int stride, long long rows) {
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    const int b = (int)(row / L0), f = (int)(row - (long long)b * L0);
+    const float* x = wav + (long long)b * S + (long long)f * stride;
+    __align__(16) bf16 v[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = __float2bfloat16_rn(0.f);
+    for (int t = 0; t < k; ++t) {
+        const float xv = __ldg(x + t);
+        const bf16 hi = __float2bfloat16_rn(xv);
+        const bf16 lo = __float2bfloat16_rn(xv - __bfloat162float(hi));
+        v[t] = hi; v[16 + t] = hi; v[32 + t] = lo;
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + row * 64);
+    const uint4* s4 = reinterpret_cast<const uint4*>(v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = s4[i];
+}
+
+// conv0 weights [C, k] fp32 -> [C, 64] bf16: [w_hi | w_lo | w_hi | 0] so that A.W^T = x_hi w_hi + x_hi w_lo + x_lo w_hi
+__global__ void conv0_pack_w_kernel(const float* __restrict__ w, bf16* __restrict__ out, int C, int k) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    for (int i = 0; i < 64; ++i) out[c * 64 + i] = __float2bfloat16_rn(0.f);
+    for (int t = 0; t < k; ++t) {
+        const float wv = w[c * k + t];
+        const bf16 hi = __float2bfloat16_rn(wv);
+        const bf16 lo = __float2bfloat16_rn(wv - __bfloat162float(hi));
+        out[c * 64 + t] = hi; out[c * 64 + 16 + t] = lo; out[c * 64 + 32 + t] = hi;
+    }
+}
+
+}  // namespace
+
+int tc_gemm_ln_gelu(const TcLnGemmArgs& g, int num_sms, cudaStream_t stream) {
+    if (g.N != NCH) { set_error("tc_gemm_ln_gelu: N must be 512 (got %d)", g.N); return -1; }
+    if (g.K % BLOCK_K != 0 || g.K <= 0) { set_error("tc_gemm_ln_gelu: K=%d must be a positive multiple of 64", g.K); return -1; }
+    if (g.M <= 0 || g.batches <= 0) return 0;
+    LnDev dp{};
+    dp.M = g.M; dp.K = g.K; dp.batches = g.batches; dp.m_tiles = (g.M + BLOCK_M - 1) / BLOCK_M;
+    dp.conv_cin = g.conv_cin; dp.conv_stride = g.conv_stride;
+    dp.out = static_cast<bf16*>(g.out); dp.out_batch_stride = g.out_batch_stride;
+    dp.bias = g.bias; dp.ln_w = g.ln_w; dp.ln_b = g.ln_b; dp.eps = g.eps;
+    CUtensorMap ta, tb;
+    {
+        uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)NCH};
+        uint64_t strides[1] = {(uint64_t)g.K * 2};
+        uint32_t box[2] = {BLOCK_K, 256};
+        if (encode_tmap_bf16(&tb, g.W, 2, dims, strides, box)) return -1;
+    }
+    if (g.a_mode == A_PLAIN) {
+        uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.M};
+        uint64_t strides[1] = {(uint64_t)g.lda * 2};
+        uint32_t box[2] = {BLOCK_K, BLOCK_M};
+        if (encode_tmap_bf16(&ta, g.A, 2, dims, strides, box)) return -1;
+        return launch_ln<A_PLAIN>(ta, tb, dp, num_sms, stream);
+    }
+    const uint64_t C = g.conv_cin, s = g.conv_stride, Lin = g.conv_lin;
+    uint64_t dims[4] = {C, s, (Lin + s - 1) / s, (uint64_t)g.batches};
+    uint64_t strides[3] = {C * 2, s * C * 2, Lin * C * 2};
+    uint32_t box[4] = {BLOCK_K, 1, BLOCK_M, 1};
+    if (encode_tmap_bf16(&ta, g.A, 4, dims, strides, box)) return -1;
+    return launch_ln<A_CONV>(ta, tb, dp, num_sms, stream);
+}
+
+int conv0_im2col(const float* wav, void* out, int B, int S, int L0, int k, int stride, cudaStream_t stream) {
+    if (k > 16) { set_error("conv0_im2col: k=%d > 16", k); return -1; }
+    const long long rows = (long long)B * L0;
+    conv0_im2col_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, stream>>>(wav, static_cast<bf16*>(out), S, L0, k, stride, rows);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int conv0_pack_weights(const float* w, void* out, int C, int k, cudaStream_t stream) {
+    conv0_pack_w_kernel<<<(C + 127) / 128, 128, 0, stream>>>(w, static_cast<bf16*>(out), C, k);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace slsb

@@ -170,15 +170,17 @@ __global__ void window_votes_kernel(const float* __restrict__ acts, const float*
     votes[((long long)b * T + t) * D + f] = v;
 }
 
-// ---- classifier: LN(D) -> Linear(D, Hd) -> ReLU -> Linear(Hd, 2) -> log_softmax ; one block per utterance
-__global__ void __launch_bounds__(256) classifier_kernel(const float* __restrict__ pooled, int D, int Hd, const float* __restrict__ ln_w,
-                                                         const float* __restrict__ ln_b, const float* __restrict__ w1, const float* __restrict__ b1,
-                                                         const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ logprob) {
-    extern __shared__ float cls_smem[];
-    float* xs = cls_smem;            // D
-    float* hs = cls_smem + D;        // Hd
+// ---- classifier: LN(D) -> Linear(D, Hd) -> ReLU -> Linear(Hd, 2) -> log_softmax
+// stage 1: grid (Hd / 32, B): every block normalises its utterance's pooled row (cheap, redundant) and computes 32 hidden
+// units, one warp per unit with coalesced weight reads; stage 2: one warp per utterance.
+constexpr int CLS_UNITS = 32;
+__global__ void __launch_bounds__(256) classifier_hidden_kernel(const float* __restrict__ pooled, int D, int Hd, const float* __restrict__ ln_w,
+                                                                const float* __restrict__ ln_b, const float* __restrict__ w1,
+                                                                const float* __restrict__ b1, float* __restrict__ hidden) {
+    extern __shared__ float cls_smem[];   // D
+    float* xs = cls_smem;
     __shared__ float red[8];
-    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* x = pooled + (long long)b * D;
     float s = 0.f;
     for (int i = threadIdx.x; i < D; i += 256) { const float v = x[i]; xs[i] = v; s += v; }
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(256) classifier_kernel(const float* __restrict
     const float rstd = 1.0f / sqrtf(var / (float)D + 1e-5f);
     for (int i = threadIdx.x; i < D; i += 256) xs[i] = (xs[i] - mean) * rstd * ln_w[i] + ln_b[i];
     __syncthreads();
-    for (int u = warp; u < Hd; u += 8) {
+    for (int u = blockIdx.x * CLS_UNITS + warp; u < min(Hd, (int)(blockIdx.x + 1) * CLS_UNITS); u += 8) {
         const float* wr = w1 + (long long)u * D;
         float a = 0.f;
         for (int i = lane * 4; i < D; i += 128) {
@@ -208,18 +210,20 @@ __global__ void __launch_bounds__(256) classifier_kernel(const float* __restrict
             a = fmaf(wv.x, xv.x, a); a = fmaf(wv.y, xv.y, a); a = fmaf(wv.z, xv.z, a); a = fmaf(wv.w, xv.w, a);
         }
         a = warp_sum(a);
-        if (lane == 0) hs[u] = fmaxf(a + b1[u], 0.f);
+        if (lane == 0) hidden[(long long)b * Hd + u] = fmaxf(a + b1[u], 0.f);
     }
-    __syncthreads();
-    if (warp == 0) {
-        float l0 = 0.f, l1 = 0.f;
-        for (int i = lane; i < Hd; i += 32) { l0 = fmaf(w2[i], hs[i], l0); l1 = fmaf(w2[Hd + i], hs[i], l1); }
-        l0 = warp_sum(l0) + b2[0]; l1 = warp_sum(l1) + b2[1];
-        if (lane == 0) {
-            const float m = fmaxf(l0, l1);
-            const float lse = m + logf(expf(l0 - m) + expf(l1 - m));
-            logprob[b * 2 + 0] = l0 - lse; logprob[b * 2 + 1] = l1 - lse;
-        }
+}
+__global__ void classifier_out_kernel(const float* __restrict__ hidden, int Hd, const float* __restrict__ w2, const float* __restrict__ b2,
+                                      float* __restrict__ logprob) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const float* hs = hidden + (long long)b * Hd;
+    float l0 = 0.f, l1 = 0.f;
+    for (int i = lane; i < Hd; i += 32) { l0 = fmaf(w2[i], hs[i], l0); l1 = fmaf(w2[Hd + i], hs[i], l1); }
+    l0 = warp_sum(l0) + b2[0]; l1 = warp_sum(l1) + b2[1];
+    if (lane == 0) {
+        const float m = fmaxf(l0, l1);
+        const float lse = m + logf(expf(l0 - m) + expf(l1 - m));
+        logprob[b * 2 + 0] = l0 - lse; logprob[b * 2 + 1] = l1 - lse;
     }
 }
 
@@ -386,9 +390,11 @@ int window_votes(const float* acts, const float* sums, const float* thr_w, const
     return 0;
 }
 int classifier_head(const float* pooled, int B, int D, int Hd, const float* ln_w, const float* ln_b, const float* w1, const float* b1,
-                    const float* w2, const float* b2, float* logprob, cudaStream_t stream) {
+                    const float* w2, const float* b2, float* hidden, float* logprob, cudaStream_t stream) {
     if (D % 128 != 0) { set_error("classifier: D=%d must be a multiple of 128", D); return -1; }
-    classifier_kernel<<<B, 256, (D + Hd) * sizeof(float), stream>>>(pooled, D, Hd, ln_w, ln_b, w1, b1, w2, b2, logprob);
+    dim3 grid((Hd + CLS_UNITS - 1) / CLS_UNITS, B);
+    classifier_hidden_kernel<<<grid, 256, D * sizeof(float), stream>>>(pooled, D, Hd, ln_w, ln_b, w1, b1, hidden);
+    classifier_out_kernel<<<B, 32, 0, stream>>>(hidden, Hd, w2, b2, logprob);
     SLSB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -28,6 +28,22 @@ struct TcGemmArgs {
 };
 int tc_gemm(const TcGemmArgs& g, int num_sms, cudaStream_t stream);
 
+// ---------------------------------------------------------------- tcgen05 GEMM + LayerNorm(512) + GELU epilogue (gemm_tc_ln.cu)
+struct TcLnGemmArgs {
+    int a_mode = A_PLAIN;
+    const void* A = nullptr; long long lda = 0;
+    const void* W = nullptr;                 // bf16 [512, K]
+    int M = 0, N = 512, K = 0, batches = 1;
+    int conv_cin = 0, conv_stride = 0, conv_lin = 0;
+    void* out = nullptr; long long out_batch_stride = 0;   // bf16 [.., 512]
+    const float* bias = nullptr; const float* ln_w = nullptr; const float* ln_b = nullptr;
+    float eps = 1e-5f;
+};
+int tc_gemm_ln_gelu(const TcLnGemmArgs& g, int num_sms, cudaStream_t stream);
+// conv0 on tensor cores: raw audio -> hi/lo-split bf16 im2col rows [B*L0, 64]; weights [C, k] -> [C, 64] (hi | lo | hi | 0)
+int conv0_im2col(const float* wav, void* out, int B, int S, int L0, int k, int stride, cudaStream_t stream);
+int conv0_pack_weights(const float* w, void* out, int C, int k, cudaStream_t stream);
+
 // ---------------------------------------------------------------- fp32 SIMT GEMM (gemm_simt.cu)
 // C[z][m][n] = act(sum_k A[z][m][k] * W[zw][n][k] + bias[n_off + n]) (+ residual); A/W/out element types selectable.
 struct SimtGemmArgs {
@@ -90,7 +106,7 @@ int votes_densify(const float* acts, const float* votes, const float* thr, const
 int votes_mean_pool(const float* acts, const float* votes, const float* thr, const int* tie_cut, float* pooled, int B, int T, int D, const int* lens, cudaStream_t stream);
 // classifier: LN(D) -> Linear(D,Hd) -> ReLU -> Linear(Hd,2) -> log_softmax   (model.py:183-189, :246-247)
 int classifier_head(const float* pooled, int B, int D, int Hd, const float* ln_w, const float* ln_b, const float* w1, const float* b1,
-                    const float* w2, const float* b2, float* logprob, cudaStream_t stream);
+                    const float* w2, const float* b2, float* hidden /*[B, Hd] scratch*/, float* logprob, cudaStream_t stream);
 // mean over valid frames of a [B, T, D] fp32 stream (use_sae=False / use_sparse_features=False pooling)
 int mean_pool_frames(const float* x, float* pooled, int B, int T, int D, const int* lens, cudaStream_t stream);
 // SLS (model_backup.py:186-202 + upstream classifier)

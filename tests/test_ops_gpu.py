@@ -10,6 +10,10 @@ from helpers import P, ok, report, stream
 
 pytestmark = pytest.mark.gpu
 
+# the PyTorch references must be true fp32: cuDNN / cuBLAS default to TF32 for fp32 convs and matmuls on this GPU
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
 FP32, BF16 = 0, 1
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 
@@ -135,6 +139,40 @@ def test_conv0_ln_gelu(lib, cuda, out_bf16):
     y = F.conv1d(wav.unsqueeze(1), w.unsqueeze(1), b, stride=5).transpose(1, 2)
     ref = F.gelu(F.layer_norm(y, (C,), g, be, 1e-5))
     report(f"conv0 bf16={out_bf16}", out, ref, atol=1e-2 if out_bf16 else 2e-5, rtol=8e-3 if out_bf16 else 1e-5)
+
+
+def test_conv0_tensor_core_hi_lo_split(lib, cuda):
+    """conv0 + LN + GELU as ONE tcgen05 kernel; the raw audio and the taps are split into bf16 hi + lo parts so the
+    products keep ~16 mantissa bits (x_hi w_hi + x_hi w_lo + x_lo w_hi)."""
+    B, S, C = 3, 16000, 512
+    wav = _rand((B, S), 45)
+    w, b = _rand((C, 10), 46, math.sqrt(2.0 / 10)), _rand((C,), 47, 0.05)
+    g, be = 1 + _rand((C,), 48, 0.1), _rand((C,), 49, 0.05)
+    L0 = (S - 10) // 5 + 1
+    out = torch.empty(B, L0, C, device=cuda, dtype=torch.bfloat16)
+    scratch = torch.zeros(65536 + B * L0 * 128 + (8 << 20), device=cuda, dtype=torch.uint8)
+    ok(lib, lib.slsb_op_conv0_tc(P(wav), P(w), P(b), P(g), P(be), P(out), P(scratch), B, S, stream()), "conv0 tc")
+    y = F.conv1d(wav.unsqueeze(1), w.unsqueeze(1), b, stride=5).transpose(1, 2)
+    ref = F.gelu(F.layer_norm(y, (C,), g, be, 1e-5))
+    report("conv0_tc", out, ref, atol=1e-2, rtol=8e-3)           # bf16 output rounding dominates
+    # against the bf16-rounded fp32 result the agreement is (almost) bit-level: the split loses only ~2^-17
+    assert float((out.float() - ref.bfloat16().float()).abs().max()) <= 2 ** -6
+
+
+@pytest.mark.parametrize("B,Lin,k,s", [(2, 1291, 3, 2), (3, 403, 2, 2), (2, 6459, 3, 2), (5, 130, 3, 2)])
+def test_conv_ln_gelu_fused(lib, cuda, B, Lin, k, s):
+    C = N = 512
+    x = _rand((B, Lin, C), 23).bfloat16()
+    w = _rand((N, C, k), 24, 1.0 / math.sqrt(C * k)).bfloat16()
+    b = _rand((N,), 25, 0.3)
+    g, be = 1 + _rand((C,), 26, 0.1), _rand((C,), 27, 0.05)
+    Lout = (Lin - k) // s + 1
+    wp = w.permute(0, 2, 1).reshape(N, k * C).contiguous()
+    out = torch.empty(B, Lout, N, device=cuda, dtype=torch.bfloat16)
+    ok(lib, lib.slsb_op_conv_ln_gelu(P(x), P(wp), P(b), P(g), P(be), P(out), B, Lin, C, k, s, stream()), "conv ln gelu")
+    y = F.conv1d(x.float().transpose(1, 2), w.float(), b, stride=s).transpose(1, 2)
+    ref = F.gelu(F.layer_norm(y, (C,), g, be, 1e-5))
+    report(f"conv_ln_gelu B={B} Lin={Lin} k={k}", out, ref, atol=1e-2, rtol=8e-3)
 
 
 @pytest.mark.parametrize("C", [512, 1024])
