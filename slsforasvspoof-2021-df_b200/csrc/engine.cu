@@ -120,7 +120,7 @@ struct slsb_engine {
     int64_t launches = 0;
     // workspace
     Buf fe[2], lnbuf, qkv, attn, ffn, xmid, xfinal, xc, xpad, acts, encoded, sums, votes, thr, cut, thr_w, cut_w, pooled, logprob,
-        sls_w, sls_in, sls_part, zeros, scratch, flens, wav_stage, lens_stage, score_stage, recon, tmp_bf16, im2col, conv0_w64;
+        sls_w, sls_in, sls_part, zeros, scratch, flens, wav_stage, lens_stage, score_stage, recon, tmp_bf16, im2col, conv0_w64, ybuf;
     std::vector<Buf> X;
     // last call
     int B = 0, S = 0, T = 0, prec = 0, head = 0;
@@ -376,6 +376,37 @@ static int run_trunk(slsb_engine* e, const float* wav, const int* slens, int B, 
     if (pos_conv(e, bf, e->xmid.as<float>(), bf ? (const void*)W16("pos.w") : (const void*)W32("pos.w"), W32("pos.b"), e->X[0].as<float>(),
                  e->xpad.p, B, T, D, c.pos_kernel, c.pos_groups, flens, st)) return -1;
     // 4. transformer layers, pre-LN (wav2vec2.py:1044-1062)
+    if (bf) {
+        // bf16: the GEMMs write their branch outputs in bf16 (TMA-store epilogue, no residual traffic inside the GEMM); the fp32
+        // residual stream is advanced by the LayerNorm kernels, which are coalesced and HBM-bound anyway:
+        //   LN1_l : X_l = xmid_{l-1} + fc2_{l-1}   (written as layer result l-1), lnbuf = LN(X_l)
+        //   LN2_l : xmid = X_l + out_proj_l,        lnbuf = LN(xmid)
+        if (e->ybuf.reserve((size_t)M * D * 2)) return -1;
+        for (int l = 0; l < c.n_layers; ++l) {
+            const std::string p = "L" + std::to_string(l);
+            LnArgs a;
+            a.out = e->lnbuf.p; a.out_bf16 = 1; a.w = W32(p + ".ln1.w"); a.b = W32(p + ".ln1.b"); a.rows = M; a.C = D;
+            if (l == 0) a.in = e->X[0].p;
+            else { a.in = e->xmid.p; a.add = e->ybuf.p; a.sum_out = e->X[l].as<float>(); }
+            LAUNCH(layernorm(a, st));
+            if (linear(e, true, e->lnbuf.p, D, p + ".qkv.w", 3 * D, D, M, W32(p + ".qkv.b"), nullptr, 0, e->qkv.p, 3 * D, 1, ACT_NONE, st, PK_ENC_QKV)) return -1;
+            if (attention(e, true, e->qkv.p, e->attn.p, B, T, H, flens, st)) return -1;
+            if (linear(e, true, e->attn.p, D, p + ".out.w", D, D, M, W32(p + ".out.b"), nullptr, 0, e->ybuf.p, D, 1, ACT_NONE, st, PK_ENC_OUT)) return -1;
+            LnArgs a2;
+            a2.in = e->X[l].p; a2.add = e->ybuf.p; a2.sum_out = e->xmid.as<float>();
+            a2.out = e->lnbuf.p; a2.out_bf16 = 1; a2.w = W32(p + ".ln2.w"); a2.b = W32(p + ".ln2.b"); a2.rows = M; a2.C = D;
+            LAUNCH(layernorm(a2, st));
+            if (linear(e, true, e->lnbuf.p, D, p + ".fc1.w", F, D, M, W32(p + ".fc1.b"), nullptr, 0, e->ffn.p, F, 1, ACT_GELU, st, PK_ENC_FC1)) return -1;
+            if (linear(e, true, e->ffn.p, F, p + ".fc2.w", D, F, M, W32(p + ".fc2.b"), nullptr, 0, e->ybuf.p, D, 1, ACT_NONE, st, PK_ENC_FC2)) return -1;
+        }
+        // 5. X_n = xmid + fc2_{n-1}; final LayerNorm on x only (wav2vec2.py:905-906); xc = x - b_dec feeds the SAE (model.py:70)
+        LnArgs a;
+        a.in = e->xmid.p; a.add = e->ybuf.p; a.sum_out = e->X[c.n_layers].as<float>();
+        a.out = e->xfinal.p; a.w = W32("enc_ln.w"); a.b = W32("enc_ln.b"); a.rows = M; a.C = D;
+        if (want_xc && c.sae_dict > 0) { a.out2 = e->xc.p; a.out2_bf16 = 1; a.sub = W32("sae.b_dec"); }
+        LAUNCH(layernorm(a, st));
+        return 0;
+    }
     for (int l = 0; l < c.n_layers; ++l) {
         const std::string p = "L" + std::to_string(l);
         float* xin = e->X[l].as<float>();
@@ -535,7 +566,7 @@ int slsb_destroy(slsb_engine* e) {
     for (auto& kv : e->w) { if (kv.second.f32) cudaFree(kv.second.f32); if (kv.second.b16) cudaFree(kv.second.b16); }
     Buf* bufs[] = {&e->fe[0], &e->fe[1], &e->lnbuf, &e->qkv, &e->attn, &e->ffn, &e->xmid, &e->xfinal, &e->xc, &e->xpad, &e->acts, &e->encoded,
                    &e->sums, &e->votes, &e->thr, &e->cut, &e->thr_w, &e->cut_w, &e->pooled, &e->logprob, &e->sls_w, &e->sls_in, &e->sls_part,
-                   &e->zeros, &e->scratch, &e->flens, &e->wav_stage, &e->lens_stage, &e->score_stage, &e->recon, &e->tmp_bf16, &e->im2col, &e->conv0_w64};
+                   &e->zeros, &e->scratch, &e->flens, &e->wav_stage, &e->lens_stage, &e->score_stage, &e->recon, &e->tmp_bf16, &e->im2col, &e->conv0_w64, &e->ybuf};
     for (Buf* b : bufs) b->release();
     for (auto& b : e->X) b.release();
     delete e;

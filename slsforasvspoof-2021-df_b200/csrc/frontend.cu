@@ -92,7 +92,8 @@ template <> __device__ __forceinline__ void store4<bf16>(bf16* p, const float (&
 }
 
 template <typename TI, typename TO, typename TO2, int NV, bool GELU, bool EXACT>
-__global__ void __launch_bounds__(256) ln_kernel(const TI* __restrict__ in, TO* __restrict__ out, TO2* __restrict__ out2,
+__global__ void __launch_bounds__(256) ln_kernel(const TI* __restrict__ in, const bf16* __restrict__ add, float* __restrict__ sum_out,
+                                                 TO* __restrict__ out, TO2* __restrict__ out2,
                                                  const float* __restrict__ sub, const float* __restrict__ w, const float* __restrict__ b,
                                                  long long rows, float eps) {
     constexpr int C = NV * 128;
@@ -105,6 +106,12 @@ __global__ void __launch_bounds__(256) ln_kernel(const TI* __restrict__ in, TO* 
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         load4<TI>(x + (i * 32 + lane) * 4, v[i]);
+        if (add) {      // residual stream + bf16 branch output (out_proj / fc2), summed in fp32 and optionally written back
+            float y[4];
+            load4<bf16>(add + row * C + (i * 32 + lane) * 4, y);
+            v[i][0] += y[0]; v[i][1] += y[1]; v[i][2] += y[2]; v[i][3] += y[3];
+            if (sum_out) store4<float>(sum_out + row * C + (i * 32 + lane) * 4, v[i]);
+        }
         s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
     }
     const float mean = warp_sum(s) * (1.0f / C);
@@ -138,11 +145,12 @@ template <typename TI, typename TO, typename TO2, int NV>
 int ln_launch(const LnArgs& a, cudaStream_t stream) {
     const unsigned grid = (unsigned)((a.rows + 7) / 8);
     const TI* in = static_cast<const TI*>(a.in); TO* out = static_cast<TO*>(a.out); TO2* out2 = static_cast<TO2*>(a.out2);
+    const bf16* add = static_cast<const bf16*>(a.add);
     if (a.gelu) {
-        if (a.exact_gelu) ln_kernel<TI, TO, TO2, NV, true, true><<<grid, 256, 0, stream>>>(in, out, out2, a.sub, a.w, a.b, a.rows, a.eps);
-        else ln_kernel<TI, TO, TO2, NV, true, false><<<grid, 256, 0, stream>>>(in, out, out2, a.sub, a.w, a.b, a.rows, a.eps);
+        if (a.exact_gelu) ln_kernel<TI, TO, TO2, NV, true, true><<<grid, 256, 0, stream>>>(in, add, a.sum_out, out, out2, a.sub, a.w, a.b, a.rows, a.eps);
+        else ln_kernel<TI, TO, TO2, NV, true, false><<<grid, 256, 0, stream>>>(in, add, a.sum_out, out, out2, a.sub, a.w, a.b, a.rows, a.eps);
     } else {
-        ln_kernel<TI, TO, TO2, NV, false, true><<<grid, 256, 0, stream>>>(in, out, out2, a.sub, a.w, a.b, a.rows, a.eps);
+        ln_kernel<TI, TO, TO2, NV, false, true><<<grid, 256, 0, stream>>>(in, add, a.sum_out, out, out2, a.sub, a.w, a.b, a.rows, a.eps);
     }
     SLSB_CUDA_CHECK(cudaGetLastError());
     return 0;

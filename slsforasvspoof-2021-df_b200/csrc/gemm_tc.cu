@@ -17,6 +17,8 @@
 //             [m0 + t, m0 + t + 128) x channels [64 g, 64 g + 64) of the zero-padded [B, T+128, 1024] stream.
 #include "common.cuh"
 #include "kernels.h"
+#include <cstdlib>
+#include <cstring>
 
 namespace slsb {
 
@@ -33,8 +35,11 @@ template <int BLOCK_N> struct SmemPlan {
     static constexpr int kStageB = BLOCK_N * BLOCK_K * 2;
     static constexpr int kStage = kStageA + kStageB;
     static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
-    static constexpr int kBarOffset = kStages * kStage;
-    static constexpr int kBytes = kBarOffset + 256 /*barriers + tmem ptr*/ + 1024 /*alignment slack*/;
+    static constexpr int kStoreOffset = kStages * kStage;           // 2 x [128 rows x 64 bf16] SWIZZLE_128B staging tiles for TMA stores
+    static constexpr int kStoreBytes = (BLOCK_N >= 128) ? 2 * 16384 : 0;
+    static constexpr int kBiasOffset = kStoreOffset + kStoreBytes;    // this tile's bias slice
+    static constexpr int kBarOffset = kBiasOffset + BLOCK_N * 4;
+    static constexpr int kBytes = kBarOffset + 256 /*barriers + tmem ptr*/;
 };
 
 struct DevParams {
@@ -47,6 +52,8 @@ struct DevParams {
     const float* residual;
     long long ldr, res_batch_stride;
     int act, out_bf16;
+    int tma_store;     // bf16 output leaves through smem staging + cp.async.bulk.tensor stores
+    int debug_flags;   // bit0: epilogue does everything except the global stores / residual loads (mainloop ceiling measurements)
 };
 
 // One warp's share of a tile: kCols accumulator columns of its 32 TMEM lanes (thread == output row).
@@ -57,6 +64,7 @@ template <int ACT, bool OUT_BF16, bool HAS_RES, int kCols>
 __device__ __forceinline__ void epilogue_tile(const DevParams& p, uint32_t taddr, long long out_off, long long res_off, int col_base,
                                               bool row_ok, uint64_t* full_bar, uint32_t full_parity) {
     constexpr int kChunks = kCols / 32;
+    if (p.debug_flags & 1) row_ok = false;
     float4 rnext[8];
     if constexpr (HAS_RES) {
         if (row_ok) {
@@ -126,15 +134,83 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, uint32_t taddr
     }
 }
 
+// bf16 output through shared memory + TMA store: each column half (4 warps = 128 rows) converts 64 columns at a time into a
+// SWIZZLE_128B staging tile and one thread issues a cp.async.bulk.tensor store.  Rows past M / L_out are clipped by the tensor
+// map, global writes are full 128-byte lines, and the L1/LSU never sees the 128 different rows of a tile.
+template <int ACT, int kCols, bool kConvOut>
+__device__ __forceinline__ void epilogue_tile_tma(const DevParams& p, const CUtensorMap* tmap_out, uint32_t taddr, uint8_t* stage_tile,
+                                                  const float* bias_s, int half, int r, int col_base, int row0, int b,
+                                                  uint64_t* full_bar, uint32_t full_parity, uint64_t* empty_bar) {
+    constexpr int kGroups = kCols / 64;
+    const int bar_id = 1 + half;
+    const bool issuer = r == 0;
+    mbar_wait(full_bar, full_parity);
+    tc_fence_after();
+#pragma unroll 1
+    for (int g = 0; g < kGroups; ++g) {
+        uint32_t acc[2][32];
+        tmem_ld_32x32b_x32(taddr + g * 64, acc[0]);
+        tmem_ld_32x32b_x32(taddr + g * 64 + 32, acc[1]);
+        if (issuer) tma_store_wait_read<0>();                        // the previous store no longer reads the staging tile
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        tmem_ld_wait();
+        if (g == kGroups - 1) {                                      // accumulator fully read: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if ((r & 31) == 0) mbar_arrive(empty_bar);
+        }
+        uint8_t* srow = stage_tile + r * 128;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float* bs = bias_s + half * kCols + g * 64 + h * 32;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 bb = *reinterpret_cast<const float4*>(bs + 4 * j);
+                v[4 * j + 0] = __uint_as_float(acc[h][4 * j + 0]) + bb.x;
+                v[4 * j + 1] = __uint_as_float(acc[h][4 * j + 1]) + bb.y;
+                v[4 * j + 2] = __uint_as_float(acc[h][4 * j + 2]) + bb.z;
+                v[4 * j + 3] = __uint_as_float(acc[h][4 * j + 3]) + bb.w;
+            }
+            if constexpr (ACT == ACT_GELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+            } else if constexpr (ACT == ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint4 w;
+                w.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                w.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                w.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                w.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                const int c16 = h * 4 + j;                           // 16-byte chunk index inside the 128-byte row
+                *reinterpret_cast<uint4*>(srow + ((c16 ^ (r & 7)) << 4)) = w;
+            }
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (issuer) {
+            if constexpr (kConvOut) tma_store_3d(tmap_out, stage_tile, col_base + g * 64, row0, b);
+            else tma_store_2d(tmap_out, stage_tile, col_base + g * 64, row0);
+            tma_store_commit();
+        }
+    }
+}
+
 template <int BLOCK_N, int A_MODE>
 __global__ void __launch_bounds__(kNumThreads, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const DevParams p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_out, const DevParams p) {
     using Plan = SmemPlan<BLOCK_N>;
     constexpr int kStages = Plan::kStages;
     constexpr uint32_t kTmemCols = 2 * BLOCK_N;   // two accumulator stages (power of two >= 32 for BLOCK_N in {64,128,256})
 
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) { if (threadIdx.x == 0) printf("slsb: dynamic smem base not 1024-aligned\n"); __trap(); }
+    float* bias_s = reinterpret_cast<float*>(smem + Plan::kBiasOffset);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Plan::kBarOffset);
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tmem_full = empty_bar + kStages;
@@ -149,6 +225,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
+        if (p.tma_store) tma_prefetch_desc(&tmap_out);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -239,6 +316,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const long long res_off = (long long)b * p.res_batch_stride + (long long)row * p.ldr;
             const uint32_t taddr0 = tmem_base + (uint32_t(q * 32) << 16) + acc * BLOCK_N + half * kColsPerWarp;
             const int col_base = n_blk * BLOCK_N + half * kColsPerWarp;
+            if constexpr (BLOCK_N >= 128) {
+                if (p.tma_store) {
+                    // this half's 128 bias values -> smem (visible after the first named barrier of the tile)
+                    bias_s[half * kColsPerWarp + r] = __ldg(p.bias + col_base + r);
+                    uint8_t* stage_tile = smem + Plan::kStoreOffset + half * 16384;
+                    constexpr bool kConvOut = (A_MODE == A_CONV);
+                    if (p.act == ACT_GELU)
+                        epilogue_tile_tma<ACT_GELU, kColsPerWarp, kConvOut>(p, &tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, m_blk * BLOCK_M, b, &tmem_full[acc], acc_phase, &tmem_empty[acc]);
+                    else if (p.act == ACT_RELU)
+                        epilogue_tile_tma<ACT_RELU, kColsPerWarp, kConvOut>(p, &tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, m_blk * BLOCK_M, b, &tmem_full[acc], acc_phase, &tmem_empty[acc]);
+                    else
+                        epilogue_tile_tma<ACT_NONE, kColsPerWarp, kConvOut>(p, &tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, m_blk * BLOCK_M, b, &tmem_full[acc], acc_phase, &tmem_empty[acc]);
+                    continue;
+                }
+            }
             const int sel = p.act * 4 + p.out_bf16 * 2 + (p.residual != nullptr ? 1 : 0);
 #define SLSB_EPI(A_, O_, R_) epilogue_tile<A_, O_, R_, kColsPerWarp>(p, taddr0, out_off, res_off, col_base, row_ok, &tmem_full[acc], acc_phase)
             switch (sel) {
@@ -257,6 +349,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
+        if (p.tma_store && r == 0) tma_store_wait<0>();
     }
 
     tc_fence_before();
@@ -278,7 +371,7 @@ bool epilogue_supported(int act, int out_bf16, bool has_res) {
 }
 
 template <int BLOCK_N, int A_MODE>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const DevParams& dp, int num_sms, cudaStream_t stream) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const DevParams& dp, int num_sms, cudaStream_t stream) {
     using Plan = SmemPlan<BLOCK_N>;
     static bool configured = false;
     auto kern = tc_gemm_kernel<BLOCK_N, A_MODE>;
@@ -288,7 +381,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const DevParams& dp, in
     }
     const int tiles = dp.batches * dp.m_tiles * dp.n_tiles;
     const int grid = tiles < num_sms ? tiles : num_sms;
-    kern<<<grid, kNumThreads, Plan::kBytes, stream>>>(ta, tb, dp);
+    kern<<<grid, kNumThreads, Plan::kBytes, stream>>>(ta, tb, to, dp);
     SLSB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -318,8 +411,25 @@ int tc_gemm(const TcGemmArgs& g, int num_sms, cudaStream_t stream) {
     dp.out = g.out; dp.ldc = g.ldc; dp.out_batch_stride = g.out_batch_stride;
     dp.bias = g.bias; dp.residual = g.residual; dp.ldr = g.ldr; dp.res_batch_stride = g.res_batch_stride;
     dp.act = g.act; dp.out_bf16 = g.out_bf16;
+    { const char* dbg = getenv("SLSB_DEBUG_FLAGS"); dp.debug_flags = dbg ? atoi(dbg) : 0; }
 
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, to;
+    memset(&to, 0, sizeof(to));
+    // bf16 outputs of full-width tiles leave through TMA stores (BLOCK_N = 256 -> two 128-column halves of two 64-column groups)
+    dp.tma_store = (g.out_bf16 && g.residual == nullptr && block_n == 256 && g.a_mode != A_POS && !getenv("SLSB_NO_TMA_STORE")) ? 1 : 0;
+    if (dp.tma_store) {
+        if (g.a_mode == A_CONV) {
+            uint64_t dims[3] = {(uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.batches};
+            uint64_t strides[2] = {(uint64_t)g.ldc * 2, (uint64_t)g.out_batch_stride * 2};
+            uint32_t box[3] = {64, BLOCK_M, 1};
+            if (encode_tmap_bf16(&to, g.out, 3, dims, strides, box)) return -1;
+        } else {
+            uint64_t dims[2] = {(uint64_t)g.N, (uint64_t)g.M};
+            uint64_t strides[1] = {(uint64_t)g.ldc * 2};
+            uint32_t box[2] = {64, BLOCK_M};
+            if (encode_tmap_bf16(&to, g.out, 2, dims, strides, box)) return -1;
+        }
+    }
     {   // W: [N, K] K-major
         uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.N};
         uint64_t strides[1] = {(uint64_t)g.ldw * 2};
@@ -346,15 +456,15 @@ int tc_gemm(const TcGemmArgs& g, int num_sms, cudaStream_t stream) {
         if (encode_tmap_bf16(&ta, g.A, 3, dims, strides, box)) return -1;
     }
     if (g.a_mode == A_PLAIN) {
-        if (block_n == 256) return launch<256, A_PLAIN>(ta, tb, dp, num_sms, stream);
-        if (block_n == 128) return launch<128, A_PLAIN>(ta, tb, dp, num_sms, stream);
-        return launch<64, A_PLAIN>(ta, tb, dp, num_sms, stream);
+        if (block_n == 256) return launch<256, A_PLAIN>(ta, tb, to, dp, num_sms, stream);
+        if (block_n == 128) return launch<128, A_PLAIN>(ta, tb, to, dp, num_sms, stream);
+        return launch<64, A_PLAIN>(ta, tb, to, dp, num_sms, stream);
     } else if (g.a_mode == A_CONV) {
-        if (block_n == 256) return launch<256, A_CONV>(ta, tb, dp, num_sms, stream);
-        if (block_n == 128) return launch<128, A_CONV>(ta, tb, dp, num_sms, stream);
-        return launch<64, A_CONV>(ta, tb, dp, num_sms, stream);
+        if (block_n == 256) return launch<256, A_CONV>(ta, tb, to, dp, num_sms, stream);
+        if (block_n == 128) return launch<128, A_CONV>(ta, tb, to, dp, num_sms, stream);
+        return launch<64, A_CONV>(ta, tb, to, dp, num_sms, stream);
     }
-    return launch<64, A_POS>(ta, tb, dp, num_sms, stream);
+    return launch<64, A_POS>(ta, tb, to, dp, num_sms, stream);
 }
 
 }  // namespace slsb

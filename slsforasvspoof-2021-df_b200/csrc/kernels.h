@@ -68,6 +68,7 @@ int conv0_ln_gelu(const float* wav, int B, int S, int L0, int k, int stride, con
 // row-wise LayerNorm over C (C in {512, 1024}), optional GELU, optional second output (y - sub[c]); in/out fp32 or bf16
 struct LnArgs {
     const void* in = nullptr; int in_bf16 = 0;
+    const void* add = nullptr; float* sum_out = nullptr;   // optional: rows = in + add (bf16), written to sum_out (fp32) before the norm
     void* out = nullptr; int out_bf16 = 0;
     void* out2 = nullptr; int out2_bf16 = 0; const float* sub = nullptr;   // out2 = y - sub
     const float* w = nullptr; const float* b = nullptr;
