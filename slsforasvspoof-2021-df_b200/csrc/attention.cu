@@ -112,29 +112,32 @@ constexpr int kSmemQ = AQ * 128;              // 16 KB
 constexpr int kSmemK = 256 * 128;             // 32 KB (Tp <= 256 keys)
 constexpr int kSmemPExtra = 16 * 1024;        // P (64 KB) aliases Q + K + this
 constexpr int kSmemV = 256 * 128;             // 32 KB
-constexpr int kAttnSmem = kSmemQ + kSmemK + kSmemPExtra + kSmemV + 64 + 1024;
+constexpr int kAttnSmem = kSmemQ + kSmemK + kSmemPExtra + kSmemV + 64 + 4 * 128 * 4;
 
-__global__ void __launch_bounds__(160, 2)
+constexpr int kAttnThreads = 288;     // warps 0-7: softmax / epilogue (two per TMEM lane quadrant), warp 8: TMA + MMA issue
+
+__global__ void __launch_bounds__(kAttnThreads, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                bf16* __restrict__ out, int Tn, int Tp, int H, const int* __restrict__ lens) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) { if (threadIdx.x == 0) printf("slsb: dynamic smem base not 1024-aligned\n"); __trap(); }
     uint8_t* sQ = smem;
     uint8_t* sK = smem + kSmemQ;
     uint8_t* sP = smem;                                    // alias: valid once S = QK^T has completed
     uint8_t* sV = smem + kSmemQ + kSmemK + kSmemPExtra;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kSmemV);   // [0] loads, [1] S ready, [2] P ready, [3] O ready
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+    float* xch = reinterpret_cast<float*>(bars + 6);             // [2 halves][128 rows] row max, then [2][128] row sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AQ;
     const int len = lens ? min(lens[b], Tn) : Tn;
     const int D = H * HD;
 
-    if (warp == 4 && lane == 0) {
+    if (warp == 8 && lane == 0) {
         tma_prefetch_desc(&tm_q);
         tma_prefetch_desc(&tm_kv);
-        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 128); mbar_init(&bars[3], 1);
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 256); mbar_init(&bars[3], 1);
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc<256>(tmem_ptr);
@@ -143,7 +146,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (lane == 0) {
             mbar_expect_tx(&bars[0], (uint32_t)(kSmemQ + 2 * Tp * 128));
             tma_load_2d(sQ, &tm_q, &bars[0], h * HD, b * Tn + q0);
@@ -173,22 +176,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             }
         }
     } else {
-        // softmax + epilogue: thread == query row == TMEM lane
-        const int r = warp * 32 + lane;
-        const uint32_t trow = tmem + (uint32_t(warp * 32) << 16);
+        // softmax + epilogue: thread == query row == TMEM lane; the two warps of a quadrant split the key columns
+        const int q = warp & 3, half = warp >> 2;
+        const int r = q * 32 + lane;
+        const uint32_t trow = tmem + (uint32_t(q * 32) << 16);
+        const int nchunk = Tp / 16;
+        const int c_lo = half == 0 ? 0 : (nchunk + 1) / 2;
+        const int c_hi = half == 0 ? (nchunk + 1) / 2 : nchunk;
         mbar_wait(&bars[1], 0);
         tc_fence_after();
-        // Scores are read from TMEM in 16-column chunks, double-buffered in registers so the next tcgen05.ld is in
-        // flight while the current chunk is processed.  Pass 1: row max.  Pass 2: p = exp2(s*log2e - max*log2e).
-        const int nchunk = Tp / 16;
+        // pass 1: row max over this warp's chunks (TMEM loads double-buffered in registers)
         float mx = -INFINITY;
         {
             uint32_t a[2][16];
-            tmem_ld_32x32b_x16(trow, a[0]);
-            tmem_ld_wait();
+            if (c_lo < c_hi) { tmem_ld_32x32b_x16(trow + c_lo * 16, a[0]); tmem_ld_wait(); }
 #pragma unroll 1
-            for (int c = 0; c < nchunk; c += 2) {
-                if (c + 1 < nchunk) tmem_ld_32x32b_x16(trow + (c + 1) * 16, a[1]);
+            for (int c = c_lo; c < c_hi; c += 2) {
+                if (c + 1 < c_hi) tmem_ld_32x32b_x16(trow + (c + 1) * 16, a[1]);
                 if (c * 16 + 16 <= len) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(a[0][j]));
@@ -197,8 +201,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                     for (int j = 0; j < 16; ++j) if (c * 16 + j < len) mx = fmaxf(mx, __uint_as_float(a[0][j]));
                 }
                 tmem_ld_wait();
-                if (c + 1 >= nchunk) break;
-                if (c + 2 < nchunk) tmem_ld_32x32b_x16(trow + (c + 2) * 16, a[0]);
+                if (c + 1 >= c_hi) break;
+                if (c + 2 < c_hi) tmem_ld_32x32b_x16(trow + (c + 2) * 16, a[0]);
                 if (c * 16 + 32 <= len) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(a[1][j]));
@@ -209,6 +213,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                 tmem_ld_wait();
             }
         }
+        xch[half * 128 + r] = mx;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mx = fmaxf(mx, xch[(half ^ 1) * 128 + r]);            // at least one key is valid, so the row max is finite
         const float mxl = mx * 1.4426950408889634f;
         float sum = 0.f;
         auto emit = [&](const uint32_t (&a)[16], int c) {
@@ -232,33 +239,33 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         };
         {
             uint32_t a[2][16];
-            tmem_ld_32x32b_x16(trow, a[0]);
-            tmem_ld_wait();
+            if (c_lo < c_hi) { tmem_ld_32x32b_x16(trow + c_lo * 16, a[0]); tmem_ld_wait(); }
 #pragma unroll 1
-            for (int c = 0; c < nchunk; c += 2) {
-                if (c + 1 < nchunk) tmem_ld_32x32b_x16(trow + (c + 1) * 16, a[1]);
+            for (int c = c_lo; c < c_hi; c += 2) {
+                if (c + 1 < c_hi) tmem_ld_32x32b_x16(trow + (c + 1) * 16, a[1]);
                 emit(a[0], c);
                 tmem_ld_wait();
-                if (c + 1 >= nchunk) break;
-                if (c + 2 < nchunk) tmem_ld_32x32b_x16(trow + (c + 2) * 16, a[0]);
+                if (c + 1 >= c_hi) break;
+                if (c + 2 < c_hi) tmem_ld_32x32b_x16(trow + (c + 2) * 16, a[0]);
                 emit(a[1], c + 1);
                 tmem_ld_wait();
             }
         }
-        fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        xch[256 + half * 128 + r] = sum;
+        fence_proxy_async_smem();     // generic-proxy smem writes of P -> visible to the tensor core (async proxy)
         tc_fence_before();
         mbar_arrive(&bars[2]);
         mbar_wait(&bars[3], 0);
         tc_fence_after();
-        const float inv = 1.0f / sum;
+        asm volatile("bar.sync 1, 256;" ::: "memory");        // partner's row sum is visible
+        const float inv = 1.0f / (sum + xch[256 + (half ^ 1) * 128 + r]);
         const int t = q0 + r;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        {
             uint32_t a[32];
-            tmem_ld_32x32b_x32(trow + c * 32, a);
+            tmem_ld_32x32b_x32(trow + half * 32, a);          // each warp of the pair writes 32 of the 64 output columns
             tmem_ld_wait();
             if (t < Tn) {
-                uint4* op = reinterpret_cast<uint4*>(out + ((long long)b * Tn + t) * D + h * HD + c * 32);
+                uint4* op = reinterpret_cast<uint4*>(out + ((long long)b * Tn + t) * D + h * HD + half * 32);
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
                     uint4 w;
@@ -313,7 +320,7 @@ int attention_tc(const void* qkv, void* out, int B, int T, int H, const int* len
         configured = true;
     }
     dim3 grid((T + AQ - 1) / AQ, H, B);
-    attn_tc_kernel<<<grid, 160, kAttnSmem, stream>>>(tq, tkv, static_cast<bf16*>(out), T, Tp, H, lens);
+    attn_tc_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(tq, tkv, static_cast<bf16*>(out), T, Tp, H, lens);
     SLSB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

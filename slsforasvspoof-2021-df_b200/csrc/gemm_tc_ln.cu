@@ -21,9 +21,11 @@ constexpr int kStages = 2;
 constexpr int kStageA = BLOCK_M * BLOCK_K * 2;          // 16 KB
 constexpr int kStageB = NCH * BLOCK_K * 2;              // 64 KB
 constexpr int kStage = kStageA + kStageB;
-constexpr int kPartOffset = kStages * kStage;           // float2 part[2 buffers][2 halves][128 rows]
+constexpr int kStoreOffset = kStages * kStage;          // 2 x [128 rows x 64 bf16] SWIZZLE_128B staging tiles (one per column half)
+constexpr int kParamOffset = kStoreOffset + 2 * 16384;  // bias | ln_w | ln_b, 512 floats each (constant per launch)
+constexpr int kPartOffset = kParamOffset + 3 * NCH * 4; // float2 part[2 buffers][2 halves][128 rows]
 constexpr int kBarOffset = kPartOffset + 2 * 2 * 128 * 8;
-constexpr int kSmemBytes = kBarOffset + 128 + 1024;
+constexpr int kSmemBytes = kBarOffset + 128;
 constexpr int kThreads = 384;
 
 struct LnDev {
@@ -36,9 +38,11 @@ struct LnDev {
 
 template <int A_MODE>
 __global__ void __launch_bounds__(kThreads, 1)
-tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const LnDev p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const __grid_constant__ CUtensorMap tmap_out, const LnDev p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) { if (threadIdx.x == 0) printf("slsb: dynamic smem base not 1024-aligned\n"); __trap(); }
+    float* par = reinterpret_cast<float*>(smem + kParamOffset);
     float2* part = reinterpret_cast<float2*>(smem + kPartOffset);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kBarOffset);
     uint64_t* empty_bar = full_bar + kStages;
@@ -50,7 +54,8 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int num_tiles = p.batches * p.m_tiles;
     const int num_kb = p.K / BLOCK_K;
 
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); tma_prefetch_desc(&tmap_out); }
+    for (int i = threadIdx.x; i < NCH; i += kThreads) { par[i] = p.bias[i]; par[NCH + i] = p.ln_w[i]; par[2 * NCH + i] = p.ln_b[i]; }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(tmem_full, 1); mbar_init(tmem_empty, 8);
@@ -118,28 +123,35 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int r = q * 32 + lane;
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + half * 256;
         const int col_base = half * 256;
+        const float* bias_s = par + col_base;
+        const float* g_s = par + NCH + col_base;
+        const float* h_s = par + 2 * NCH + col_base;
+        uint8_t* stage_tile = smem + kStoreOffset + half * 16384;
+        uint8_t* srow = stage_tile + r * 128;
+        const int bar_id = 2 + half;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int m_blk = tile % p.m_tiles, b = tile / p.m_tiles;
-            const int row = m_blk * BLOCK_M + r;
-            const bool row_ok = row < p.M;
             mbar_wait(tmem_full, it & 1);
             tc_fence_after();
-            // pass 1: statistics over this warp's 256 columns
+            // pass 1: statistics over this warp's 256 columns; TMEM loads double-buffered in registers
             float s = 0.f, ss = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 8; ++c) {
-                uint32_t acc[32];
-                tmem_ld_32x32b_x32(taddr + c * 32, acc);
-                const float4* b4 = reinterpret_cast<const float4*>(p.bias + col_base + c * 32);
+            {
+                uint32_t acc[2][32];
+                tmem_ld_32x32b_x32(taddr, acc[0]);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 bb = __ldg(b4 + j);
-                    const float v0 = __uint_as_float(acc[4 * j + 0]) + bb.x, v1 = __uint_as_float(acc[4 * j + 1]) + bb.y;
-                    const float v2 = __uint_as_float(acc[4 * j + 2]) + bb.z, v3 = __uint_as_float(acc[4 * j + 3]) + bb.w;
-                    s += (v0 + v1) + (v2 + v3);
-                    ss = fmaf(v0, v0, ss); ss = fmaf(v1, v1, ss); ss = fmaf(v2, v2, ss); ss = fmaf(v3, v3, ss);
+                for (int c = 0; c < 8; ++c) {
+                    if (c + 1 < 8) tmem_ld_32x32b_x32(taddr + (c + 1) * 32, acc[(c + 1) & 1]);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 bb = *reinterpret_cast<const float4*>(bias_s + c * 32 + 4 * j);
+                        const float v0 = __uint_as_float(acc[c & 1][4 * j + 0]) + bb.x, v1 = __uint_as_float(acc[c & 1][4 * j + 1]) + bb.y;
+                        const float v2 = __uint_as_float(acc[c & 1][4 * j + 2]) + bb.z, v3 = __uint_as_float(acc[c & 1][4 * j + 3]) + bb.w;
+                        s += (v0 + v1) + (v2 + v3);
+                        ss = fmaf(v0, v0, ss); ss = fmaf(v1, v1, ss); ss = fmaf(v2, v2, ss); ss = fmaf(v3, v3, ss);
+                    }
+                    tmem_ld_wait();
                 }
             }
             float2* pbuf = part + (it & 1) * 256;
@@ -149,40 +161,52 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const float mean = (s + other.x) * (1.0f / NCH);
             const float var = fmaxf((ss + other.y) * (1.0f / NCH) - mean * mean, 0.0f);
             const float rstd = rsqrtf(var + p.eps);
-            // pass 2: normalise + affine + GELU + store
-            bf16* orow = p.out + (long long)b * p.out_batch_stride + (long long)row * NCH + col_base;
+            // pass 2: normalise + affine + GELU -> bf16 staging tile (64 columns at a time) -> TMA store
 #pragma unroll 1
-            for (int c = 0; c < 8; ++c) {
-                uint32_t acc[32];
-                tmem_ld_32x32b_x32(taddr + c * 32, acc);
-                const float4* b4 = reinterpret_cast<const float4*>(p.bias + col_base + c * 32);
-                const float4* g4 = reinterpret_cast<const float4*>(p.ln_w + col_base + c * 32);
-                const float4* h4 = reinterpret_cast<const float4*>(p.ln_b + col_base + c * 32);
+            for (int g = 0; g < 4; ++g) {
+                uint32_t acc[2][32];
+                tmem_ld_32x32b_x32(taddr + g * 64, acc[0]);
+                tmem_ld_32x32b_x32(taddr + g * 64 + 32, acc[1]);
+                if (r == 0) tma_store_wait_read<0>();
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                 tmem_ld_wait();
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 bb = __ldg(b4 + j), g = __ldg(g4 + j), h = __ldg(h4 + j);
-                    v[4 * j + 0] = gelu_fast(fmaf((__uint_as_float(acc[4 * j + 0]) + bb.x - mean) * rstd, g.x, h.x));
-                    v[4 * j + 1] = gelu_fast(fmaf((__uint_as_float(acc[4 * j + 1]) + bb.y - mean) * rstd, g.y, h.y));
-                    v[4 * j + 2] = gelu_fast(fmaf((__uint_as_float(acc[4 * j + 2]) + bb.z - mean) * rstd, g.z, h.z));
-                    v[4 * j + 3] = gelu_fast(fmaf((__uint_as_float(acc[4 * j + 3]) + bb.w - mean) * rstd, g.w, h.w));
+                if (g == 3) {                                          // accumulator fully read -> MMA warp may start the next tile
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty);
                 }
-                if (row_ok) {
-                    uint4* o = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int c0 = g * 64 + h * 32;
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 bb = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * j);
+                        const float4 gg = *reinterpret_cast<const float4*>(g_s + c0 + 4 * j);
+                        const float4 hh = *reinterpret_cast<const float4*>(h_s + c0 + 4 * j);
+                        v[4 * j + 0] = gelu_fast(fmaf((__uint_as_float(acc[h][4 * j + 0]) + bb.x - mean) * rstd, gg.x, hh.x));
+                        v[4 * j + 1] = gelu_fast(fmaf((__uint_as_float(acc[h][4 * j + 1]) + bb.y - mean) * rstd, gg.y, hh.y));
+                        v[4 * j + 2] = gelu_fast(fmaf((__uint_as_float(acc[h][4 * j + 2]) + bb.z - mean) * rstd, gg.z, hh.z));
+                        v[4 * j + 3] = gelu_fast(fmaf((__uint_as_float(acc[h][4 * j + 3]) + bb.w - mean) * rstd, gg.w, hh.w));
+                    }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         uint4 w;
                         w.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]); w.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
                         w.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); w.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-                        o[j] = w;
+                        *reinterpret_cast<uint4*>(srow + (((h * 4 + j) ^ (r & 7)) << 4)) = w;
                     }
                 }
+                fence_proxy_async_smem();
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                if (r == 0) {
+                    if constexpr (A_MODE == A_CONV) tma_store_3d(&tmap_out, stage_tile, col_base + g * 64, m_blk * BLOCK_M, b);
+                    else tma_store_2d(&tmap_out, stage_tile, col_base + g * 64, m_blk * BLOCK_M);
+                    tma_store_commit();
+                }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty);
         }
+        if (r == 0) tma_store_wait<0>();
     }
     tc_fence_before();
     __syncthreads();
@@ -193,7 +217,7 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 }
 
 template <int A_MODE>
-int launch_ln(const CUtensorMap& ta, const CUtensorMap& tb, const LnDev& dp, int num_sms, cudaStream_t stream) {
+int launch_ln(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const LnDev& dp, int num_sms, cudaStream_t stream) {
     static bool configured = false;
     auto kern = tc_gemm_ln_kernel<A_MODE>;
     if (!configured) {
@@ -201,7 +225,7 @@ int launch_ln(const CUtensorMap& ta, const CUtensorMap& tb, const LnDev& dp, int
         configured = true;
     }
     const int tiles = dp.batches * dp.m_tiles;
-    kern<<<tiles < num_sms ? tiles : num_sms, kThreads, kSmemBytes, stream>>>(ta, tb, dp);
+    kern<<<tiles < num_sms ? tiles : num_sms, kThreads, kSmemBytes, stream>>>(ta, tb, to, dp);
     SLSB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -251,7 +275,18 @@ int tc_gemm_ln_gelu(const TcLnGemmArgs& g, int num_sms, cudaStream_t stream) {
     dp.conv_cin = g.conv_cin; dp.conv_stride = g.conv_stride;
     dp.out = static_cast<bf16*>(g.out); dp.out_batch_stride = g.out_batch_stride;
     dp.bias = g.bias; dp.ln_w = g.ln_w; dp.ln_b = g.ln_b; dp.eps = g.eps;
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, to;
+    if (g.a_mode == A_PLAIN) {
+        uint64_t dims[2] = {(uint64_t)NCH, (uint64_t)g.M};
+        uint64_t strides[1] = {(uint64_t)NCH * 2};
+        uint32_t box[2] = {64, BLOCK_M};
+        if (encode_tmap_bf16(&to, g.out, 2, dims, strides, box)) return -1;
+    } else {
+        uint64_t dims[3] = {(uint64_t)NCH, (uint64_t)g.M, (uint64_t)g.batches};
+        uint64_t strides[2] = {(uint64_t)NCH * 2, (uint64_t)g.out_batch_stride * 2};
+        uint32_t box[3] = {64, BLOCK_M, 1};
+        if (encode_tmap_bf16(&to, g.out, 3, dims, strides, box)) return -1;
+    }
     {
         uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)NCH};
         uint64_t strides[1] = {(uint64_t)g.K * 2};
@@ -263,14 +298,14 @@ int tc_gemm_ln_gelu(const TcLnGemmArgs& g, int num_sms, cudaStream_t stream) {
         uint64_t strides[1] = {(uint64_t)g.lda * 2};
         uint32_t box[2] = {BLOCK_K, BLOCK_M};
         if (encode_tmap_bf16(&ta, g.A, 2, dims, strides, box)) return -1;
-        return launch_ln<A_PLAIN>(ta, tb, dp, num_sms, stream);
+        return launch_ln<A_PLAIN>(ta, tb, to, dp, num_sms, stream);
     }
     const uint64_t C = g.conv_cin, s = g.conv_stride, Lin = g.conv_lin;
     uint64_t dims[4] = {C, s, (Lin + s - 1) / s, (uint64_t)g.batches};
     uint64_t strides[3] = {C * 2, s * C * 2, Lin * C * 2};
     uint32_t box[4] = {BLOCK_K, 1, BLOCK_M, 1};
     if (encode_tmap_bf16(&ta, g.A, 4, dims, strides, box)) return -1;
-    return launch_ln<A_CONV>(ta, tb, dp, num_sms, stream);
+    return launch_ln<A_CONV>(ta, tb, to, dp, num_sms, stream);
 }
 
 int conv0_im2col(const float* wav, void* out, int B, int S, int L0, int k, int stride, cudaStream_t stream) {
