@@ -1,11 +1,13 @@
 #!/usr/bin/env python
-"""Benchmark of the scoring hot path: 4-s utterances/second through XLS-R-300M + TopK-SAE head (BASELINE.json).
+"""Benchmark of the scoring hot path: 4-s utterances/second through XLS-R-300M + SLS head (BASELINE.json).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 A "step" is one pass of the hot path over one batch of 64 synthetic 64 600-sample clips per GPU (BASELINE
 config 2, bf16).  ``value`` = whole-job utterances/s with the clips already resident in HBM; ``e2e`` = the same
-metric through ``slsb_score_host`` (pinned host clips -> H2D -> forward -> scores -> D2H every step).
+metric through the C ABI with HOST buffers (``slsb_score_submit`` per step: pinned host clips -> H2D -> forward ->
+scores -> D2H every step, the upload of step i+1 overlapping the forward of step i; ``e2e.sync_value`` is the
+un-pipelined ``slsb_score_host`` loop).
 One JSON line on rank 0.  Multi-GPU: one process per GPU (torchrun), utterance-sharded, weak scaling; the only
 collective is the final all-gather of scores, outside the per-step hot path.
 """
@@ -25,7 +27,17 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 FLOP_PER_UTT_ENC_GEMM = 121.40e9   # 24 x (qkv + out + fc1 + fc2) GEMMs per 64 600-sample clip
-FLOP_PER_UTT_TOTAL = 150.45e9      # trunk + SAE encoder + classifier
+FLOP_PER_UTT_TOTAL = {"sls": 148.81e9, "sae": 150.45e9, "window": 150.45e9}   # trunk + head
+HEAD_NAMES = {"sls": "SLS layer-attention head", "sae": "TopK-SAE head", "window": "window-TopK SAE head"}
+
+
+def _traffic(kernel_key):
+    """Per-launch DRAM bytes of the dominant kernel from the committed ``ncu --set full`` capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p)).get(kernel_key)
+    except Exception:
+        return None
 
 
 def _peaks():
@@ -77,7 +89,7 @@ def run_reference(args, rank, world):
     from oracle.trunk import synth_clips
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    m = OracleModel(head="sae").eval()
+    m = OracleModel(head=args.head).eval()
     bs = 4
     x = synth_clips(0, bs)
     with torch.no_grad():
@@ -92,8 +104,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "utterances_per_second", "value": v, "unit": "utt/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "XLS-R-300M + TopK-SAE head, 64600-sample clips (BASELINE config 2)", "sample": f"{bs} clips per step on CPU"},
-        "cpu_baseline": {"value": v, "unit": "utt/s", "cores": cores, "kind": "port", "sample": f"{args.steps} steps x {bs} clips, fp32, torch CPU"},
+        "config": {"workload": f"XLS-R-300M + {HEAD_NAMES[args.head]}, 64600-sample clips (BASELINE config 2), random-init weights",
+                   "sample": f"{bs} clips per step on CPU"},
+        "cpu_baseline": {"value": v, "unit": "utt/s", "cores": cores, "kind": "port", "sample": f"{args.steps} steps x {bs} clips, fp32, torch CPU oracle port (reference head code on the restated fairseq trunk)"},
         "e2e": {"value": v, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -104,7 +117,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64)
-    ap.add_argument("--head", default="sae", choices=["sae", "window", "sls"])
+    ap.add_argument("--head", default="sls", choices=["sls", "sae", "window"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -175,15 +188,27 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     assert torch.isfinite(out).all()
 
-    # end to end through the C ABI with host buffers (H2D + forward + D2H every step)
-    for i in range(2):
-        eng.score_host(host[i % n_pool], head, prec)
+    # end to end through the C ABI with host buffers: every step uploads its own clips from pinned host memory and
+    # downloads its own scores; submissions are pipelined (upload of step i+1 overlaps the forward of step i)
+    outs = [torch.empty(B, dtype=torch.float32, pin_memory=True) for _ in range(4)]
+    for i in range(3):
+        eng.score_submit(host[i % n_pool], head, prec, out=outs[i % 4])
+    eng.score_wait()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        eng.score_submit(host[i % n_pool], head, prec, out=outs[i % 4])
+    eng.score_wait()
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    assert all(bool(torch.isfinite(o).all()) for o in outs)
+    # the un-pipelined loop (one synchronising slsb_score_host call per step) for comparison
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
         sc = eng.score_host(host[i % n_pool], head, prec)
     torch.cuda.synchronize()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    e2e_sync_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
 
     # roofline of the dominant kernel (tcgen05 encoder GEMMs): per-launch CUDA events on the launch stream, separate
     # pass over the same workload so the event records do not sit inside the headline timing
@@ -198,14 +223,22 @@ def main():
         g_ms, g_fl, g_n = (sum(v[j] for v in enc.values()) for j in range(3))
         other = {k: eng.profile_read(i) for i, k in ((4, "conv_gemm"), (5, "pos_conv"), (6, "other_gemm"), (7, "attention"))}
         other.update(enc)
+        hbm = {k: eng.profile_read(i) for i, k in ((8, "layernorm_residual"), (9, "sls_fuse_pool"), (10, "sls_fc1"))}
         eng.profile(False)
         ach = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "tc_gemm_kernel (encoder qkv/out/fc1/fc2)", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
-                "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["source"] + " (sustained)",
+                "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": _traffic("tc_gemm_kernel"),
+                "peak_source": peaks["source"] + " (sustained)",
                 "launches": g_n, "avg_launch_ms": g_ms / max(g_n, 1), "flops_per_launch": g_fl / max(g_n, 1),
                 "share_of_step": (g_ms / psteps) / (ms / args.steps),
                 "other_kernels_ms_per_step": {k: v[0] / psteps for k, v in other.items()},
-                "other_kernels_tflops": {k: (v[1] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else 0.0) for k, v in other.items()}}
+                "other_kernels_tflops": {k: (v[1] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else 0.0) for k, v in other.items()},
+                # HBM-bound kernels: algorithmic bytes / CUDA-event time against the measured copy bandwidth
+                "hbm_kernels": {k: {"ms_per_step": v[0] / psteps, "launches_per_step": v[2] / psteps,
+                                    "achieved_gbs": (v[1] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else 0.0),
+                                    "frac": (v[1] / (v[0] * 1e-3) / 1e9 / peaks["hbm_gbs"] if v[0] > 0 else 0.0)}
+                                for k, v in hbm.items() if v[2] > 0},
+                "hbm_peak_gbs": peaks["hbm_gbs"]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -213,13 +246,13 @@ def main():
         from oracle.trunk import synth_clips
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        om = OracleModel(head="sae").eval()
+        om = OracleModel(head=args.head).eval()
         xb = synth_clips(0, 4)
         with torch.no_grad():
             om(xb[:1])
             t0 = time.perf_counter()
             n = 0
-            while time.perf_counter() - t0 < 12.0 and n < 8:
+            while time.perf_counter() - t0 < 15.0 and n < 16:
                 om(xb)
                 n += 1
             dt = time.perf_counter() - t0
@@ -232,12 +265,15 @@ def main():
             "metric": "utterances_per_second", "value": utt / (ms * 1e-3), "unit": "utt/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
             "data": "synthetic",
-            "config": {"workload": f"XLS-R-300M + {args.head} head, batch={B} x 64600-sample clips per GPU (BASELINE config 2), random-init weights",
+            "config": {"workload": f"XLS-R-300M + {HEAD_NAMES[args.head]}, batch={B} x 64600-sample clips per GPU (BASELINE config 2), random-init weights",
+                       "head": args.head,
                        "global_batch": B * world, "parallelism": f"utterance-sharded x{world}",
                        "l2": "per-step working set (631 MB bf16 weights + >2 GB activations) exceeds the 126 MB L2; 4 rotating input batches"},
-            "e2e": {"value": utt / (e2e_ms * 1e-3), "unit": "utt/s", "h2d_bytes_per_step": B * S * 4, "d2h_bytes_per_step": B * 4},
+            "e2e": {"value": utt / (e2e_ms * 1e-3), "unit": "utt/s", "h2d_bytes_per_step": B * S * 4, "d2h_bytes_per_step": B * 4,
+                    "api": "slsb_score_submit/slsb_score_wait (pipelined uploads)", "sync_value": utt / (e2e_sync_ms * 1e-3),
+                    "sync_api": "slsb_score_host (one host sync per step)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-            "tflops_per_gpu_whole_step": FLOP_PER_UTT_TOTAL * B * args.steps / (ms * 1e-3) / 1e12,
+            "tflops_per_gpu_whole_step": FLOP_PER_UTT_TOTAL[args.head] * B * args.steps / (ms * 1e-3) / 1e12,
         }
         print(json.dumps(line))
     if world > 1:

@@ -34,7 +34,7 @@ extern "C" {
 
 enum { SLSB_HEAD_NONE = 0, SLSB_HEAD_SAE = 1, SLSB_HEAD_WINDOW = 2, SLSB_HEAD_SLS = 3 };
 enum { SLSB_PREC_FP32 = 0, SLSB_PREC_BF16 = 1 };
-enum { SLSB_ATTN_AUTO = 0, SLSB_ATTN_SIMT = 1, SLSB_ATTN_TC = 2 };
+enum { SLSB_ATTN_AUTO = 0, SLSB_ATTN_SIMT = 1, SLSB_ATTN_TC = 2 /* persistent, P in TMEM */, SLSB_ATTN_TC_V1 = 3 /* one CTA per query tile, P in smem */ };
 
 typedef struct slsb_config {
     int32_t n_conv;              /* 7 */
@@ -104,6 +104,15 @@ int slsb_sae_loss(slsb_engine* e, int precision, float* loss_dev, void* stream);
 int slsb_score_host(slsb_engine* e, const float* wav_host, const int32_t* sample_lens_host, int B, int S,
                     int head, int precision, float* scores_host, void* stream);
 
+/* The same, pipelined: slsb_score_submit enqueues upload + forward + score download and returns a ticket (>= 0) without
+ * waiting; the upload runs on a private copy stream into one of two staging slots, so the H2D copy of batch i+1 overlaps
+ * the forward of batch i.  At most 4 submissions are in flight (the 5th submit waits for the 1st).  wav_host / scores_host
+ * must stay valid until slsb_score_wait(e, ticket) returns (ticket < 0 waits for everything submitted so far).
+ * slsb_score_host == submit + wait.  (DataLoader prefetch + batch_x.to(device, non_blocking=True), main.py:165-178.) */
+int64_t slsb_score_submit(slsb_engine* e, const float* wav_host, const int32_t* sample_lens_host, int B, int S,
+                          int head, int precision, float* scores_host, void* stream);
+int slsb_score_wait(slsb_engine* e, int64_t ticket);
+
 /* synthetic clips keyed by utterance index, bit-identical to oracle.trunk.synth_clips */
 int slsb_synth_clips(float* wav_dev, int64_t first_utt, int count, int samples, void* stream);
 
@@ -111,8 +120,9 @@ int slsb_synth_clips(float* wav_dev, int64_t first_utt, int count, int samples, 
 int64_t slsb_launch_count(const slsb_engine* e);
 
 /* Per-launch CUDA-event timing of the tensor-core kernels (events recorded on the launch stream).
- * kind: 0 qkv, 1 out_proj, 2 fc1, 3 fc2 (encoder GEMMs), 4 conv-stack implicit GEMMs, 5 positional conv, 6 other GEMMs, 7 attention.
- * slsb_profile_read synchronises the device and sums elapsed ms / algorithmic FLOPs / launches since enable. */
+ * kind: 0 qkv, 1 out_proj, 2 fc1, 3 fc2 (encoder GEMMs), 4 conv-stack implicit GEMMs, 5 positional conv, 6 other GEMMs, 7 attention
+ * (these report algorithmic FLOPs); 8 LayerNorm(+residual) kernels, 9 SLS weighted-sum/BN/SELU/max-pool, 10 SLS fc1 (these
+ * report algorithmic HBM BYTES in flops_out).  slsb_profile_read synchronises the device and sums elapsed ms / work / launches. */
 int slsb_profile_enable(slsb_engine* e, int on);
 int slsb_profile_read(slsb_engine* e, int kind, double* ms_out, double* flops_out, int64_t* launches_out);
 
@@ -121,6 +131,9 @@ int slsb_profile_read(slsb_engine* e, int kind, double* ms_out, double* flops_ou
  * precision fp32: A, W, out fp32 (CUDA cores).  bf16: A, W bf16 (tcgen05), out bf16 if out_bf16 else fp32. */
 int slsb_op_gemm(int precision, const void* A, const void* W, const float* bias, const float* residual, void* out,
                  int M, int N, int K, int act, int out_bf16, void* stream);
+/* split-K tcgen05 GEMM (SLS fc1): A bf16 [M,K], W bf16 [N,K] -> fp32 partials [M][k_splits][N]; split s covers k-blocks
+ * [s*ceil(K/64/k_splits), ...); k_splits must leave no empty split.  Synchronises the stream (test hook). */
+int slsb_op_gemm_splitk(const void* A, const void* W, float* partial, int M, int N, int K, int k_splits, void* stream);
 /* Conv1d(C->N, k, stride) over channels-last x[B, L_in, C] as implicit GEMM; W is [N, k*C] tap-major */
 int slsb_op_conv(int precision, const void* x, const void* W, const float* bias, void* out, int B, int L_in, int C, int N,
                  int k, int stride, void* stream);

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libslsb200.so")
 
 HEAD_NONE, HEAD_SAE, HEAD_WINDOW, HEAD_SLS = 0, 1, 2, 3
 PREC_FP32, PREC_BF16 = 0, 1
-ATTN_AUTO, ATTN_SIMT, ATTN_TC = 0, 1, 2
+ATTN_AUTO, ATTN_SIMT, ATTN_TC, ATTN_TC_V1 = 0, 1, 2, 3
 
 
 class SlsbError(RuntimeError):
@@ -52,11 +52,14 @@ _SIGNATURES = {
     "slsb_sae_decode": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, _P]),
     "slsb_sae_loss": (C.c_int, [_P, C.c_int, _P, _P]),
     "slsb_score_host": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "slsb_score_submit": (C.c_int64, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "slsb_score_wait": (C.c_int, [_P, C.c_int64]),
     "slsb_synth_clips": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, _P]),
     "slsb_launch_count": (C.c_int64, [_P]),
     "slsb_profile_enable": (C.c_int, [_P, C.c_int]),
     "slsb_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "slsb_op_gemm": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "slsb_op_gemm_splitk": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "slsb_op_conv": (C.c_int, [C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "slsb_op_conv_ln_gelu": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "slsb_op_conv0_tc": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),

@@ -117,7 +117,7 @@ constexpr int kAttnSmem = kSmemQ + kSmemK + kSmemPExtra + kSmemV + 64 + 4 * 128 
 constexpr int kAttnThreads = 288;     // warps 0-7: softmax / epilogue (two per TMEM lane quadrant), warp 8: TMA + MMA issue
 
 __global__ void __launch_bounds__(kAttnThreads, 2)
-attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+attn_tc_v1_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                bf16* __restrict__ out, int Tn, int Tp, int H, const int* __restrict__ lens) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0) { if (threadIdx.x == 0) printf("slsb: dynamic smem base not 1024-aligned\n"); __trap(); }
@@ -286,6 +286,233 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     }
 }
 
+
+// =================================================================================================
+// tcgen05, persistent + warp-specialised (the production kernel)
+//
+//   item  = one (utterance, head): K and V are loaded ONCE per item and shared by its query tiles;
+//   unit  = one 128-query tile of an item; units alternate between two softmax warpgroups (WG0 = warps 0-3, WG1 = warps 4-7),
+//           each owning one 256-column half of TMEM, so the tensor-core work of one unit hides behind the softmax of the other;
+//   warp 8 = TMA producer (2-stage ring of {Q tiles, K, V}, 96 KB / stage), warp 9 = single-thread MMA issuer.
+//   S = Q K^T lands in TMEM (fp32, Tp columns); the owning thread (== query row) takes the row max and the exponentials
+//   straight from TMEM and writes P back INTO TMEM as packed bf16 over the columns of S it has already consumed
+//   (tcgen05.st), so the second MMA (O = P V) takes its A operand from tensor memory and P never touches shared memory;
+//   V is the MN-major B operand in exactly the [key][d] layout TMA delivers.  O lands in columns 192..255 of the same half.
+// =================================================================================================
+constexpr int P_STAGES = 2;
+constexpr int P_SQ = 2 * AQ * 128;            // up to two 128-row query tiles, 32 KB
+constexpr int P_SK = 256 * 128;               // 32 KB (Tp <= 256 keys)
+constexpr int P_SV = 256 * 128;               // 32 KB
+constexpr int P_STAGE = P_SQ + P_SK + P_SV;   // 96 KB
+constexpr int P_BAR_OFFSET = P_STAGES * P_STAGE;
+constexpr int P_SMEM = P_BAR_OFFSET + 256;
+constexpr int P_THREADS = 320;
+constexpr int P_OCOL = 192;                   // O accumulator columns inside a TMEM half
+
+__global__ void __launch_bounds__(P_THREADS, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+               bf16* __restrict__ out, int Tn, int Tp, int H, int n_items, int n_qt, const int* __restrict__ lens) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) { if (threadIdx.x == 0) printf("slsb: dynamic smem base not 1024-aligned\n"); __trap(); }
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_BAR_OFFSET);
+    uint64_t* full = bars;                    // [P_STAGES] loads landed
+    uint64_t* stage_free = bars + 2;          // [P_STAGES] every MMA that reads the stage has completed
+    uint64_t* s_ready = bars + 4;             // [2] S = Q K^T complete in TMEM half w
+    uint64_t* p_ready = bars + 6;             // [2] P written back to TMEM half w (4 warp arrivals)
+    uint64_t* o_ready = bars + 8;             // [2] O = P V complete
+    uint64_t* tmem_free = bars + 10;          // [2] epilogue has read O out of half w (4 warp arrivals)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int D = H * HD;
+    const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // items blockIdx.x, +grid, ...
+    const int my_units = my_items * n_qt;
+
+    if (warp == 8 && lane == 0) {
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_kv);
+        for (int i = 0; i < P_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&stage_free[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&s_ready[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_ready[i], 1); mbar_init(&tmem_free[i], 4); }
+        mbar_fence_init();
+    }
+    if (warp == 9) tmem_alloc<512>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr;
+
+    if (warp == 8) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            const uint32_t tx = (uint32_t)(n_qt * AQ * 128 + 2 * Tp * 128);
+            for (int n = 0; n < my_items; ++n) {
+                const int item = blockIdx.x + n * gridDim.x;
+                const int b = item / H, h = item - b * H;
+                const int st = n % P_STAGES;
+                mbar_wait(&stage_free[st], ((n / P_STAGES) & 1) ^ 1);
+                uint8_t* base = smem + st * P_STAGE;
+                mbar_expect_tx(&full[st], tx);
+                for (int qt = 0; qt < n_qt; ++qt) tma_load_2d(base + qt * (AQ * 128), &tm_q, &full[st], h * HD, b * Tn + qt * AQ);
+                tma_load_2d(base + P_SQ, &tm_kv, &full[st], D + h * HD, b * Tn);
+                tma_load_2d(base + P_SQ + P_SK, &tm_kv, &full[st], 2 * D + h * HD, b * Tn);
+            }
+        }
+    } else if (warp == 9) {
+        // ===================== MMA issuer (single thread) =====================
+        if (lane == 0) {
+            const uint32_t idesc_s = make_idesc_bf16(AQ, Tp);
+            const uint32_t idesc_o = make_idesc_bf16(AQ, HD, 0, 1);
+            const int ksteps = Tp / 16;
+            for (int u = 0; u <= my_units; ++u) {
+                if (u < my_units) {                      // S(u) = Q_qt K^T -> TMEM half (u & 1), columns [0, Tp)
+                    const int n = u / n_qt, qt = u - n * n_qt, st = n % P_STAGES, w = u & 1, k = u >> 1;
+                    mbar_wait(&full[st], (n / P_STAGES) & 1);
+                    mbar_wait(&tmem_free[w], (k & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t sq = smem_u32(smem + st * P_STAGE + qt * (AQ * 128));
+                    const uint32_t sk = smem_u32(smem + st * P_STAGE + P_SQ);
+                    const uint64_t da = make_smem_desc_sw128(sq, 0, 1024);
+                    const uint64_t db = make_smem_desc_sw128(sk, 0, 1024);
+#pragma unroll
+                    for (int kk = 0; kk < HD / 16; ++kk) tc_mma_f16(tmem + w * 256, da + uint64_t(2 * kk), db + uint64_t(2 * kk), idesc_s, kk != 0);
+                    tc_commit(&s_ready[w]);
+                }
+                if (u >= 1) {                            // O(u-1) = P V ; A = packed bf16 P in TMEM, B = V [key][d] (MN-major)
+                    const int v = u - 1;
+                    const int n = v / n_qt, qt = v - n * n_qt, st = n % P_STAGES, w = v & 1, k = v >> 1;
+                    mbar_wait(&p_ready[w], k & 1);
+                    tc_fence_after();
+                    const uint32_t sv = smem_u32(smem + st * P_STAGE + P_SQ + P_SK);
+                    for (int kk = 0; kk < ksteps; ++kk) {
+                        const uint64_t db = make_smem_desc_sw128(sv + kk * 2048, 32768, 1024);
+                        tc_mma_f16_ts(tmem + w * 256 + P_OCOL, tmem + w * 256 + kk * 8, db, idesc_o, kk != 0);
+                    }
+                    tc_commit(&o_ready[w]);
+                    if (qt == n_qt - 1) tc_commit(&stage_free[st]);      // all MMAs reading this stage are tracked by this commit
+                }
+            }
+        }
+    } else {
+        // ===================== softmax + epilogue warpgroups: thread == query row == TMEM lane =====================
+        const int w = warp >> 2, q = warp & 3;
+        const int r = q * 32 + lane;
+        const uint32_t trow = tmem + (uint32_t(q * 32) << 16) + w * 256;
+        const int nchunk = Tp / 16;
+        constexpr float kLog2e = 1.4426950408889634f;
+        for (int u = w, k = 0; u < my_units; u += 2, ++k) {
+            const int n = u / n_qt, qt = u - n * n_qt;
+            const int item = blockIdx.x + n * gridDim.x;
+            const int b = item / H, h = item - b * H;
+            const int len = lens ? min(lens[b], Tn) : Tn;
+            const int rows_valid = min(AQ, Tn - qt * AQ);
+            const bool active = q * 32 < rows_valid;           // warp-uniform: quadrants with no valid query row skip the math
+            mbar_wait(&s_ready[w], k & 1);
+            tc_fence_after();
+            float sum = 0.f;
+            if (active) {
+                // pass 1: row max over the valid keys (TMEM loads double-buffered in registers, statically indexed)
+                float mx = -INFINITY;
+                auto max_chunk = [&](const uint32_t (&cur)[16], int c) {
+                    if (c * 16 + 16 <= len) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(cur[j]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) if (c * 16 + j < len) mx = fmaxf(mx, __uint_as_float(cur[j]));
+                    }
+                };
+                {
+                    uint32_t a0[16], a1[16];
+                    tmem_ld_32x32b_x16(trow, a0);
+                    tmem_ld_wait();
+#pragma unroll 1
+                    for (int c = 0; c < nchunk; c += 2) {
+                        if (c + 1 < nchunk) tmem_ld_32x32b_x16(trow + (c + 1) * 16, a1);
+                        max_chunk(a0, c);
+                        tmem_ld_wait();
+                        if (c + 1 >= nchunk) break;
+                        if (c + 2 < nchunk) tmem_ld_32x32b_x16(trow + (c + 2) * 16, a0);
+                        max_chunk(a1, c + 1);
+                        tmem_ld_wait();
+                    }
+                }
+                // pass 2: p = exp(s - max) -> packed bf16 written back over the columns of S this thread has already consumed
+                // (P chunk c covers 32-bit columns [8c, 8c+8); the S columns still to be read start at 16(c+1))
+                const float mxl = mx * kLog2e;                 // at least one key is valid, so the row max is finite
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                auto exp_chunk = [&](const uint32_t (&cur)[16], int c) {
+                    float p[16];
+                    const bool fullc = c * 16 + 16 <= len;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float e = ex2_approx(fmaf(__uint_as_float(cur[j]), kLog2e, -mxl));
+                        p[j] = (fullc || c * 16 + j < len) ? e : 0.f;
+                    }
+                    s0 += (p[0] + p[4]) + (p[8] + p[12]); s1 += (p[1] + p[5]) + (p[9] + p[13]);
+                    s2 += (p[2] + p[6]) + (p[10] + p[14]); s3 += (p[3] + p[7]) + (p[11] + p[15]);
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(p[2 * j], p[2 * j + 1]);
+                    tmem_st_32x32b_x8(trow + c * 8, pk);
+                };
+                {
+                    uint32_t a0[16], a1[16];
+                    tmem_ld_32x32b_x16(trow, a0);
+                    tmem_ld_wait();
+#pragma unroll 1
+                    for (int c = 0; c < nchunk; c += 2) {
+                        if (c + 1 < nchunk) tmem_ld_32x32b_x16(trow + (c + 1) * 16, a1);
+                        exp_chunk(a0, c);
+                        tmem_ld_wait();
+                        if (c + 1 >= nchunk) break;
+                        if (c + 2 < nchunk) tmem_ld_32x32b_x16(trow + (c + 2) * 16, a0);
+                        exp_chunk(a1, c + 1);
+                        tmem_ld_wait();
+                    }
+                }
+                sum = (s0 + s1) + (s2 + s3);
+                tmem_st_wait();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_ready[w]);
+            mbar_wait(&o_ready[w], k & 1);
+            tc_fence_after();
+            if (active) {
+                const int t = qt * AQ + r;
+                uint32_t o[2][32];
+                tmem_ld_32x32b_x32(trow + P_OCOL, o[0]);
+                tmem_ld_32x32b_x32(trow + P_OCOL + 32, o[1]);
+                tmem_ld_wait();
+                if (t < Tn) {
+                    const float inv = 1.0f / sum;
+                    uint4* op = reinterpret_cast<uint4*>(out + ((long long)b * Tn + t) * D + h * HD);
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            uint4 wv;
+                            wv.x = pack_bf16x2(__uint_as_float(o[hh][8 * v + 0]) * inv, __uint_as_float(o[hh][8 * v + 1]) * inv);
+                            wv.y = pack_bf16x2(__uint_as_float(o[hh][8 * v + 2]) * inv, __uint_as_float(o[hh][8 * v + 3]) * inv);
+                            wv.z = pack_bf16x2(__uint_as_float(o[hh][8 * v + 4]) * inv, __uint_as_float(o[hh][8 * v + 5]) * inv);
+                            wv.w = pack_bf16x2(__uint_as_float(o[hh][8 * v + 6]) * inv, __uint_as_float(o[hh][8 * v + 7]) * inv);
+                            op[hh * 4 + v] = wv;
+                        }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_free[w]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem);
+    }
+}
+
 }  // namespace
 
 int attention_simt(const void* qkv, void* out, int io_bf16, int B, int T, int H, const int* lens, cudaStream_t stream) {
@@ -303,8 +530,32 @@ int attention_simt(const void* qkv, void* out, int io_bf16, int B, int T, int H,
     return 0;
 }
 
-int attention_tc(const void* qkv, void* out, int B, int T, int H, const int* lens, int num_sms, cudaStream_t stream) {
+int attention_tc_v1(const void* qkv, void* out, int B, int T, int H, const int* lens, int num_sms, cudaStream_t stream) {
     (void)num_sms;
+    const int Tp = (T + 15) / 16 * 16;
+    if (Tp > 256) { set_error("attention_tc_v1: T=%d > 256 (use attention_simt)", T); return -1; }
+    const int D = H * HD;
+    CUtensorMap tq, tkv;
+    uint64_t dims[2] = {(uint64_t)(3 * D), (uint64_t)B * T};
+    uint64_t strides[1] = {(uint64_t)(3 * D) * 2};
+    uint32_t boxq[2] = {HD, AQ}, boxkv[2] = {HD, (uint32_t)Tp};
+    if (encode_tmap_bf16(&tq, qkv, 2, dims, strides, boxq)) return -1;
+    if (encode_tmap_bf16(&tkv, qkv, 2, dims, strides, boxkv)) return -1;
+    static bool configured = false;
+    if (!configured) {
+        SLSB_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+        configured = true;
+    }
+    dim3 grid((T + AQ - 1) / AQ, H, B);
+    attn_tc_v1_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(tq, tkv, static_cast<bf16*>(out), T, Tp, H, lens);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace slsb
+
+namespace slsb {
+int attention_tc(const void* qkv, void* out, int B, int T, int H, const int* lens, int num_sms, cudaStream_t stream) {
     const int Tp = (T + 15) / 16 * 16;
     if (Tp > 256) { set_error("attention_tc: T=%d > 256 (use attention_simt)", T); return -1; }
     const int D = H * HD;
@@ -316,13 +567,13 @@ int attention_tc(const void* qkv, void* out, int B, int T, int H, const int* len
     if (encode_tmap_bf16(&tkv, qkv, 2, dims, strides, boxkv)) return -1;
     static bool configured = false;
     if (!configured) {
-        SLSB_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+        SLSB_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
         configured = true;
     }
-    dim3 grid((T + AQ - 1) / AQ, H, B);
-    attn_tc_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(tq, tkv, static_cast<bf16*>(out), T, Tp, H, lens);
+    const int n_items = B * H, n_qt = (T + AQ - 1) / AQ;
+    const int grid = n_items < num_sms ? n_items : num_sms;
+    attn_tc_kernel<<<grid, P_THREADS, P_SMEM, stream>>>(tq, tkv, static_cast<bf16*>(out), T, Tp, H, n_items, n_qt, lens);
     SLSB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
-
 }  // namespace slsb

@@ -120,19 +120,26 @@ struct slsb_engine {
     int64_t launches = 0;
     // workspace
     Buf fe[2], lnbuf, qkv, attn, ffn, xmid, xfinal, xc, xpad, acts, encoded, sums, votes, thr, cut, thr_w, cut_w, pooled, logprob,
-        sls_w, sls_in, sls_part, zeros, scratch, flens, wav_stage, lens_stage, score_stage, recon, tmp_bf16, im2col, conv0_w64, ybuf;
+        sls_w, sls_in, sls_part, sls_dots, zeros, scratch, flens, wav_stage[2], lens_stage[2], score_stage[4], recon, tmp_bf16, im2col, conv0_w64, ybuf;
+    // pipelined host scoring (slsb_score_submit / slsb_score_wait): uploads run on a private copy stream into two staging
+    // slots so the H2D copy of batch i+1 overlaps the forward of batch i; up to 4 submissions may be in flight
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_slot_free[2] = {nullptr, nullptr}, ev_done[4] = {nullptr, nullptr, nullptr, nullptr};
+    int64_t submit_seq = 0;
     std::vector<Buf> X;
     // last call
     int B = 0, S = 0, T = 0, prec = 0, head = 0;
-    bool have_lens = false, have_acts = false, have_sel = false;
-    int sls_ks = 17, sls_kp = 0;
+    bool have_lens = false, have_acts = false, have_sel = false, have_dots = false;
+    int sls_ks = 17, sls_kp = 0;      // fp32 path: 17-way split-K over Kp (a multiple of 16 * 17 * 4 = 1088, so also of the 64-wide k-blocks)
     // optional per-launch CUDA-event timing of the tensor-core kernels (bench.py roofline)
     bool profiling = false;
     struct ProfRec { cudaEvent_t a, b; double flops; int kind; };
     std::vector<ProfRec> prof;
 };
 
-enum ProfKind { PK_ENC_QKV = 0, PK_ENC_OUT = 1, PK_ENC_FC1 = 2, PK_ENC_FC2 = 3, PK_CONV_GEMM = 4, PK_POS_GEMM = 5, PK_OTHER_GEMM = 6, PK_ATTN = 7, PK_COUNT = 8 };
+// kinds 0-7 count FLOPs, kinds 8+ count algorithmic HBM bytes (HBM-bound kernels)
+enum ProfKind { PK_ENC_QKV = 0, PK_ENC_OUT = 1, PK_ENC_FC1 = 2, PK_ENC_FC2 = 3, PK_CONV_GEMM = 4, PK_POS_GEMM = 5, PK_OTHER_GEMM = 6, PK_ATTN = 7,
+                PK_LN = 8, PK_SLS_POOL = 9, PK_SLS_FC1 = 10, PK_COUNT = 11 };
 
 struct ProfScope {
     slsb_engine* e; cudaStream_t st; int idx = -1;
@@ -197,11 +204,11 @@ static int build_weight_table(slsb_engine* e) {
     }
     if (c.sls_frames > 0) {
         const int kraw = (c.sls_frames / 3) * (D / 3);
-        const int q = 16 * e->sls_ks;
+        const int q = 64 * e->sls_ks;
         e->sls_kp = (kraw + q - 1) / q * q;
         add_weight(e, "sls.fc0.w", D); add_weight(e, "sls.fc0.b", 1);
         add_weight(e, "sls.bn", 4);
-        add_weight(e, "sls.fc1.w", (int64_t)c.sls_hidden * e->sls_kp); add_weight(e, "sls.fc1.b", c.sls_hidden);
+        add_weight(e, "sls.fc1.w", (int64_t)c.sls_hidden * e->sls_kp, true); add_weight(e, "sls.fc1.b", c.sls_hidden);
         add_weight(e, "sls.fc3.w", (int64_t)2 * c.sls_hidden); add_weight(e, "sls.fc3.b", 2);
     }
     for (auto& kv : e->w) {
@@ -286,8 +293,20 @@ static int attention(slsb_engine* e, bool bf, const void* qkv, void* out, int B,
     ProfScope ps(e, st, PK_ATTN, 4.0 * (double)B * H * T * T * 64);
     int impl = e->cfg.attn_impl;
     if (impl == SLSB_ATTN_AUTO) impl = (bf && T <= 256) ? SLSB_ATTN_TC : SLSB_ATTN_SIMT;
+    if ((impl == SLSB_ATTN_TC || impl == SLSB_ATTN_TC_V1) && T > 256) impl = SLSB_ATTN_SIMT;
     if (impl == SLSB_ATTN_TC && bf) LAUNCH(attention_tc(qkv, out, B, T, H, flens, e->num_sms, st));
+    else if (impl == SLSB_ATTN_TC_V1 && bf) LAUNCH(attention_tc_v1(qkv, out, B, T, H, flens, e->num_sms, st));
     else LAUNCH(attention_simt(qkv, out, bf ? 1 : 0, B, T, H, flens, st));
+    return 0;
+}
+
+// LayerNorm launch with its algorithmic HBM bytes recorded (every operand is touched exactly once)
+static int layernorm_timed(slsb_engine* e, const LnArgs& a, cudaStream_t st) {
+    const double n = (double)a.rows * a.C;
+    const double bytes = n * ((a.in_bf16 ? 2 : 4) + (a.add ? 2 : 0) + (a.sum_out ? 4 : 0) + (a.out ? (a.out_bf16 ? 2 : 4) : 0) +
+                              (a.out2 ? (a.out2_bf16 ? 2 : 4) : 0));
+    ProfScope ps(e, st, PK_LN, bytes);
+    LAUNCH(layernorm(a, st));
     return 0;
 }
 
@@ -298,11 +317,12 @@ static int check_ready(slsb_engine* e) {
 }
 
 // ---- the trunk: wav -> X[0..n_layers], xfinal (+ xc = xfinal - b_dec) ---------------------------
-static int run_trunk(slsb_engine* e, const float* wav, const int* slens, int B, int S, int prec, bool want_xc, cudaStream_t st) {
+static int run_trunk(slsb_engine* e, const float* wav, const int* slens, int B, int S, int prec, int head, cudaStream_t st) {
     const slsb_config& c = e->cfg;
     const bool bf = prec == SLSB_PREC_BF16;
     const size_t es = bf ? 2 : 4;
     const int C = c.conv_dim, D = c.embed_dim, F = c.ffn_dim, H = c.n_heads;
+    const bool want_xc = head == SLSB_HEAD_SAE || head == SLSB_HEAD_WINDOW;
     if (B <= 0 || S <= 0) { set_error("empty batch (B=%d, S=%d)", B, S); return -1; }
     std::vector<int> L(c.n_conv);
     for (int i = 0; i < c.n_conv; ++i) L[i] = conv_len(c, S, i + 1);
@@ -324,7 +344,7 @@ static int run_trunk(slsb_engine* e, const float* wav, const int* slens, int B, 
         flens = e->flens.as<int>();
         LAUNCH(frame_lengths(slens, flens, B, c.n_conv, c.conv_kernel, c.conv_stride, st));
     }
-    e->B = B; e->S = S; e->T = T; e->prec = prec; e->have_lens = slens != nullptr; e->have_acts = false; e->have_sel = false;
+    e->B = B; e->S = S; e->T = T; e->prec = prec; e->have_lens = slens != nullptr; e->have_acts = false; e->have_sel = false; e->have_dots = false;
 
     // 1. feature extractor (wav2vec2.py:843-851)
     const bool fused_ln = bf && c.reserved[0] == 0;     // reserved[0] = 1 disables the fused conv+LN+GELU tensor-core kernel
@@ -382,20 +402,31 @@ static int run_trunk(slsb_engine* e, const float* wav, const int* slens, int B, 
         //   LN1_l : X_l = xmid_{l-1} + fc2_{l-1}   (written as layer result l-1), lnbuf = LN(X_l)
         //   LN2_l : xmid = X_l + out_proj_l,        lnbuf = LN(xmid)
         if (e->ybuf.reserve((size_t)M * D * 2)) return -1;
+        // SLS head: the LayerNorm kernel that writes layer result l also emits fc0 . x_l per frame (sls_layer_weights_from_dots)
+        const bool want_dots = head == SLSB_HEAD_SLS && c.sls_frames > 0 && !slens;
+        float* dots = nullptr;
+        if (want_dots) {
+            if (e->sls_dots.reserve((size_t)c.n_layers * M * 4)) return -1;
+            dots = e->sls_dots.as<float>();
+            e->have_dots = true;
+        }
         for (int l = 0; l < c.n_layers; ++l) {
             const std::string p = "L" + std::to_string(l);
             LnArgs a;
             a.out = e->lnbuf.p; a.out_bf16 = 1; a.w = W32(p + ".ln1.w"); a.b = W32(p + ".ln1.b"); a.rows = M; a.C = D;
             if (l == 0) a.in = e->X[0].p;
-            else { a.in = e->xmid.p; a.add = e->ybuf.p; a.sum_out = e->X[l].as<float>(); }
-            LAUNCH(layernorm(a, st));
+            else {
+                a.in = e->xmid.p; a.add = e->ybuf.p; a.sum_out = e->X[l].as<float>();
+                if (want_dots) { a.dot_w = W32("sls.fc0.w"); a.dot_out = dots + (long long)(l - 1) * M; }
+            }
+            if (layernorm_timed(e, a, st)) return -1;
             if (linear(e, true, e->lnbuf.p, D, p + ".qkv.w", 3 * D, D, M, W32(p + ".qkv.b"), nullptr, 0, e->qkv.p, 3 * D, 1, ACT_NONE, st, PK_ENC_QKV)) return -1;
             if (attention(e, true, e->qkv.p, e->attn.p, B, T, H, flens, st)) return -1;
             if (linear(e, true, e->attn.p, D, p + ".out.w", D, D, M, W32(p + ".out.b"), nullptr, 0, e->ybuf.p, D, 1, ACT_NONE, st, PK_ENC_OUT)) return -1;
             LnArgs a2;
             a2.in = e->X[l].p; a2.add = e->ybuf.p; a2.sum_out = e->xmid.as<float>();
             a2.out = e->lnbuf.p; a2.out_bf16 = 1; a2.w = W32(p + ".ln2.w"); a2.b = W32(p + ".ln2.b"); a2.rows = M; a2.C = D;
-            LAUNCH(layernorm(a2, st));
+            if (layernorm_timed(e, a2, st)) return -1;
             if (linear(e, true, e->lnbuf.p, D, p + ".fc1.w", F, D, M, W32(p + ".fc1.b"), nullptr, 0, e->ffn.p, F, 1, ACT_GELU, st, PK_ENC_FC1)) return -1;
             if (linear(e, true, e->ffn.p, F, p + ".fc2.w", D, F, M, W32(p + ".fc2.b"), nullptr, 0, e->ybuf.p, D, 1, ACT_NONE, st, PK_ENC_FC2)) return -1;
         }
@@ -404,7 +435,8 @@ static int run_trunk(slsb_engine* e, const float* wav, const int* slens, int B, 
         a.in = e->xmid.p; a.add = e->ybuf.p; a.sum_out = e->X[c.n_layers].as<float>();
         a.out = e->xfinal.p; a.w = W32("enc_ln.w"); a.b = W32("enc_ln.b"); a.rows = M; a.C = D;
         if (want_xc && c.sae_dict > 0) { a.out2 = e->xc.p; a.out2_bf16 = 1; a.sub = W32("sae.b_dec"); }
-        LAUNCH(layernorm(a, st));
+        if (want_dots) { a.dot_w = W32("sls.fc0.w"); a.dot_out = dots + (long long)(c.n_layers - 1) * M; }
+        if (layernorm_timed(e, a, st)) return -1;
         return 0;
     }
     for (int l = 0; l < c.n_layers; ++l) {
@@ -510,18 +542,39 @@ static int run_head(slsb_engine* e, int head, int prec, float* logprob, cudaStre
         if (c.sls_frames <= 0) { set_error("engine was created without SLS weights"); return -1; }
         if (T != c.sls_frames) { set_error("SLS head: fc1 is sized for %d frames, got %d", c.sls_frames, T); return -1; }
         if (flens) { set_error("SLS head with per-utterance lengths is not defined by the reference"); return -1; }
-        const int KS = e->sls_ks, Kp = e->sls_kp, Hs = c.sls_hidden;
+        const int Kp = e->sls_kp, Hs = c.sls_hidden;
+        // split-K over the 22 848-wide fc1 reduction: bf16 -> one tcgen05 tile per SM (n-tile x k-split), fp32 -> 17 SIMT groups
+        int KS = e->sls_ks;
+        if (bf) {
+            const int total_kb = Kp / 64, n_tiles = Hs / 256 > 0 ? Hs / 256 : 1;
+            int want = e->num_sms / n_tiles; if (want < 1) want = 1; if (want > total_kb) want = total_kb;
+            const int per = (total_kb + want - 1) / want;
+            KS = (total_kb + per - 1) / per;
+        }
         if (e->sls_w.reserve((size_t)B * c.n_layers * 4) || e->sls_in.reserve((size_t)B * Kp * 4) ||
-            e->sls_part.reserve((size_t)B * KS * Hs * 4) || e->zeros.reserve((size_t)KS * Hs * 4)) return -1;
+            e->sls_part.reserve((size_t)B * KS * Hs * 4) || e->zeros.reserve((size_t)(KS > 1 ? KS : 1) * Hs * 4)) return -1;
         std::vector<const float*> layers(c.n_layers);
         for (int l = 0; l < c.n_layers; ++l) layers[l] = e->X[l + 1].as<float>();
-        LAUNCH(sls_layer_weights(layers.data(), c.n_layers, B, T, D, W32("sls.fc0.w"), W32("sls.fc0.b"), e->sls_w.as<float>(), nullptr, st));
-        LAUNCH(sls_fuse_pool(layers.data(), c.n_layers, e->sls_w.as<float>(), B, T, D, W32("sls.bn"), 1e-5f, e->sls_in.as<float>(), Kp, st));
-        SimtGemmArgs g;      // split-K: group ks handles columns [ks*Kp/KS, (ks+1)*Kp/KS) of both operands
-        g.A = e->sls_in.p; g.lda = Kp; g.a_group_offset = Kp / KS; g.W = W32("sls.fc1.w"); g.ldw = Kp; g.w_group_stride = Kp / KS;
-        g.groups = KS; g.n_per_group = Hs; g.M = B; g.N = Hs; g.K = Kp / KS; g.batches = 1;
-        g.out = e->sls_part.p; g.ldc = (long long)KS * Hs; g.bias = e->zeros.as<float>(); g.act = ACT_NONE;
-        LAUNCH(simt_gemm(g, st));
+        if (e->have_dots) LAUNCH(sls_layer_weights_from_dots(e->sls_dots.as<float>(), c.n_layers, B, T, W32("sls.fc0.b"), e->sls_w.as<float>(), st));
+        else LAUNCH(sls_layer_weights(layers.data(), c.n_layers, B, T, D, W32("sls.fc0.w"), W32("sls.fc0.b"), e->sls_w.as<float>(), nullptr, st));
+        {   // every fp32 layer output is read once; the pooled [B, 67*341] matrix is written once
+            ProfScope ps(e, st, PK_SLS_POOL, (double)c.n_layers * M * D * 4 + (double)B * Kp * (bf ? 2 : 4));
+            LAUNCH(sls_fuse_pool(layers.data(), c.n_layers, e->sls_w.as<float>(), B, T, D, W32("sls.bn"), 1e-5f, e->sls_in.p, bf ? 1 : 0, Kp, st));
+        }
+        if (bf) {   // fc1 weight [1024, 22848] bf16 streamed once per batch; fp32 partials [B][KS][Hs]
+            ProfScope ps(e, st, PK_SLS_FC1, (double)Hs * Kp * 2 + (double)B * Kp * 2 + (double)B * KS * Hs * 4);
+            TcGemmArgs g;
+            g.a_mode = A_PLAIN; g.A = e->sls_in.p; g.lda = Kp; g.W = W16("sls.fc1.w"); g.ldw = Kp; g.M = B; g.N = Hs; g.K = Kp; g.k_splits = KS;
+            g.out = e->sls_part.p; g.ldc = (long long)KS * Hs; g.out_batch_stride = Hs; g.out_bf16 = 0; g.bias = e->zeros.as<float>(); g.act = ACT_NONE;
+            LAUNCH(tc_gemm(g, e->num_sms, st));
+        } else {
+            SimtGemmArgs g;      // split-K: group ks handles columns [ks*Kp/KS, (ks+1)*Kp/KS) of both operands
+            g.A = e->sls_in.p; g.lda = Kp; g.a_group_offset = Kp / KS; g.W = W32("sls.fc1.w"); g.ldw = Kp; g.w_group_stride = Kp / KS;
+            g.groups = KS; g.n_per_group = Hs; g.M = B; g.N = Hs; g.K = Kp / KS; g.batches = 1;
+            g.out = e->sls_part.p; g.ldc = (long long)KS * Hs; g.bias = e->zeros.as<float>(); g.act = ACT_NONE;
+            ProfScope ps(e, st, PK_SLS_FC1, (double)Hs * Kp * 4 + (double)B * Kp * 4 + (double)B * KS * Hs * 4);
+            LAUNCH(simt_gemm(g, st));
+        }
         LAUNCH(sls_tail(e->sls_part.as<float>(), KS, B, Hs, W32("sls.fc1.b"), W32("sls.fc3.w"), W32("sls.fc3.b"), logprob, st));
         return 0;
     }
@@ -565,9 +618,14 @@ int slsb_destroy(slsb_engine* e) {
     cudaDeviceSynchronize();
     for (auto& kv : e->w) { if (kv.second.f32) cudaFree(kv.second.f32); if (kv.second.b16) cudaFree(kv.second.b16); }
     Buf* bufs[] = {&e->fe[0], &e->fe[1], &e->lnbuf, &e->qkv, &e->attn, &e->ffn, &e->xmid, &e->xfinal, &e->xc, &e->xpad, &e->acts, &e->encoded,
-                   &e->sums, &e->votes, &e->thr, &e->cut, &e->thr_w, &e->cut_w, &e->pooled, &e->logprob, &e->sls_w, &e->sls_in, &e->sls_part,
-                   &e->zeros, &e->scratch, &e->flens, &e->wav_stage, &e->lens_stage, &e->score_stage, &e->recon, &e->tmp_bf16, &e->im2col, &e->conv0_w64, &e->ybuf};
+                   &e->sums, &e->votes, &e->thr, &e->cut, &e->thr_w, &e->cut_w, &e->pooled, &e->logprob, &e->sls_w, &e->sls_in, &e->sls_part, &e->sls_dots,
+                   &e->zeros, &e->scratch, &e->flens, &e->wav_stage[0], &e->wav_stage[1], &e->lens_stage[0], &e->lens_stage[1], &e->score_stage[0],
+                   &e->score_stage[1], &e->score_stage[2], &e->score_stage[3], &e->recon, &e->tmp_bf16, &e->im2col, &e->conv0_w64, &e->ybuf};
     for (Buf* b : bufs) b->release();
+    for (int i = 0; i < 2; ++i) { if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]); if (e->ev_slot_free[i]) cudaEventDestroy(e->ev_slot_free[i]); }
+    for (int i = 0; i < 4; ++i) if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    for (auto& r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto& b : e->X) b.release();
     delete e;
     return 0;
@@ -609,7 +667,7 @@ int slsb_forward(slsb_engine* e, const float* wav_dev, const int32_t* sample_len
                  float* logprob_dev, void* stream) {
     if (check_ready(e)) return -1;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (run_trunk(e, wav_dev, sample_lens_dev, B, S, precision, head == SLSB_HEAD_SAE || head == SLSB_HEAD_WINDOW, st)) return -1;
+    if (run_trunk(e, wav_dev, sample_lens_dev, B, S, precision, head, st)) return -1;
     e->head = head;
     if (head == SLSB_HEAD_NONE) return 0;
     if (!logprob_dev) { set_error("slsb_forward: logprob_dev is null"); return -1; }
@@ -619,7 +677,7 @@ int slsb_forward(slsb_engine* e, const float* wav_dev, const int32_t* sample_len
 int slsb_extract_feat(slsb_engine* e, const float* wav_dev, const int32_t* sample_lens_dev, int B, int S, int precision, float* x_dev, void* stream) {
     if (check_ready(e)) return -1;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (run_trunk(e, wav_dev, sample_lens_dev, B, S, precision, false, st)) return -1;
+    if (run_trunk(e, wav_dev, sample_lens_dev, B, S, precision, SLSB_HEAD_NONE, st)) return -1;
     e->head = SLSB_HEAD_NONE;
     if (x_dev) SLSB_CUDA_CHECK(cudaMemcpyAsync(x_dev, e->xfinal.p, (size_t)B * e->T * e->cfg.embed_dim * 4, cudaMemcpyDeviceToDevice, st));
     return 0;
@@ -711,23 +769,60 @@ int slsb_sae_loss(slsb_engine* e, int precision, float* loss_dev, void* stream) 
     return 0;
 }
 
-int slsb_score_host(slsb_engine* e, const float* wav_host, const int32_t* lens_host, int B, int S, int head, int precision, float* scores_host, void* stream) {
+int64_t slsb_score_submit(slsb_engine* e, const float* wav_host, const int32_t* lens_host, int B, int S, int head, int precision,
+                          float* scores_host, void* stream) {
     if (check_ready(e)) return -1;
-    if (!wav_host || !scores_host) { set_error("slsb_score_host: null buffer"); return -1; }
+    if (!wav_host || !scores_host) { set_error("slsb_score_submit: null buffer"); return -1; }
+    if (head == SLSB_HEAD_NONE) { set_error("slsb_score_submit: a classifier head is required"); return -1; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (e->wav_stage.reserve((size_t)B * S * 4) || e->logprob.reserve((size_t)B * 2 * 4) || e->score_stage.reserve((size_t)B * 4) ||
-        e->lens_stage.reserve((size_t)B * 4)) return -1;
-    SLSB_CUDA_CHECK(cudaMemcpyAsync(e->wav_stage.p, wav_host, (size_t)B * S * 4, cudaMemcpyHostToDevice, st));
+    if (!e->copy_stream) {
+        SLSB_CUDA_CHECK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            SLSB_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDisableTiming));
+            SLSB_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_slot_free[i], cudaEventDisableTiming));
+        }
+        for (int i = 0; i < 4; ++i) SLSB_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming));
+    }
+    const int64_t ticket = e->submit_seq;
+    const int slot = (int)(ticket & 1), ring = (int)(ticket & 3);
+    if (ticket >= 4) SLSB_CUDA_CHECK(cudaEventSynchronize(e->ev_done[ring]));      // bound the submissions in flight (scores_host reuse is the caller's business)
+    if (e->wav_stage[slot].reserve((size_t)B * S * 4) || e->lens_stage[slot].reserve((size_t)B * 4) || e->logprob.reserve((size_t)B * 2 * 4) ||
+        e->score_stage[ring].reserve((size_t)B * 4)) return -1;
+    // upload on the copy stream once the forward that last read this slot has finished
+    if (ticket >= 2) SLSB_CUDA_CHECK(cudaStreamWaitEvent(e->copy_stream, e->ev_slot_free[slot], 0));
+    SLSB_CUDA_CHECK(cudaMemcpyAsync(e->wav_stage[slot].p, wav_host, (size_t)B * S * 4, cudaMemcpyHostToDevice, e->copy_stream));
     const int32_t* lens_dev = nullptr;
     if (lens_host) {
-        SLSB_CUDA_CHECK(cudaMemcpyAsync(e->lens_stage.p, lens_host, (size_t)B * 4, cudaMemcpyHostToDevice, st));
-        lens_dev = e->lens_stage.as<int32_t>();
+        SLSB_CUDA_CHECK(cudaMemcpyAsync(e->lens_stage[slot].p, lens_host, (size_t)B * 4, cudaMemcpyHostToDevice, e->copy_stream));
+        lens_dev = e->lens_stage[slot].as<int32_t>();
     }
-    if (slsb_forward(e, e->wav_stage.as<float>(), lens_dev, B, S, head, precision, e->logprob.as<float>(), stream)) return -1;
-    LAUNCH(scores_from_logprob(e->logprob.as<float>(), e->score_stage.as<float>(), B, st));
-    SLSB_CUDA_CHECK(cudaMemcpyAsync(scores_host, e->score_stage.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-    SLSB_CUDA_CHECK(cudaStreamSynchronize(st));
+    SLSB_CUDA_CHECK(cudaEventRecord(e->ev_h2d[slot], e->copy_stream));
+    SLSB_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_h2d[slot], 0));
+    if (slsb_forward(e, e->wav_stage[slot].as<float>(), lens_dev, B, S, head, precision, e->logprob.as<float>(), stream)) return -1;
+    SLSB_CUDA_CHECK(cudaEventRecord(e->ev_slot_free[slot], st));
+    LAUNCH(scores_from_logprob(e->logprob.as<float>(), e->score_stage[ring].as<float>(), B, st));
+    SLSB_CUDA_CHECK(cudaMemcpyAsync(scores_host, e->score_stage[ring].p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    SLSB_CUDA_CHECK(cudaEventRecord(e->ev_done[ring], st));
+    e->submit_seq = ticket + 1;
+    return ticket;
+}
+
+int slsb_score_wait(slsb_engine* e, int64_t ticket) {
+    if (!e) { set_error("null engine"); return -1; }
+    if (ticket >= e->submit_seq) { set_error("slsb_score_wait: ticket %lld was never submitted", (long long)ticket); return -1; }
+    const int64_t lo = ticket < 0 ? (e->submit_seq > 4 ? e->submit_seq - 4 : 0) : ticket;
+    const int64_t hi = ticket < 0 ? e->submit_seq : ticket + 1;
+    for (int64_t t = lo; t < hi; ++t) {
+        if (t + 4 < e->submit_seq) continue;                 // its ring slot was re-used, which already waited for it
+        SLSB_CUDA_CHECK(cudaEventSynchronize(e->ev_done[t & 3]));
+    }
     return 0;
+}
+
+int slsb_score_host(slsb_engine* e, const float* wav_host, const int32_t* lens_host, int B, int S, int head, int precision, float* scores_host, void* stream) {
+    const int64_t t = slsb_score_submit(e, wav_host, lens_host, B, S, head, precision, scores_host, stream);
+    if (t < 0) return -1;
+    return slsb_score_wait(e, t);
 }
 
 int slsb_profile_enable(slsb_engine* e, int on) {
@@ -781,6 +876,20 @@ int slsb_op_gemm(int precision, const void* A, const void* W, const float* bias,
     return simt_gemm(g, st);
 }
 
+int slsb_op_gemm_splitk(const void* A, const void* W, float* partial, int M, int N, int K, int k_splits, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* zeros = nullptr;
+    SLSB_CUDA_CHECK(cudaMalloc(&zeros, (size_t)N * 4));
+    SLSB_CUDA_CHECK(cudaMemsetAsync(zeros, 0, (size_t)N * 4, st));
+    TcGemmArgs g;
+    g.A = A; g.lda = K; g.W = W; g.ldw = K; g.M = M; g.N = N; g.K = K; g.k_splits = k_splits;
+    g.out = partial; g.ldc = (long long)k_splits * N; g.out_batch_stride = N; g.out_bf16 = 0; g.bias = zeros; g.act = ACT_NONE;
+    const int rc = tc_gemm(g, device_sms(), st);
+    cudaStreamSynchronize(st);
+    cudaFree(zeros);
+    return rc;
+}
+
 int slsb_op_conv(int precision, const void* x, const void* W, const float* bias, void* out, int B, int L_in, int C, int N, int k, int stride, void* stream) {
     slsb_engine tmp;      // only num_sms / launches are touched
     tmp.num_sms = device_sms();
@@ -832,8 +941,9 @@ int slsb_op_layernorm(const void* in, int in_bf16, void* out, int out_bf16, cons
 
 int slsb_op_attention(int impl, int io_bf16, const void* qkv, void* out, int B, int T, int H, const int32_t* frame_lens_dev, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (impl == SLSB_ATTN_TC) {
+    if (impl == SLSB_ATTN_TC || impl == SLSB_ATTN_TC_V1) {
         if (!io_bf16) { set_error("attention_tc is bf16 only"); return -1; }
+        if (impl == SLSB_ATTN_TC_V1) return attention_tc_v1(qkv, out, B, T, H, frame_lens_dev, device_sms(), st);
         return attention_tc(qkv, out, B, T, H, frame_lens_dev, device_sms(), st);
     }
     return attention_simt(qkv, out, io_bf16, B, T, H, frame_lens_dev, st);

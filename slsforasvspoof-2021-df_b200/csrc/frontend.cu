@@ -91,10 +91,11 @@ template <> __device__ __forceinline__ void store4<bf16>(bf16* p, const float (&
     *reinterpret_cast<uint2*>(p) = t;
 }
 
-template <typename TI, typename TO, typename TO2, int NV, bool GELU, bool EXACT>
-__global__ void __launch_bounds__(256) ln_kernel(const TI* __restrict__ in, const bf16* __restrict__ add, float* __restrict__ sum_out,
+template <typename TI, typename TO, typename TO2, int NV, bool GELU, bool EXACT, bool DOT>
+__global__ void __launch_bounds__(256, 4) ln_kernel(const TI* __restrict__ in, const bf16* __restrict__ add, float* __restrict__ sum_out,
                                                  TO* __restrict__ out, TO2* __restrict__ out2,
                                                  const float* __restrict__ sub, const float* __restrict__ w, const float* __restrict__ b,
+                                                 const float* __restrict__ dot_w, float* __restrict__ dot_out,
                                                  long long rows, float eps) {
     constexpr int C = NV * 128;
     const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -104,15 +105,25 @@ __global__ void __launch_bounds__(256) ln_kernel(const TI* __restrict__ in, cons
     float v[NV][4];
     float s = 0.f;
 #pragma unroll
+    for (int i = 0; i < NV; ++i) load4<TI>(x + (i * 32 + lane) * 4, v[i]);      // all loads of the row in flight before the first use
+    float dot = 0.f;
+#pragma unroll
     for (int i = 0; i < NV; ++i) {
-        load4<TI>(x + (i * 32 + lane) * 4, v[i]);
         if (add) {      // residual stream + bf16 branch output (out_proj / fc2), summed in fp32 and optionally written back
             float y[4];
             load4<bf16>(add + row * C + (i * 32 + lane) * 4, y);
             v[i][0] += y[0]; v[i][1] += y[1]; v[i][2] += y[2]; v[i][3] += y[3];
             if (sum_out) store4<float>(sum_out + row * C + (i * 32 + lane) * 4, v[i]);
         }
+        if constexpr (DOT) {   // SLS layer weighting: fc0 . x_row of the (pre-norm) residual stream
+            const float4 dw = __ldg(reinterpret_cast<const float4*>(dot_w + (i * 32 + lane) * 4));
+            dot = fmaf(v[i][0], dw.x, dot); dot = fmaf(v[i][1], dw.y, dot); dot = fmaf(v[i][2], dw.z, dot); dot = fmaf(v[i][3], dw.w, dot);
+        }
         s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+    }
+    if constexpr (DOT) {
+        dot = warp_sum(dot);                       // fixed shuffle tree: bit-stable
+        if (lane == 0) dot_out[row] = dot;
     }
     const float mean = warp_sum(s) * (1.0f / C);
     float q = 0.f;
@@ -147,10 +158,13 @@ int ln_launch(const LnArgs& a, cudaStream_t stream) {
     const TI* in = static_cast<const TI*>(a.in); TO* out = static_cast<TO*>(a.out); TO2* out2 = static_cast<TO2*>(a.out2);
     const bf16* add = static_cast<const bf16*>(a.add);
     if (a.gelu) {
-        if (a.exact_gelu) ln_kernel<TI, TO, TO2, NV, true, true><<<grid, 256, 0, stream>>>(in, add, a.sum_out, out, out2, a.sub, a.w, a.b, a.rows, a.eps);
-        else ln_kernel<TI, TO, TO2, NV, true, false><<<grid, 256, 0, stream>>>(in, add, a.sum_out, out, out2, a.sub, a.w, a.b, a.rows, a.eps);
+        if (a.dot_out) { set_error("layernorm: dot_out is not combined with gelu"); return -1; }
+        if (a.exact_gelu) ln_kernel<TI, TO, TO2, NV, true, true, false><<<grid, 256, 0, stream>>>(in, add, a.sum_out, out, out2, a.sub, a.w, a.b, a.dot_w, a.dot_out, a.rows, a.eps);
+        else ln_kernel<TI, TO, TO2, NV, true, false, false><<<grid, 256, 0, stream>>>(in, add, a.sum_out, out, out2, a.sub, a.w, a.b, a.dot_w, a.dot_out, a.rows, a.eps);
+    } else if (a.dot_out) {
+        ln_kernel<TI, TO, TO2, NV, false, true, true><<<grid, 256, 0, stream>>>(in, add, a.sum_out, out, out2, a.sub, a.w, a.b, a.dot_w, a.dot_out, a.rows, a.eps);
     } else {
-        ln_kernel<TI, TO, TO2, NV, false, true><<<grid, 256, 0, stream>>>(in, add, a.sum_out, out, out2, a.sub, a.w, a.b, a.rows, a.eps);
+        ln_kernel<TI, TO, TO2, NV, false, true, false><<<grid, 256, 0, stream>>>(in, add, a.sum_out, out, out2, a.sub, a.w, a.b, a.dot_w, a.dot_out, a.rows, a.eps);
     }
     SLSB_CUDA_CHECK(cudaGetLastError());
     return 0;

@@ -52,6 +52,7 @@ struct DevParams {
     const float* residual;
     long long ldr, res_batch_stride;
     int act, out_bf16;
+    int kb_per_split;  // A_PLAIN split-K: batch index b selects k-blocks [b * kb_per_split, ...) and partial-output slab b (0 = off)
     int tma_store;     // bf16 output leaves through smem staging + cp.async.bulk.tensor stores
     int debug_flags;   // bit0: epilogue does everything except the global stores / residual loads (mainloop ceiling measurements)
 };
@@ -247,7 +248,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const int n_blk = t % p.n_tiles; t /= p.n_tiles;      // n fastest: the CTAs running together share one band of A
                 const int m_blk = t % p.m_tiles;
                 const int b = t / p.m_tiles;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                int kb_lo = 0, kb_hi = num_kb;
+                if constexpr (A_MODE == A_PLAIN) {
+                    if (p.kb_per_split > 0) { kb_lo = b * p.kb_per_split; kb_hi = min(num_kb, kb_lo + p.kb_per_split); }
+                }
+                for (int kb = kb_lo; kb < kb_hi; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Plan::kStage;
                     uint8_t* sb = sa + Plan::kStageA;
@@ -278,7 +283,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                int nkb = num_kb;
+                if constexpr (A_MODE == A_PLAIN) {
+                    if (p.kb_per_split > 0) {
+                        const int kb_lo = (tile / (p.m_tiles * p.n_tiles)) * p.kb_per_split;
+                        nkb = min(num_kb, kb_lo + p.kb_per_split) - kb_lo;
+                    }
+                }
+                for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Plan::kStage);
@@ -411,12 +423,19 @@ int tc_gemm(const TcGemmArgs& g, int num_sms, cudaStream_t stream) {
     dp.out = g.out; dp.ldc = g.ldc; dp.out_batch_stride = g.out_batch_stride;
     dp.bias = g.bias; dp.residual = g.residual; dp.ldr = g.ldr; dp.res_batch_stride = g.res_batch_stride;
     dp.act = g.act; dp.out_bf16 = g.out_bf16;
+    if (g.k_splits > 1) {
+        if (g.a_mode != A_PLAIN || g.batches != 1) { set_error("tc_gemm: split-K needs A_PLAIN and batches == 1"); return -1; }
+        const int total_kb = g.K / BLOCK_K;
+        dp.kb_per_split = (total_kb + g.k_splits - 1) / g.k_splits;
+        dp.batches = (total_kb + dp.kb_per_split - 1) / dp.kb_per_split;      // every split owns >= 1 k-block
+        if (dp.batches != g.k_splits) { set_error("tc_gemm: k_splits=%d leaves empty splits for K=%d (use %d)", g.k_splits, g.K, dp.batches); return -1; }
+    }
     { const char* dbg = getenv("SLSB_DEBUG_FLAGS"); dp.debug_flags = dbg ? atoi(dbg) : 0; }
 
     CUtensorMap ta, tb, to;
     memset(&to, 0, sizeof(to));
     // bf16 outputs of full-width tiles leave through TMA stores (BLOCK_N = 256 -> two 128-column halves of two 64-column groups)
-    dp.tma_store = (g.out_bf16 && g.residual == nullptr && block_n == 256 && g.a_mode != A_POS && !getenv("SLSB_NO_TMA_STORE")) ? 1 : 0;
+    dp.tma_store = (g.out_bf16 && g.residual == nullptr && block_n == 256 && g.a_mode != A_POS && g.k_splits <= 1 && !getenv("SLSB_NO_TMA_STORE")) ? 1 : 0;
     if (dp.tma_store) {
         if (g.a_mode == A_CONV) {
             uint64_t dims[3] = {(uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.batches};

@@ -263,34 +263,65 @@ __device__ __forceinline__ float selu(float x) {
     return scale * (x > 0.f ? x : alpha * (expf(x) - 1.0f));
 }
 
-// grid (T/3, B), D threads: weighted layer sum for 3 frames, BN (eval affine) + SELU, then 3x3 max pool -> out[b][i*(D/3)+j]
-__global__ void sls_fuse_pool_kernel(LayerPtrs L, int n_layers, const float* __restrict__ layer_w, int T, int D, const float* __restrict__ bn, float bn_eps,
-                                     float* __restrict__ out, int ldo) {
+// layer weights from the per-frame fc0 dots the LayerNorm kernels emitted while they advanced the residual stream
+// (fc0(mean_t x) == mean_t fc0(x)): grid (n_layers, B), one warp, fixed-order reduction
+__global__ void __launch_bounds__(32) sls_weights_from_dots_kernel(const float* __restrict__ dots, long long M, int T, const float* __restrict__ fc0_b,
+                                                                   float* __restrict__ layer_w, int n_layers) {
+    const int l = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;
+    const float* d = dots + (long long)l * M + (long long)b * T;
+    float s = 0.f;
+    for (int t = lane; t < T; t += 32) s += d[t];
+    s = warp_sum(s);
+    if (lane == 0) layer_w[b * n_layers + l] = 1.0f / (1.0f + expf(-(s / (float)T + fc0_b[0])));
+}
+
+// grid (T/3, B), D/4 threads x 4 channels: weighted layer sum for 3 frames (12 independent 16-byte loads in flight per
+// layer group), BN (eval affine) + SELU, then 3x3 max pool -> out[b][i*(D/3)+j].  Every layer output is read exactly once.
+template <typename TO>
+__global__ void __launch_bounds__(256) sls_fuse_pool_kernel(LayerPtrs L, int n_layers, const float* __restrict__ layer_w, int T, int D,
+                                                            const float* __restrict__ bn, float bn_eps, TO* __restrict__ out, int ldo) {
     extern __shared__ float fp_smem[];   // [3][D]
     __shared__ float lw[32];
-    const int i = blockIdx.x, b = blockIdx.y, c = threadIdx.x;
-    if (c < n_layers) lw[c] = layer_w[b * n_layers + c];
+    const int i = blockIdx.x, b = blockIdx.y, c = threadIdx.x * 4;
+    if (threadIdx.x < n_layers) lw[threadIdx.x] = layer_w[b * n_layers + threadIdx.x];
     __syncthreads();
     const float g = bn[0] / sqrtf(bn[3] + bn_eps), beta = bn[1], rm = bn[2];
     if (c < D) {
+        const long long off = ((long long)b * T + 3 * i) * D + c;
+        float4 s[3];
+#pragma unroll
+        for (int di = 0; di < 3; ++di) s[di] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int l = 0; l < n_layers; ++l) {
+            const float w = lw[l];
+            const float* base = L.p[l] + off;
+#pragma unroll
+            for (int di = 0; di < 3; ++di) {
+                const float4 v = __ldcs(reinterpret_cast<const float4*>(base + (long long)di * D));
+                s[di].x = fmaf(v.x, w, s[di].x); s[di].y = fmaf(v.y, w, s[di].y);
+                s[di].z = fmaf(v.z, w, s[di].z); s[di].w = fmaf(v.w, w, s[di].w);
+            }
+        }
 #pragma unroll
         for (int di = 0; di < 3; ++di) {
-            const long long off = ((long long)b * T + 3 * i + di) * D + c;
-            float s = 0.f;
-            for (int l = 0; l < n_layers; ++l) s = fmaf(L.p[l][off], lw[l], s);
-            fp_smem[di * D + c] = selu((s - rm) * g + beta);
+            float4 o;
+            o.x = selu((s[di].x - rm) * g + beta); o.y = selu((s[di].y - rm) * g + beta);
+            o.z = selu((s[di].z - rm) * g + beta); o.w = selu((s[di].w - rm) * g + beta);
+            *reinterpret_cast<float4*>(fp_smem + di * D + c) = o;
         }
     }
     __syncthreads();
     const int J = D / 3;
-    if (c < J) {
+    for (int j = threadIdx.x; j < J; j += blockDim.x) {
         float m = -INFINITY;
 #pragma unroll
         for (int di = 0; di < 3; ++di)
 #pragma unroll
-            for (int dj = 0; dj < 3; ++dj) m = fmaxf(m, fp_smem[di * D + 3 * c + dj]);
-        out[(long long)b * ldo + i * J + c] = m;
+            for (int dj = 0; dj < 3; ++dj) m = fmaxf(m, fp_smem[di * D + 3 * j + dj]);
+        out[(long long)b * ldo + i * J + j] = from_f32<TO>(m);
     }
+    if (i == (int)gridDim.x - 1)          // zero the K padding of this utterance's row (fc1 reads whole 64-column k-blocks)
+        for (int j = (int)gridDim.x * J + threadIdx.x; j < ldo; j += blockDim.x) out[(long long)b * ldo + j] = from_f32<TO>(0.f);
 }
 
 // partial sums [B][KS][N] -> h = selu(sum + bias) -> fc3 -> selu -> log_softmax ; one block per utterance
@@ -408,13 +439,21 @@ int sls_layer_weights(const float* const* layers, int n_layers, int B, int T, in
     SLSB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
+int sls_layer_weights_from_dots(const float* dots, int n_layers, int B, int T, const float* fc0_b, float* layer_w, cudaStream_t stream) {
+    dim3 grid(n_layers, B);
+    sls_weights_from_dots_kernel<<<grid, 32, 0, stream>>>(dots, (long long)B * T, T, fc0_b, layer_w, n_layers);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
 int sls_fuse_pool(const float* const* layers, int n_layers, const float* layer_w, int B, int T, int D, const float* bn, float bn_eps,
-                  float* out, int ldo, cudaStream_t stream) {
+                  void* out, int out_bf16, int ldo, cudaStream_t stream) {
     if (n_layers > 32 || D > 1024) { set_error("sls_fuse_pool: n_layers<=32, D<=1024"); return -1; }
     LayerPtrs L{};
     for (int i = 0; i < n_layers; ++i) L.p[i] = layers[i];
+    if (D % 4 != 0) { set_error("sls_fuse_pool: D must be a multiple of 4"); return -1; }
     dim3 grid(T / 3, B);
-    sls_fuse_pool_kernel<<<grid, D, 3 * D * sizeof(float), stream>>>(L, n_layers, layer_w, T, D, bn, bn_eps, out, ldo);
+    if (out_bf16) sls_fuse_pool_kernel<bf16><<<grid, 256, 3 * D * sizeof(float), stream>>>(L, n_layers, layer_w, T, D, bn, bn_eps, static_cast<bf16*>(out), ldo);
+    else sls_fuse_pool_kernel<float><<<grid, 256, 3 * D * sizeof(float), stream>>>(L, n_layers, layer_w, T, D, bn, bn_eps, static_cast<float*>(out), ldo);
     SLSB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

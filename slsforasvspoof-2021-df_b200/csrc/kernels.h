@@ -16,6 +16,7 @@ struct TcGemmArgs {
     long long ldw = 0;
     int M = 0, N = 0, K = 0;      // M = rows per batch item
     int batches = 1;
+    int k_splits = 1;             // A_PLAIN only: split s computes k-blocks [s*ceil(K/64/k_splits), ...) into out + s*out_batch_stride
     // A_CONV
     int conv_cin = 0, conv_stride = 0, conv_lin = 0;
     // A_POS
@@ -72,6 +73,7 @@ struct LnArgs {
     void* out = nullptr; int out_bf16 = 0;
     void* out2 = nullptr; int out2_bf16 = 0; const float* sub = nullptr;   // out2 = y - sub
     const float* w = nullptr; const float* b = nullptr;
+    const float* dot_w = nullptr; float* dot_out = nullptr;   // optional: dot_out[row] = sum_c (in + add)[row, c] * dot_w[c]
     long long rows = 0; int C = 0; int gelu = 0; int exact_gelu = 1; float eps = 1e-5f;
 };
 int layernorm(const LnArgs& a, cudaStream_t stream);
@@ -89,6 +91,7 @@ int frame_lengths(const int* sample_lens, int* frame_lens, int B, int n_conv, co
 // qkv [B*T, 3*D] (q pre-scaled), heads of 64; out [B*T, D]; keys >= lens[b] masked (lens may be null)
 int attention_simt(const void* qkv, void* out, int io_bf16, int B, int T, int H, const int* lens, cudaStream_t stream);
 int attention_tc(const void* qkv_bf16, void* out_bf16, int B, int T, int H, const int* lens, int num_sms, cudaStream_t stream);
+int attention_tc_v1(const void* qkv_bf16, void* out_bf16, int B, int T, int H, const int* lens, int num_sms, cudaStream_t stream);
 
 // ---------------------------------------------------------------- heads (heads.cu)
 // per-row top-k threshold of non-negative fp32 rows: writes thr[row] (k-th largest value) and tie_cut[row]
@@ -113,8 +116,10 @@ int mean_pool_frames(const float* x, float* pooled, int B, int T, int D, const i
 // SLS (model_backup.py:186-202 + upstream classifier)
 int sls_layer_weights(const float* const* layers, int n_layers, int B, int T, int D, const float* fc0_w, const float* fc0_b,
                       float* layer_w /*[B, n_layers]*/, const int* lens, cudaStream_t stream);
+// same weights from dots[l][b*T + t] = fc0_w . x_l[b, t, :] (emitted by the LayerNorm kernels, LnArgs::dot_out)
+int sls_layer_weights_from_dots(const float* dots, int n_layers, int B, int T, const float* fc0_b, float* layer_w, cudaStream_t stream);
 int sls_fuse_pool(const float* const* layers, int n_layers, const float* layer_w, int B, int T, int D, const float* bn /*w,b,rm,rv*/,
-                  float bn_eps, float* out /*[B, (T/3)*(D/3) padded to ldo]*/, int ldo, cudaStream_t stream);
+                  float bn_eps, void* out /*[B, (T/3)*(D/3) zero-padded to ldo], fp32 or bf16*/, int out_bf16, int ldo, cudaStream_t stream);
 // fc1 split-K partials [B][KS][Hd] -> selu(sum + b1) -> fc3 -> selu -> log_softmax
 int sls_tail(const float* partial, int KS, int B, int Hd, const float* b1, const float* w3, const float* b3, float* logprob, cudaStream_t stream);
 // scores = exp(logprob[:, 1])   (main.py:183-184)

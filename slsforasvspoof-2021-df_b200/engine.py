@@ -111,6 +111,25 @@ class Engine:
                                        stream_ptr(self.device)), "slsb_score_host")
         return scores
 
+    def score_submit(self, wav_host: torch.Tensor, head: int, precision: int, lens_host: Optional[torch.Tensor] = None,
+                     out: Optional[torch.Tensor] = None):
+        """Pipelined variant: returns ``(ticket, scores)``; ``scores`` (pinned CPU tensor) is valid after
+        ``score_wait(ticket)``.  The upload of this batch overlaps the forward of the previous submission."""
+        B, S = wav_host.shape
+        scores = out if out is not None else torch.empty(B, dtype=torch.float32, pin_memory=True)
+        t = self.lib.slsb_score_submit(self._h, ptr(wav_host), ptr(lens_host), B, S, head, precision, ptr(scores), stream_ptr(self.device))
+        if t < 0:
+            check(-1, "slsb_score_submit")
+        self._inflight = getattr(self, "_inflight", {})
+        self._inflight[t] = (wav_host, lens_host, scores)          # keep the host buffers alive until waited
+        return t, scores
+
+    def score_wait(self, ticket: int = -1) -> None:
+        check(self.lib.slsb_score_wait(self._h, ticket), "slsb_score_wait")
+        infl = getattr(self, "_inflight", {})
+        for k in [k for k in infl if ticket < 0 or k <= ticket]:
+            del infl[k]
+
     def synth_clips(self, first_utt: int, count: int, samples: int = 64600) -> torch.Tensor:
         wav = torch.empty(count, samples, device=self.device, dtype=torch.float32)
         check(self.lib.slsb_synth_clips(ptr(wav), first_utt, count, samples, stream_ptr(self.device)), "slsb_synth_clips")

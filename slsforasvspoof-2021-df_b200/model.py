@@ -277,7 +277,7 @@ class ModelSLS(_EngineOwner, nn.Module):
         return make_config(self.ssl_model.model.geo, sls_frames=self._frames, sls_hidden=self.fc1.out_features)
 
     def _sls_kp(self) -> int:
-        q = 16 * 17
+        q = 64 * 17          # matches csrc/engine.cu: a multiple of the fp32 17-way split and of the 64-wide k-blocks
         return (self.fc1.in_features + q - 1) // q * q
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

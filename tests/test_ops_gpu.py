@@ -77,6 +77,21 @@ def test_gemm_bf16_tc_deterministic(lib, cuda):
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])   # bit-stable
 
 
+@pytest.mark.parametrize("M,N,K,KS", [(64, 1024, 22848, 36), (2, 1024, 22848, 36), (100, 512, 640, 5), (130, 256, 1024, 16)])
+def test_gemm_bf16_tc_split_k(lib, cuda, M, N, K, KS):
+    """SLS fc1 path: partials[m][s][n] summed over the splits == the full product; splits are bit-stable."""
+    A, W = _rand((M, K), 12).bfloat16(), _rand((N, K), 13, 0.05).bfloat16()
+    part = torch.full((M, KS, N), float("nan"), device=cuda)
+    ok(lib, lib.slsb_op_gemm_splitk(P(A), P(W), P(part), M, N, K, KS, stream()), "gemm split-k")
+    ref = A.double() @ W.double().T
+    report(f"gemm_tc split-k {M}x{N}x{K}/{KS}", part.double().sum(1), ref, atol=2e-3 * (K / 1024) ** 0.5, rtol=1e-4)
+    per = -(-(K // 64) // KS) * 64
+    report("gemm_tc split-k slab 1", part[:, 1], A[:, per:2 * per].double() @ W[:, per:2 * per].double().T, atol=1e-3, rtol=1e-4)
+    part2 = torch.empty_like(part)
+    ok(lib, lib.slsb_op_gemm_splitk(P(A), P(W), P(part2), M, N, K, KS, stream()), "gemm split-k")
+    assert torch.equal(part, part2)
+
+
 # ------------------------------------------------------------------------------------------ strided convs as implicit GEMM
 @pytest.mark.parametrize("prec", [FP32, BF16])
 @pytest.mark.parametrize("B,Lin,k,s", [(2, 1291, 3, 2), (3, 403, 2, 2), (1, 806, 2, 2), (2, 6459, 3, 2)])
@@ -202,8 +217,8 @@ def _attn_ref(qkv, B, T, H, lens):
     return o.permute(0, 2, 1, 3).reshape(B, T, D)
 
 
-@pytest.mark.parametrize("impl,bf16", [(1, 0), (1, 1), (2, 1)])
-@pytest.mark.parametrize("B,T,lens", [(2, 201, None), (3, 137, [137, 60, 1]), (1, 256, None), (2, 49, None)])
+@pytest.mark.parametrize("impl,bf16", [(1, 0), (1, 1), (2, 1), (3, 1)])
+@pytest.mark.parametrize("B,T,lens", [(2, 201, None), (3, 137, [137, 60, 1]), (1, 256, None), (2, 49, None), (40, 201, None), (21, 100, None)])
 def test_attention(lib, cuda, impl, bf16, B, T, lens):
     H = 16
     qkv = _rand((B, T, 3 * H * 64), 60, 0.5)
