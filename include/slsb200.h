@@ -152,6 +152,10 @@ int slsb_op_layernorm(const void* in, int in_bf16, void* out, int out_bf16, cons
                       int64_t rows, int C, int gelu, int exact_gelu, void* stream);
 int slsb_op_attention(int impl, int io_bf16, const void* qkv, void* out, int B, int T, int H,
                       const int32_t* frame_lens_dev, void* stream);
+/* tcgen05 attention with a pipeline timeline: trace_dev int64 [64 units][16 events] of CTA 0, SM clock64 stamps
+ * (0 S issue, 1 S committed, 2 P seen by MMA warp, 3 PV committed, 4 S seen by softmax, 5 max pass done, 6 P published,
+ *  7 O seen, 8 epilogue done, 9 stage free seen by producer, 10 loads landed) -- tuning hook, no reference counterpart */
+int slsb_op_attention_trace(const void* qkv, void* out, int B, int T, int H, int64_t* trace_dev, void* stream);
 int slsb_op_topk(const float* x, int64_t rows, int D, int k, float* thr, int32_t* tie_cut, float* encoded_or_null, void* stream);
 
 #ifdef __cplusplus

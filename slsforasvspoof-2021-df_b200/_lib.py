@@ -67,6 +67,7 @@ _SIGNATURES = {
     "slsb_op_conv0": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "slsb_op_layernorm": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _P]),
     "slsb_op_attention": (C.c_int, [C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "slsb_op_attention_trace": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "slsb_op_topk": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, _P, _P, _P, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

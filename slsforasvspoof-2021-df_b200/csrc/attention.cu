@@ -11,6 +11,7 @@
 //                    the T > 256 path.
 #include "common.cuh"
 #include "kernels.h"
+#include <cstdlib>
 
 namespace slsb {
 namespace {
@@ -292,46 +293,67 @@ attn_tc_v1_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 //
 //   item  = one (utterance, head): K and V are loaded ONCE per item and shared by its query tiles;
 //   unit  = one 128-query tile of an item; units alternate between two softmax warpgroups (WG0 = warps 0-3, WG1 = warps 4-7),
-//           each owning one 256-column half of TMEM, so the tensor-core work of one unit hides behind the softmax of the other;
-//   warp 8 = TMA producer (2-stage ring of {Q tiles, K, V}, 96 KB / stage), warp 9 = single-thread MMA issuer.
-//   S = Q K^T lands in TMEM (fp32, Tp columns); the owning thread (== query row) takes the row max and the exponentials
-//   straight from TMEM and writes P back INTO TMEM as packed bf16 over the columns of S it has already consumed
-//   (tcgen05.st), so the second MMA (O = P V) takes its A operand from tensor memory and P never touches shared memory;
-//   V is the MN-major B operand in exactly the [key][d] layout TMA delivers.  O lands in columns 192..255 of the same half.
+//           each owning one 256-column half of TMEM;
+//   warp 8 = TMA producer (2-stage ring of {Q tiles, K, V}, 96 KB / stage);
+//   warps 9, 10 = one single-thread MMA issuer per TMEM half, so neither warpgroup ever waits behind the other one's
+//            barrier or MMA issue.
+//   S = Q K^T lands in TMEM (fp32, Tp columns); the thread that owns a query row (== TMEM lane) takes the row max and the
+//   exponentials straight from TMEM in compact loops and writes P back INTO TMEM as packed bf16 over score columns it has
+//   already consumed (tcgen05.st), so the second MMA (O = P V) takes its A operand from tensor memory and P never touches
+//   shared memory; V is the MN-major B operand in exactly the [key][d] layout TMA delivers.  O lands in columns 192..255
+//   of the same half, is pulled into registers, the half is handed back to the MMA warp at once, and the normalised rows
+//   leave through a SWIZZLE_128B smem tile + 3-D TMA store (rows >= T are clipped by the tensor map).
 // =================================================================================================
 constexpr int P_STAGES = 2;
 constexpr int P_SQ = 2 * AQ * 128;            // up to two 128-row query tiles, 32 KB
 constexpr int P_SK = 256 * 128;               // 32 KB (Tp <= 256 keys)
 constexpr int P_SV = 256 * 128;               // 32 KB
 constexpr int P_STAGE = P_SQ + P_SK + P_SV;   // 96 KB
-constexpr int P_BAR_OFFSET = P_STAGES * P_STAGE;
+constexpr int P_OUT_OFFSET = P_STAGES * P_STAGE;          // 2 x [128 rows x 64 bf16] output staging tiles (one per warpgroup)
+constexpr int P_BAR_OFFSET = P_OUT_OFFSET + 2 * 16384;
 constexpr int P_SMEM = P_BAR_OFFSET + 256;
-constexpr int P_THREADS = 320;
+constexpr int P_THREADS = 352;                // 8 softmax warps + TMA producer + 2 MMA issuers
 constexpr int P_OCOL = 192;                   // O accumulator columns inside a TMEM half
 
+// 32 score columns in registers -> four independent running maxima (cols >= len are padding / other utterances)
+__device__ __forceinline__ void max32(const uint32_t (&a)[32], int col0, int len, float (&mx)[4]) {
+    if (col0 + 32 <= len) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mx[j & 3] = fmaxf(mx[j & 3], __uint_as_float(a[j]));
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (col0 + j < len) mx[j & 3] = fmaxf(mx[j & 3], __uint_as_float(a[j]));
+    }
+}
+
 __global__ void __launch_bounds__(P_THREADS, 1)
-attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
-               bf16* __restrict__ out, int Tn, int Tp, int H, int n_items, int n_qt, const int* __restrict__ lens) {
+attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_out,
+               int Tn, int Tp, int H, int n_items, int n_qt, const int* __restrict__ lens, int stagger, long long* __restrict__ trace) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0) { if (threadIdx.x == 0) printf("slsb: dynamic smem base not 1024-aligned\n"); __trap(); }
+    // optional timeline of CTA 0 (slsb_op_attention_trace): trace[unit * 16 + event] = clock64()
+#define ATT_TRACE(unit, ev) do { if (trace != nullptr && blockIdx.x == 0 && (unit) < 64) trace[(unit) * 16 + (ev)] = clock64(); } while (0)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_BAR_OFFSET);
     uint64_t* full = bars;                    // [P_STAGES] loads landed
     uint64_t* stage_free = bars + 2;          // [P_STAGES] every MMA that reads the stage has completed
     uint64_t* s_ready = bars + 4;             // [2] S = Q K^T complete in TMEM half w
     uint64_t* p_ready = bars + 6;             // [2] P written back to TMEM half w (4 warp arrivals)
     uint64_t* o_ready = bars + 8;             // [2] O = P V complete
-    uint64_t* tmem_free = bars + 10;          // [2] epilogue has read O out of half w (4 warp arrivals)
+    uint64_t* tmem_free = bars + 10;          // [2] O has been read out of half w (4 warp arrivals)
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int D = H * HD;
     const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // items blockIdx.x, +grid, ...
     const int my_units = my_items * n_qt;
+    const int nchunk = Tp / 16;               // 16-key chunks (MMA k-steps of the second product)
 
+    griddep_launch();
     if (warp == 8 && lane == 0) {
         tma_prefetch_desc(&tm_q);
         tma_prefetch_desc(&tm_kv);
-        for (int i = 0; i < P_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&stage_free[i], 1); }
+        tma_prefetch_desc(&tm_out);
+        for (int i = 0; i < P_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&stage_free[i], n_qt); }
         for (int i = 0; i < 2; ++i) { mbar_init(&s_ready[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_ready[i], 1); mbar_init(&tmem_free[i], 4); }
         mbar_fence_init();
     }
@@ -340,6 +362,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
+    griddep_wait();                     // the prologue overlapped the QKV GEMM's tail; qkv is visible from here
 
     if (warp == 8) {
         // ===================== TMA producer =====================
@@ -350,6 +373,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                 const int b = item / H, h = item - b * H;
                 const int st = n % P_STAGES;
                 mbar_wait(&stage_free[st], ((n / P_STAGES) & 1) ^ 1);
+                ATT_TRACE(n * n_qt, 9);
                 uint8_t* base = smem + st * P_STAGE;
                 mbar_expect_tx(&full[st], tx);
                 for (int qt = 0; qt < n_qt; ++qt) tma_load_2d(base + qt * (AQ * 128), &tm_q, &full[st], h * HD, b * Tn + qt * AQ);
@@ -357,39 +381,47 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                 tma_load_2d(base + P_SQ + P_SK, &tm_kv, &full[st], 2 * D + h * HD, b * Tn);
             }
         }
-    } else if (warp == 9) {
-        // ===================== MMA issuer (single thread) =====================
+    } else if (warp >= 9) {
+        // ===================== MMA issuers: warp 9 serves TMEM half 0, warp 10 half 1 (one thread each) =====================
+        // Two independent issuers: issuing the 13 TS-MMAs of one half (~1k cycles of issue back-pressure) never delays the other
+        // half's S, and neither warpgroup waits behind the other one's barrier.  `stagger` (SLSB_ATTN_STAGGER, default 0) can
+        // start half 1 late to run the warpgroups in anti-phase; measured neutral (the softmax warps are issue-bound, not
+        // MUFU-bound: profiles/r01_attention_notes.md).
         if (lane == 0) {
+            const int w = warp - 9;
             const uint32_t idesc_s = make_idesc_bf16(AQ, Tp);
             const uint32_t idesc_o = make_idesc_bf16(AQ, HD, 0, 1);
-            const int ksteps = Tp / 16;
-            for (int u = 0; u <= my_units; ++u) {
-                if (u < my_units) {                      // S(u) = Q_qt K^T -> TMEM half (u & 1), columns [0, Tp)
-                    const int n = u / n_qt, qt = u - n * n_qt, st = n % P_STAGES, w = u & 1, k = u >> 1;
-                    mbar_wait(&full[st], (n / P_STAGES) & 1);
-                    mbar_wait(&tmem_free[w], (k & 1) ^ 1);
-                    tc_fence_after();
-                    const uint32_t sq = smem_u32(smem + st * P_STAGE + qt * (AQ * 128));
-                    const uint32_t sk = smem_u32(smem + st * P_STAGE + P_SQ);
-                    const uint64_t da = make_smem_desc_sw128(sq, 0, 1024);
-                    const uint64_t db = make_smem_desc_sw128(sk, 0, 1024);
+            const uint32_t th = tmem + w * 256;
+            for (int u = w, k = 0; u < my_units; u += 2, ++k) {
+                const int n = u / n_qt, qt = u - n * n_qt, st = n % P_STAGES;
+                // S(u) = Q_qt K^T -> TMEM half w, columns [0, Tp)
+                mbar_wait(&full[st], (n / P_STAGES) & 1);
+                ATT_TRACE(u, 10);
+                if (k == 0 && w == 1 && stagger > 0) { const long long t0 = clock64(); while (clock64() - t0 < stagger) { } }
+                mbar_wait(&tmem_free[w], (k & 1) ^ 1);
+                tc_fence_after();
+                ATT_TRACE(u, 0);
+                const uint32_t sq = smem_u32(smem + st * P_STAGE + qt * (AQ * 128));
+                const uint32_t sk = smem_u32(smem + st * P_STAGE + P_SQ);
+                const uint64_t da = make_smem_desc_sw128(sq, 0, 1024);
+                const uint64_t dk = make_smem_desc_sw128(sk, 0, 1024);
 #pragma unroll
-                    for (int kk = 0; kk < HD / 16; ++kk) tc_mma_f16(tmem + w * 256, da + uint64_t(2 * kk), db + uint64_t(2 * kk), idesc_s, kk != 0);
-                    tc_commit(&s_ready[w]);
+                for (int kk = 0; kk < HD / 16; ++kk) tc_mma_f16(th, da + uint64_t(2 * kk), dk + uint64_t(2 * kk), idesc_s, kk != 0);
+                tc_commit(&s_ready[w]);
+                ATT_TRACE(u, 1);
+                // O(u) = P V ; A = packed bf16 P in TMEM, B = V [key][d] (MN-major)
+                mbar_wait(&p_ready[w], k & 1);
+                tc_fence_after();
+                ATT_TRACE(u, 2);
+                const uint32_t sv = smem_u32(smem + st * P_STAGE + P_SQ + P_SK);
+                uint64_t db = make_smem_desc_sw128(sv, 32768, 1024);
+                for (int kk = 0; kk < nchunk; ++kk) {
+                    tc_mma_f16_ts(th + P_OCOL, th + kk * 8, db, idesc_o, kk != 0);
+                    db += 2048 >> 4;                 // next 16 keys of V
                 }
-                if (u >= 1) {                            // O(u-1) = P V ; A = packed bf16 P in TMEM, B = V [key][d] (MN-major)
-                    const int v = u - 1;
-                    const int n = v / n_qt, qt = v - n * n_qt, st = n % P_STAGES, w = v & 1, k = v >> 1;
-                    mbar_wait(&p_ready[w], k & 1);
-                    tc_fence_after();
-                    const uint32_t sv = smem_u32(smem + st * P_STAGE + P_SQ + P_SK);
-                    for (int kk = 0; kk < ksteps; ++kk) {
-                        const uint64_t db = make_smem_desc_sw128(sv + kk * 2048, 32768, 1024);
-                        tc_mma_f16_ts(tmem + w * 256 + P_OCOL, tmem + w * 256 + kk * 8, db, idesc_o, kk != 0);
-                    }
-                    tc_commit(&o_ready[w]);
-                    if (qt == n_qt - 1) tc_commit(&stage_free[st]);      // all MMAs reading this stage are tracked by this commit
-                }
+                tc_commit(&o_ready[w]);
+                tc_commit(&stage_free[st]);          // one arrival per unit of the item (barrier count n_qt): all its MMAs are done
+                ATT_TRACE(u, 3);
             }
         }
     } else {
@@ -397,7 +429,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         const int w = warp >> 2, q = warp & 3;
         const int r = q * 32 + lane;
         const uint32_t trow = tmem + (uint32_t(q * 32) << 16) + w * 256;
-        const int nchunk = Tp / 16;
+        uint8_t* stage_tile = smem + P_OUT_OFFSET + w * 16384;
+        const int bar_id = 1 + w;
+        const bool issuer = r == 0;
+        const int npiece = (Tp + 31) / 32;
         constexpr float kLog2e = 1.4426950408889634f;
         for (int u = w, k = 0; u < my_units; u += 2, ++k) {
             const int n = u / n_qt, qt = u - n * n_qt;
@@ -408,45 +443,40 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             const bool active = q * 32 < rows_valid;           // warp-uniform: quadrants with no valid query row skip the math
             mbar_wait(&s_ready[w], k & 1);
             tc_fence_after();
+            if (issuer) ATT_TRACE(u, 4);
             float sum = 0.f;
             if (active) {
-                // pass 1: row max over the valid keys (TMEM loads double-buffered in registers, statically indexed)
-                float mx = -INFINITY;
-                auto max_chunk = [&](const uint32_t (&cur)[16], int c) {
-                    if (c * 16 + 16 <= len) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(cur[j]));
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) if (c * 16 + j < len) mx = fmaxf(mx, __uint_as_float(cur[j]));
-                    }
-                };
+                // ---- pass 1: row max, 32-column TMEM loads double-buffered in registers (a piece may run past Tp into the stale
+                // O columns of the half: masked by len)
+                float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
                 {
-                    uint32_t a0[16], a1[16];
-                    tmem_ld_32x32b_x16(trow, a0);
+                    uint32_t a0[32], a1[32];
+                    tmem_ld_32x32b_x32(trow, a0);
                     tmem_ld_wait();
 #pragma unroll 1
-                    for (int c = 0; c < nchunk; c += 2) {
-                        if (c + 1 < nchunk) tmem_ld_32x32b_x16(trow + (c + 1) * 16, a1);
-                        max_chunk(a0, c);
+                    for (int c = 0; c < npiece; c += 2) {
+                        if (c + 1 < npiece) tmem_ld_32x32b_x32(trow + (c + 1) * 32, a1);
+                        max32(a0, c * 32, len, mx4);
                         tmem_ld_wait();
-                        if (c + 1 >= nchunk) break;
-                        if (c + 2 < nchunk) tmem_ld_32x32b_x16(trow + (c + 2) * 16, a0);
-                        max_chunk(a1, c + 1);
+                        if (c + 1 >= npiece) break;
+                        if (c + 2 < npiece) tmem_ld_32x32b_x32(trow + (c + 2) * 32, a0);
+                        max32(a1, (c + 1) * 32, len, mx4);
                         tmem_ld_wait();
                     }
                 }
-                // pass 2: p = exp(s - max) -> packed bf16 written back over the columns of S this thread has already consumed
+                if (issuer) ATT_TRACE(u, 5);
+                // ---- pass 2: p = exp(s - max) -> packed bf16 written back over the columns of S this thread has already consumed
                 // (P chunk c covers 32-bit columns [8c, 8c+8); the S columns still to be read start at 16(c+1))
-                const float mxl = mx * kLog2e;                 // at least one key is valid, so the row max is finite
+                const float mxl = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * kLog2e;   // key 0 is valid: finite
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
                 auto exp_chunk = [&](const uint32_t (&cur)[16], int c) {
                     float p[16];
-                    const bool fullc = c * 16 + 16 <= len;
+                    if (c * 16 + 16 <= len) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float e = ex2_approx(fmaf(__uint_as_float(cur[j]), kLog2e, -mxl));
-                        p[j] = (fullc || c * 16 + j < len) ? e : 0.f;
+                        for (int j = 0; j < 16; ++j) p[j] = ex2_approx(fmaf(__uint_as_float(cur[j]), kLog2e, -mxl));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) p[j] = c * 16 + j < len ? ex2_approx(fmaf(__uint_as_float(cur[j]), kLog2e, -mxl)) : 0.f;
                     }
                     s0 += (p[0] + p[4]) + (p[8] + p[12]); s1 += (p[1] + p[5]) + (p[9] + p[13]);
                     s2 += (p[2] + p[6]) + (p[10] + p[14]); s3 += (p[3] + p[7]) + (p[11] + p[15]);
@@ -476,35 +506,45 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_ready[w]);
+            if (issuer) ATT_TRACE(u, 6);
+            // ---- epilogue: O / sum -> bf16 -> swizzled smem tile -> TMA store
             mbar_wait(&o_ready[w], k & 1);
             tc_fence_after();
+            if (issuer) ATT_TRACE(u, 7);
+            uint32_t o[64];
             if (active) {
-                const int t = qt * AQ + r;
-                uint32_t o[2][32];
-                tmem_ld_32x32b_x32(trow + P_OCOL, o[0]);
-                tmem_ld_32x32b_x32(trow + P_OCOL + 32, o[1]);
+                tmem_ld_32x32b_x32(trow + P_OCOL, o);
+                tmem_ld_32x32b_x32(trow + P_OCOL + 32, o + 32);
                 tmem_ld_wait();
-                if (t < Tn) {
-                    const float inv = 1.0f / sum;
-                    uint4* op = reinterpret_cast<uint4*>(out + ((long long)b * Tn + t) * D + h * HD);
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh)
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) {
-                            uint4 wv;
-                            wv.x = pack_bf16x2(__uint_as_float(o[hh][8 * v + 0]) * inv, __uint_as_float(o[hh][8 * v + 1]) * inv);
-                            wv.y = pack_bf16x2(__uint_as_float(o[hh][8 * v + 2]) * inv, __uint_as_float(o[hh][8 * v + 3]) * inv);
-                            wv.z = pack_bf16x2(__uint_as_float(o[hh][8 * v + 4]) * inv, __uint_as_float(o[hh][8 * v + 5]) * inv);
-                            wv.w = pack_bf16x2(__uint_as_float(o[hh][8 * v + 6]) * inv, __uint_as_float(o[hh][8 * v + 7]) * inv);
-                            op[hh * 4 + v] = wv;
-                        }
-                }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_free[w]);
+            if (lane == 0) mbar_arrive(&tmem_free[w]);          // the MMA warp may start S(u + 2) while we store
+            if (issuer) { ATT_TRACE(u, 8); tma_store_wait_read<0>(); }       // the previous store no longer reads the staging tile
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            if (active) {
+                const float inv = 1.0f / sum;
+                uint8_t* srow = stage_tile + r * 128;
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) {
+                    uint4 wv;
+                    wv.x = pack_bf16x2(__uint_as_float(o[8 * c8 + 0]) * inv, __uint_as_float(o[8 * c8 + 1]) * inv);
+                    wv.y = pack_bf16x2(__uint_as_float(o[8 * c8 + 2]) * inv, __uint_as_float(o[8 * c8 + 3]) * inv);
+                    wv.z = pack_bf16x2(__uint_as_float(o[8 * c8 + 4]) * inv, __uint_as_float(o[8 * c8 + 5]) * inv);
+                    wv.w = pack_bf16x2(__uint_as_float(o[8 * c8 + 6]) * inv, __uint_as_float(o[8 * c8 + 7]) * inv);
+                    *reinterpret_cast<uint4*>(srow + ((c8 ^ (r & 7)) << 4)) = wv;
+                }
+            }
+            fence_proxy_async_smem();
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            if (issuer) {
+                tma_store_3d(&tm_out, stage_tile, h * HD, qt * AQ, b);     // rows t >= Tn fall outside the (d, t, b) tensor: clipped
+                tma_store_commit();
+            }
         }
+        if (issuer) tma_store_wait<0>();
     }
+#undef ATT_TRACE
     tc_fence_before();
     __syncthreads();
     if (warp == 9) {
@@ -555,16 +595,21 @@ int attention_tc_v1(const void* qkv, void* out, int B, int T, int H, const int* 
 }  // namespace slsb
 
 namespace slsb {
-int attention_tc(const void* qkv, void* out, int B, int T, int H, const int* lens, int num_sms, cudaStream_t stream) {
+int attention_tc(const void* qkv, void* out, int B, int T, int H, const int* lens, int num_sms, cudaStream_t stream, long long* trace) {
     const int Tp = (T + 15) / 16 * 16;
     if (Tp > 256) { set_error("attention_tc: T=%d > 256 (use attention_simt)", T); return -1; }
     const int D = H * HD;
-    CUtensorMap tq, tkv;
+    CUtensorMap tq, tkv, to;
     uint64_t dims[2] = {(uint64_t)(3 * D), (uint64_t)B * T};
     uint64_t strides[1] = {(uint64_t)(3 * D) * 2};
     uint32_t boxq[2] = {HD, AQ}, boxkv[2] = {HD, (uint32_t)Tp};
     if (encode_tmap_bf16(&tq, qkv, 2, dims, strides, boxq)) return -1;
     if (encode_tmap_bf16(&tkv, qkv, 2, dims, strides, boxkv)) return -1;
+    // output viewed as (d, t, b) so that a 128-row store box is clipped at the end of ITS utterance
+    uint64_t odims[3] = {(uint64_t)D, (uint64_t)T, (uint64_t)B};
+    uint64_t ostrides[2] = {(uint64_t)D * 2, (uint64_t)T * D * 2};
+    uint32_t obox[3] = {HD, AQ, 1};
+    if (encode_tmap_bf16(&to, out, 3, odims, ostrides, obox)) return -1;
     static bool configured = false;
     if (!configured) {
         SLSB_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
@@ -572,8 +617,9 @@ int attention_tc(const void* qkv, void* out, int B, int T, int H, const int* len
     }
     const int n_items = B * H, n_qt = (T + AQ - 1) / AQ;
     const int grid = n_items < num_sms ? n_items : num_sms;
-    attn_tc_kernel<<<grid, P_THREADS, P_SMEM, stream>>>(tq, tkv, static_cast<bf16*>(out), T, Tp, H, n_items, n_qt, lens);
-    SLSB_CUDA_CHECK(cudaGetLastError());
+    static int stagger = -1;
+    if (stagger < 0) { const char* sv = getenv("SLSB_ATTN_STAGGER"); stagger = sv ? atoi(sv) : 0; }
+    SLSB_CUDA_CHECK(launch_pdl(attn_tc_kernel, dim3(grid), dim3(P_THREADS), P_SMEM, stream, tq, tkv, to, T, Tp, H, n_items, n_qt, lens, stagger, trace));
     return 0;
 }
 }  // namespace slsb

@@ -6,6 +6,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -65,6 +66,12 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 }
 int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, bool sw) {
     return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box, sw);
+}
+
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* v = getenv("SLSB_NO_PDL"); on = (v && atoi(v) != 0) ? 0 : 1; }
+    return on != 0;
 }
 
 // small elementwise helper kernels private to the engine
@@ -947,6 +954,10 @@ int slsb_op_attention(int impl, int io_bf16, const void* qkv, void* out, int B, 
         return attention_tc(qkv, out, B, T, H, frame_lens_dev, device_sms(), st);
     }
     return attention_simt(qkv, out, io_bf16, B, T, H, frame_lens_dev, st);
+}
+
+int slsb_op_attention_trace(const void* qkv, void* out, int B, int T, int H, int64_t* trace_dev, void* stream) {
+    return attention_tc(qkv, out, B, T, H, nullptr, device_sms(), static_cast<cudaStream_t>(stream), reinterpret_cast<long long*>(trace_dev));
 }
 
 int slsb_op_topk(const float* x, int64_t rows, int D, int k, float* thr, int32_t* tie_cut, float* encoded_or_null, void* stream) {

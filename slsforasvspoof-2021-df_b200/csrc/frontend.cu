@@ -100,6 +100,8 @@ __global__ void __launch_bounds__(256, 4) ln_kernel(const TI* __restrict__ in, c
     constexpr int C = NV * 128;
     const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    griddep_launch();
+    griddep_wait();
     if (row >= rows) return;
     const TI* x = in + row * C;
     float v[NV][4];
@@ -159,12 +161,12 @@ int ln_launch(const LnArgs& a, cudaStream_t stream) {
     const bf16* add = static_cast<const bf16*>(a.add);
     if (a.gelu) {
         if (a.dot_out) { set_error("layernorm: dot_out is not combined with gelu"); return -1; }
-        if (a.exact_gelu) ln_kernel<TI, TO, TO2, NV, true, true, false><<<grid, 256, 0, stream>>>(in, add, a.sum_out, out, out2, a.sub, a.w, a.b, a.dot_w, a.dot_out, a.rows, a.eps);
-        else ln_kernel<TI, TO, TO2, NV, true, false, false><<<grid, 256, 0, stream>>>(in, add, a.sum_out, out, out2, a.sub, a.w, a.b, a.dot_w, a.dot_out, a.rows, a.eps);
+        if (a.exact_gelu) SLSB_CUDA_CHECK(launch_pdl(ln_kernel<TI, TO, TO2, NV, true, true, false>, dim3(grid), dim3(256), 0, stream, in, add, a.sum_out, out, out2, a.sub, a.w, a.b, a.dot_w, a.dot_out, a.rows, a.eps));
+        else SLSB_CUDA_CHECK(launch_pdl(ln_kernel<TI, TO, TO2, NV, true, false, false>, dim3(grid), dim3(256), 0, stream, in, add, a.sum_out, out, out2, a.sub, a.w, a.b, a.dot_w, a.dot_out, a.rows, a.eps));
     } else if (a.dot_out) {
-        ln_kernel<TI, TO, TO2, NV, false, true, true><<<grid, 256, 0, stream>>>(in, add, a.sum_out, out, out2, a.sub, a.w, a.b, a.dot_w, a.dot_out, a.rows, a.eps);
+        SLSB_CUDA_CHECK(launch_pdl(ln_kernel<TI, TO, TO2, NV, false, true, true>, dim3(grid), dim3(256), 0, stream, in, add, a.sum_out, out, out2, a.sub, a.w, a.b, a.dot_w, a.dot_out, a.rows, a.eps));
     } else {
-        ln_kernel<TI, TO, TO2, NV, false, true, false><<<grid, 256, 0, stream>>>(in, add, a.sum_out, out, out2, a.sub, a.w, a.b, a.dot_w, a.dot_out, a.rows, a.eps);
+        SLSB_CUDA_CHECK(launch_pdl(ln_kernel<TI, TO, TO2, NV, false, true, false>, dim3(grid), dim3(256), 0, stream, in, add, a.sum_out, out, out2, a.sub, a.w, a.b, a.dot_w, a.dot_out, a.rows, a.eps));
     }
     SLSB_CUDA_CHECK(cudaGetLastError());
     return 0;

@@ -223,6 +223,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int num_tiles = p.batches * p.m_tiles * p.n_tiles;
     const int num_kb = p.K / BLOCK_K;
 
+    griddep_launch();
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
@@ -238,6 +239,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    griddep_wait();                     // the prologue above overlapped the previous kernel's tail; its outputs are visible from here
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -393,8 +395,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, 
     }
     const int tiles = dp.batches * dp.m_tiles * dp.n_tiles;
     const int grid = tiles < num_sms ? tiles : num_sms;
-    kern<<<grid, kNumThreads, Plan::kBytes, stream>>>(ta, tb, to, dp);
-    SLSB_CUDA_CHECK(cudaGetLastError());
+    SLSB_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(kNumThreads), Plan::kBytes, stream, ta, tb, to, dp));
     return 0;
 }
 

@@ -54,6 +54,7 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int num_tiles = p.batches * p.m_tiles;
     const int num_kb = p.K / BLOCK_K;
 
+    griddep_launch();
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); tma_prefetch_desc(&tmap_out); }
     for (int i = threadIdx.x; i < NCH; i += kThreads) { par[i] = p.bias[i]; par[NCH + i] = p.ln_w[i]; par[2 * NCH + i] = p.ln_b[i]; }
     if (warp == 1 && lane == 0) {
@@ -66,6 +67,7 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    griddep_wait();                     // prologue (params are static weights) overlapped the previous kernel's tail
 
     if (warp == 0) {
         if (lane == 0) {
@@ -225,8 +227,7 @@ int launch_ln(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t
         configured = true;
     }
     const int tiles = dp.batches * dp.m_tiles;
-    kern<<<tiles < num_sms ? tiles : num_sms, kThreads, kSmemBytes, stream>>>(ta, tb, to, dp);
-    SLSB_CUDA_CHECK(cudaGetLastError());
+    SLSB_CUDA_CHECK(launch_pdl(kern, dim3(tiles < num_sms ? tiles : num_sms), dim3(kThreads), kSmemBytes, stream, ta, tb, to, dp));
     return 0;
 }
 

@@ -90,7 +90,9 @@ int frame_lengths(const int* sample_lens, int* frame_lens, int B, int n_conv, co
 // ---------------------------------------------------------------- attention (attention.cu)
 // qkv [B*T, 3*D] (q pre-scaled), heads of 64; out [B*T, D]; keys >= lens[b] masked (lens may be null)
 int attention_simt(const void* qkv, void* out, int io_bf16, int B, int T, int H, const int* lens, cudaStream_t stream);
-int attention_tc(const void* qkv_bf16, void* out_bf16, int B, int T, int H, const int* lens, int num_sms, cudaStream_t stream);
+// trace (optional, device): 64 units x 16 clock64 stamps of CTA 0's pipeline events (slsb_op_attention_trace)
+int attention_tc(const void* qkv_bf16, void* out_bf16, int B, int T, int H, const int* lens, int num_sms, cudaStream_t stream,
+                 long long* trace = nullptr);
 int attention_tc_v1(const void* qkv_bf16, void* out_bf16, int B, int T, int H, const int* lens, int num_sms, cudaStream_t stream);
 
 // ---------------------------------------------------------------- heads (heads.cu)

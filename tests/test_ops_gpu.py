@@ -235,6 +235,22 @@ def test_attention(lib, cuda, impl, bf16, B, T, lens):
     report(f"attention impl={impl} bf16={bf16} T={T}", out, ref, atol=1.5e-2 if bf16 else 2e-5, rtol=1e-2 if bf16 else 1e-5)
 
 
+@pytest.mark.parametrize("T,first_big", [(201, 128), (201, 112), (256, 128), (160, 150)])
+def test_attention_tc_rebase_path(lib, cuda, T, first_big):
+    """Keys of the second key block dominate (scores jump by far more than 2^8): exercises the lazy online-softmax re-base
+    of the persistent kernel (O_a rescaled in TMEM); plus rows where only SOME lanes of a warp re-base."""
+    B, H = 3, 16
+    qkv = _rand((B, T, 3 * H * 64), 62, 0.5)
+    qkv[..., :H * 64] *= 0.5
+    qkv[:, first_big:, H * 64:2 * H * 64] *= 12.0          # later keys 12x larger
+    qkv[1, first_big:, H * 64:2 * H * 64] *= 0.02           # utterance 1: later keys tiny instead -> no re-base there
+    qkv[2, ::3, :H * 64] *= 0.01                            # utterance 2: every third query nearly flat -> mixed warps
+    qkv = qkv.bfloat16()
+    out = torch.zeros(B, T, H * 64, device=cuda, dtype=torch.bfloat16)
+    ok(lib, lib.slsb_op_attention(2, 1, P(qkv), P(out), B, T, H, None, stream()), "attention")
+    report(f"attention re-base T={T}", out, _attn_ref(qkv, B, T, H, None), atol=2e-2, rtol=2e-2)
+
+
 def test_attention_long_simt(lib, cuda):
     B, T, H = 1, 499, 16
     qkv = _rand((B, T, 3 * H * 64), 61, 0.5)

@@ -1,5 +1,5 @@
 #!/bin/bash
-# One GPU visit: unit + parity tests, the bench line, and the ncu launch list of the same bench command.
+# One GPU visit: unit + parity tests, the bench line, and (NCU_LIST=1) the ncu launch list of the same bench command.
 set -u
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
@@ -7,8 +7,11 @@ run() { name=$1; shift; echo "=== $name: $*"; timeout "${T:-600}" "$@" > gpurun_
 T=600 TAILN=4 run ops python -m pytest tests/test_ops_gpu.py -q -m gpu --no-header -p no:cacheprovider -x
 T=1500 TAILN=4 run parity python -m pytest tests/test_parity_gpu.py -q -m gpu --no-header -p no:cacheprovider -s -x
 grep -E "^\.?\[|max\|err" gpurun_out/parity.log | cut -c1-160
-T=900 TAILN=3 run bench python bench.py --steps 20 --warmup 3
-if [ "${NCU_LIST:-1}" = "1" ]; then
+T=900 TAILN=1 run bench python bench.py --steps 20 --warmup 3 ${BENCH_ARGS:-}
+if [ "${AB_PDL:-0}" = "1" ]; then
+  SLSB_NO_PDL=1 T=900 TAILN=1 run bench_nopdl python bench.py --steps 20 --warmup 3 --no-cpu-baseline
+fi
+if [ "${NCU_LIST:-0}" = "1" ]; then
   CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
   ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_bench.csv $CMD > gpurun_out/ncu_list.log 2>&1
   echo "launch list rc=$?"
