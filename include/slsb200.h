@@ -113,6 +113,16 @@ int64_t slsb_score_submit(slsb_engine* e, const float* wav_host, const int32_t* 
                           int head, int precision, float* scores_host, void* stream);
 int slsb_score_wait(slsb_engine* e, int64_t ticket);
 
+/* Audio ingest on the device (replaces the float conversion + pad() of Dataset_*_eval.__getitem__, data_utils_SSL.py:109-115
+ * and :58-65): 16-bit PCM -> float32 x / 32768 (what librosa/soundfile deliver for 16-bit FLAC/WAV); a clip with >= S samples
+ * keeps its first S, a shorter one is tile-repeated up to S.  pcm_dev: the clips back to back; offsets_dev int64 [B] first
+ * sample of clip b; lens_dev int32 [B] (>= 1); wav_dev fp32 [B, S]. */
+int slsb_ingest_pcm16(const int16_t* pcm_dev, const int64_t* offsets_dev, const int32_t* lens_dev, int B, int S,
+                      float* wav_dev, void* stream);
+/* slsb_score_host for 16-bit PCM host buffers: uploads 2 bytes per sample of the UN-padded clips, ingests, scores. */
+int slsb_score_pcm16_host(slsb_engine* e, const int16_t* pcm_host, int64_t total_samples, const int64_t* offsets_host,
+                          const int32_t* lens_host, int B, int S, int head, int precision, float* scores_host, void* stream);
+
 /* synthetic clips keyed by utterance index, bit-identical to oracle.trunk.synth_clips */
 int slsb_synth_clips(float* wav_dev, int64_t first_utt, int count, int samples, void* stream);
 

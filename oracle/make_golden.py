@@ -154,8 +154,34 @@ def make_fixture(head: str, batch: int = 2, seed: int = 1234) -> dict:
     return fx
 
 
+def make_eer_fixture() -> dict:
+    """EER known-answer cases: produced by the REFERENCE's eval_metrics_DF.compute_eer where /root/reference is mounted
+    (asserted equal to oracle.eer), else by oracle.eer alone.  float32 scores so the fixture is exact on any host."""
+    from oracle.eer import compute_eer
+    ref = None
+    if os.path.isdir("/root/reference"):
+        sys.path.insert(0, "/root/reference")
+        import eval_metrics_DF as ref
+    rs = np.random.RandomState(7)
+    cases = {}
+    for name, (nt, nn, q) in {"gauss": (500, 4000, 0), "ties": (300, 900, 8), "tiny": (3, 5, 0), "separable": (50, 70, 0)}.items():
+        t, n = rs.randn(nt) + 1.0, rs.randn(nn)
+        if name == "separable":
+            t += 10
+        if q:
+            t, n = np.round(t * q) / q, np.round(n * q) / q
+        t, n = t.astype(np.float32), n.astype(np.float32)
+        e = compute_eer(t.astype(np.float64), n.astype(np.float64))
+        if ref is not None:
+            e_ref = ref.compute_eer(t.astype(np.float64), n.astype(np.float64))
+            assert e_ref[0] == e[0] and float(e_ref[1]) == e[1], (name, e_ref, e)
+        cases[name + "_t"], cases[name + "_n"], cases[name + "_eer"] = t, n, np.array(e)
+    return cases
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "eer_cases.npz"), **make_eer_fixture())
     small = TrunkConfig(layers=2)
     print("[pin] HF cross-check (2 layers):", crosscheck_hf(small))
     print("[pin] HF cross-check (24 layers):", crosscheck_hf(TrunkConfig(), batch=1))

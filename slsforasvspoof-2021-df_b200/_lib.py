@@ -54,6 +54,8 @@ _SIGNATURES = {
     "slsb_score_host": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "slsb_score_submit": (C.c_int64, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "slsb_score_wait": (C.c_int, [_P, C.c_int64]),
+    "slsb_ingest_pcm16": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P]),
+    "slsb_score_pcm16_host": (C.c_int, [_P, _P, C.c_int64, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "slsb_synth_clips": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, _P]),
     "slsb_launch_count": (C.c_int64, [_P]),
     "slsb_profile_enable": (C.c_int, [_P, C.c_int]),

@@ -127,7 +127,7 @@ struct slsb_engine {
     int64_t launches = 0;
     // workspace
     Buf fe[2], lnbuf, qkv, attn, ffn, xmid, xfinal, xc, xpad, acts, encoded, sums, votes, thr, cut, thr_w, cut_w, pooled, logprob,
-        sls_w, sls_in, sls_part, sls_dots, zeros, scratch, flens, wav_stage[2], lens_stage[2], score_stage[4], recon, tmp_bf16, im2col, conv0_w64, ybuf;
+        sls_w, sls_in, sls_part, sls_dots, zeros, scratch, flens, wav_stage[2], lens_stage[2], score_stage[4], recon, tmp_bf16, im2col, conv0_w64, ybuf, pcm_stage, off_stage;
     // pipelined host scoring (slsb_score_submit / slsb_score_wait): uploads run on a private copy stream into two staging
     // slots so the H2D copy of batch i+1 overlaps the forward of batch i; up to 4 submissions may be in flight
     cudaStream_t copy_stream = nullptr;
@@ -627,7 +627,8 @@ int slsb_destroy(slsb_engine* e) {
     Buf* bufs[] = {&e->fe[0], &e->fe[1], &e->lnbuf, &e->qkv, &e->attn, &e->ffn, &e->xmid, &e->xfinal, &e->xc, &e->xpad, &e->acts, &e->encoded,
                    &e->sums, &e->votes, &e->thr, &e->cut, &e->thr_w, &e->cut_w, &e->pooled, &e->logprob, &e->sls_w, &e->sls_in, &e->sls_part, &e->sls_dots,
                    &e->zeros, &e->scratch, &e->flens, &e->wav_stage[0], &e->wav_stage[1], &e->lens_stage[0], &e->lens_stage[1], &e->score_stage[0],
-                   &e->score_stage[1], &e->score_stage[2], &e->score_stage[3], &e->recon, &e->tmp_bf16, &e->im2col, &e->conv0_w64, &e->ybuf};
+                   &e->score_stage[1], &e->score_stage[2], &e->score_stage[3], &e->recon, &e->tmp_bf16, &e->im2col, &e->conv0_w64, &e->ybuf,
+                   &e->pcm_stage, &e->off_stage};
     for (Buf* b : bufs) b->release();
     for (int i = 0; i < 2; ++i) { if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]); if (e->ev_slot_free[i]) cudaEventDestroy(e->ev_slot_free[i]); }
     for (int i = 0; i < 4; ++i) if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
@@ -830,6 +831,38 @@ int slsb_score_host(slsb_engine* e, const float* wav_host, const int32_t* lens_h
     const int64_t t = slsb_score_submit(e, wav_host, lens_host, B, S, head, precision, scores_host, stream);
     if (t < 0) return -1;
     return slsb_score_wait(e, t);
+}
+
+int slsb_ingest_pcm16(const int16_t* pcm_dev, const int64_t* offsets_dev, const int32_t* lens_dev, int B, int S, float* wav_dev, void* stream) {
+    if (!pcm_dev || !offsets_dev || !lens_dev || !wav_dev) { set_error("slsb_ingest_pcm16: null buffer"); return -1; }
+    return ingest_pcm16(pcm_dev, reinterpret_cast<const long long*>(offsets_dev), lens_dev, B, S, wav_dev, static_cast<cudaStream_t>(stream));
+}
+
+int slsb_score_pcm16_host(slsb_engine* e, const int16_t* pcm_host, int64_t total_samples, const int64_t* offsets_host, const int32_t* lens_host,
+                          int B, int S, int head, int precision, float* scores_host, void* stream) {
+    if (check_ready(e)) return -1;
+    if (!pcm_host || !offsets_host || !lens_host || !scores_host) { set_error("slsb_score_pcm16_host: null buffer"); return -1; }
+    if (head == SLSB_HEAD_NONE) { set_error("slsb_score_pcm16_host: a classifier head is required"); return -1; }
+    for (int b = 0; b < B; ++b) {
+        if (lens_host[b] < 1 || offsets_host[b] < 0 || offsets_host[b] + lens_host[b] > total_samples) {
+            set_error("slsb_score_pcm16_host: clip %d (offset %lld, %d samples) is empty or outside the %lld-sample buffer", b,
+                      (long long)offsets_host[b], lens_host[b], (long long)total_samples);
+            return -1;
+        }
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (e->pcm_stage.reserve((size_t)total_samples * 2) || e->off_stage.reserve((size_t)B * 8) || e->lens_stage[0].reserve((size_t)B * 4) ||
+        e->wav_stage[0].reserve((size_t)B * S * 4) || e->logprob.reserve((size_t)B * 2 * 4) || e->score_stage[0].reserve((size_t)B * 4)) return -1;
+    SLSB_CUDA_CHECK(cudaMemcpyAsync(e->pcm_stage.p, pcm_host, (size_t)total_samples * 2, cudaMemcpyHostToDevice, st));
+    SLSB_CUDA_CHECK(cudaMemcpyAsync(e->off_stage.p, offsets_host, (size_t)B * 8, cudaMemcpyHostToDevice, st));
+    SLSB_CUDA_CHECK(cudaMemcpyAsync(e->lens_stage[0].p, lens_host, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    LAUNCH(ingest_pcm16(e->pcm_stage.as<int16_t>(), e->off_stage.as<long long>(), e->lens_stage[0].as<int>(), B, S, e->wav_stage[0].as<float>(), st));
+    // pad() has already brought every clip to S samples (the reference's eval path never passes lengths down)
+    if (slsb_forward(e, e->wav_stage[0].as<float>(), nullptr, B, S, head, precision, e->logprob.as<float>(), stream)) return -1;
+    LAUNCH(scores_from_logprob(e->logprob.as<float>(), e->score_stage[0].as<float>(), B, st));
+    SLSB_CUDA_CHECK(cudaMemcpyAsync(scores_host, e->score_stage[0].p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    SLSB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return 0;
 }
 
 int slsb_profile_enable(slsb_engine* e, int on) {

@@ -226,6 +226,27 @@ __global__ void synth_kernel(float* __restrict__ out, long long first_utt, int s
     }
 }
 
+// 16-bit PCM -> fp32 / 32768 with the reference's pad(): first S samples, or tile-repeat a shorter clip up to S
+// (data_utils_SSL.py:58-65, :109-115).  grid (ceil(S / 1024), B); HBM-bound: 2 B read + 4 B written per sample.
+__global__ void __launch_bounds__(256) ingest_pcm16_kernel(const int16_t* __restrict__ pcm, const long long* __restrict__ offsets,
+                                                           const int* __restrict__ lens, float* __restrict__ out, int S) {
+    const int b = blockIdx.y;
+    const int16_t* src = pcm + offsets[b];
+    const int len = lens[b];
+    const int i0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (i0 >= S) return;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int i = i0 + e;
+        const int j = len >= S ? i : i % len;
+        v[e] = i < S ? __int2float_rn((int)src[j]) * (1.0f / 32768.0f) : 0.f;
+    }
+    float* o = out + (long long)b * S + i0;
+    if (i0 + 3 < S && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+    else for (int e = 0; e < 4 && i0 + e < S; ++e) o[e] = v[e];
+}
+
 struct ConvCfg { int n; int k[8]; int s[8]; };
 __global__ void frame_len_kernel(const int* __restrict__ sl, int* __restrict__ fl, int B, ConvCfg c) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -298,6 +319,14 @@ int synth_clips(float* out, long long first_utt, int count, int samples, cudaStr
     const float scale = (float)(1.0 / sqrt(4.0 * (65536.0 * 65536.0 - 1.0) / 12.0));
     dim3 grid(64, count);
     synth_kernel<<<grid, 256, 0, stream>>>(out, first_utt, samples, scale);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int ingest_pcm16(const int16_t* pcm, const long long* offsets, const int* lens, int B, int S, float* out, cudaStream_t stream) {
+    if (B <= 0 || S <= 0) return 0;
+    dim3 grid((S + 1023) / 1024, B);
+    ingest_pcm16_kernel<<<grid, 256, 0, stream>>>(pcm, offsets, lens, out, S);
     SLSB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -84,6 +84,9 @@ int zero_padded_frames(float* x, int B, int T, int D, const int* lens, cudaStrea
 int convert_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t stream);
 // deterministic synthetic clips (same integer hash as oracle.trunk.hash_normal)
 int synth_clips(float* out, long long first_utt, int count, int samples, cudaStream_t stream);
+// 16-bit PCM clips (concatenated, offsets[b] / lens[b]) -> fp32 [B, S] in [-1, 1), truncated or tile-repeated to S samples
+// (data_utils_SSL.py:58-65 pad, :109-115 __getitem__)
+int ingest_pcm16(const int16_t* pcm, const long long* offsets, const int* lens, int B, int S, float* out, cudaStream_t stream);
 // frame lengths from sample lengths (wav2vec2.py:523-538)
 int frame_lengths(const int* sample_lens, int* frame_lens, int B, int n_conv, const int* k, const int* s, cudaStream_t stream);
 

@@ -130,6 +130,24 @@ class Engine:
         for k in [k for k in infl if ticket < 0 or k <= ticket]:
             del infl[k]
 
+    def ingest_pcm16(self, pcm: torch.Tensor, offsets: torch.Tensor, lens: torch.Tensor, samples: int = 64600) -> torch.Tensor:
+        """Device int16 PCM (clips back to back) -> fp32 [B, samples] with the reference's ``pad`` (truncate / tile-repeat)."""
+        B = lens.numel()
+        wav = torch.empty(B, samples, device=pcm.device, dtype=torch.float32)
+        check(self.lib.slsb_ingest_pcm16(ptr(pcm), ptr(offsets), ptr(lens), B, samples, ptr(wav), stream_ptr(pcm.device)), "slsb_ingest_pcm16")
+        return wav
+
+    def score_pcm16_host(self, clips, head: int, precision: int, samples: int = 64600) -> torch.Tensor:
+        """Scores a list of 1-D int16 host clips of any length (each is padded on the device like ``pad``)."""
+        lens = torch.tensor([int(c.numel()) for c in clips], dtype=torch.int32)
+        offsets = torch.zeros(len(clips), dtype=torch.int64)
+        offsets[1:] = torch.cumsum(lens[:-1].to(torch.int64), 0)
+        pcm = torch.cat([c.reshape(-1).to(torch.int16) for c in clips]).contiguous().pin_memory()
+        scores = torch.empty(len(clips), dtype=torch.float32, pin_memory=True)
+        check(self.lib.slsb_score_pcm16_host(self._h, ptr(pcm), pcm.numel(), ptr(offsets), ptr(lens), len(clips), samples, head, precision,
+                                             ptr(scores), stream_ptr(self.device)), "slsb_score_pcm16_host")
+        return scores
+
     def synth_clips(self, first_utt: int, count: int, samples: int = 64600) -> torch.Tensor:
         wav = torch.empty(count, samples, device=self.device, dtype=torch.float32)
         check(self.lib.slsb_synth_clips(ptr(wav), first_utt, count, samples, stream_ptr(self.device)), "slsb_synth_clips")

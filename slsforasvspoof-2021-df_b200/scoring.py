@@ -122,6 +122,82 @@ def score_synthetic_shard(model, lo: int, hi: int, batch: int = 64, samples: int
     return out
 
 
+# ---------------------------------------------------------------------------------------------
+# variable-length clips (BASELINE config 4): bucket by frame count, right-pad inside a bucket
+# ---------------------------------------------------------------------------------------------
+
+def bucket_by_frames(sample_lengths: Sequence[int], frames_of, bucket_frames: int = 64, max_batch: int = 64) -> List[List[int]]:
+    """Groups utterance indices so that every batch holds clips whose conv-stack frame counts fall into the same
+    ``bucket_frames``-wide bucket (``frames_of(samples) -> frames``, e.g. ``Engine.frames``).  Inside a batch the
+    indices are sorted by length (longest first: it defines the padded width); batches come out in bucket order and
+    every index appears exactly once."""
+    buckets = {}
+    for i, n in enumerate(sample_lengths):
+        buckets.setdefault((frames_of(int(n)) - 1) // bucket_frames, []).append(i)
+    out: List[List[int]] = []
+    for key in sorted(buckets):
+        idx = sorted(buckets[key], key=lambda i: (-int(sample_lengths[i]), i))
+        out.extend(idx[j:j + max_batch] for j in range(0, len(idx), max_batch))
+    return out
+
+
+@torch.no_grad()
+def score_variable_length(model, clips: Sequence[torch.Tensor], bucket_frames: int = 64, max_batch: int = 64) -> torch.Tensor:
+    """Scores 1-D float32 clips of different lengths: length-bucketed batches, zero right-padding to the longest clip
+    of the batch, sample lengths passed down so that padded frames are masked (wav2vec2.py:567-586).  Returns the
+    scores in the order of ``clips`` (CPU float32)."""
+    m = model.module if hasattr(model, "module") else model
+    eng = m.engine()
+    head, prec = (m._head() if hasattr(m, "_head") else 3), m._prec()
+    lens = [int(c.numel()) for c in clips]
+    scores = torch.empty(len(clips), dtype=torch.float32)
+    for batch in bucket_by_frames(lens, eng.frames, bucket_frames, max_batch):
+        S = lens[batch[0]]
+        wav = torch.zeros(len(batch), S, dtype=torch.float32, pin_memory=True)
+        for j, i in enumerate(batch):
+            wav[j, :lens[i]] = clips[i]
+        sl = torch.tensor([lens[i] for i in batch], dtype=torch.int32).pin_memory()
+        scores[torch.tensor(batch)] = eng.score_host(wav, head, prec, lens_host=sl)
+    return scores
+
+
+# ---------------------------------------------------------------------------------------------
+# EER on the device (closes main.py --is_eval -> score.txt -> evaluate_2021_DF.py)
+# ---------------------------------------------------------------------------------------------
+
+def compute_eer(scores: torch.Tensor, is_bonafide: torch.Tensor) -> Tuple[float, float]:
+    """eval_metrics_DF.py:21-48 on whatever device ``scores`` lives on (600 k DF-eval scores never leave the GPU):
+    targets-first concatenation, STABLE ascending sort, cumulative label sums in int64, rates in float64, EER = mean of
+    FRR and FAR where they are closest.  Returns ``(eer, threshold)`` as Python floats."""
+    scores = scores.reshape(-1)
+    lab = is_bonafide.reshape(-1).to(device=scores.device, dtype=torch.bool)
+    s = torch.cat((scores[lab], scores[~lab])).to(torch.float64)                   # :24-25 targets first
+    n_t, n_n = int(lab.sum()), int((~lab).sum())
+    if n_t == 0 or n_n == 0:
+        raise ValueError("compute_eer needs at least one bonafide and one spoof trial")
+    labels = torch.cat((torch.ones(n_t, dtype=torch.int64, device=s.device), torch.zeros(n_n, dtype=torch.int64, device=s.device)))
+    srt, order = torch.sort(s, stable=True)                                        # :28 mergesort
+    tar = torch.cumsum(labels[order], 0)                                           # :32
+    non = n_n - (torch.arange(1, n_t + n_n + 1, device=s.device, dtype=torch.int64) - tar)   # :33
+    zero, one = torch.zeros(1, dtype=torch.float64, device=s.device), torch.ones(1, dtype=torch.float64, device=s.device)
+    frr = torch.cat((zero, tar.to(torch.float64) / n_t))                           # :35
+    far = torch.cat((one, non.to(torch.float64) / n_n))                            # :36
+    thr = torch.cat((srt[:1] - 0.001, srt))                                        # :37
+    i = int(torch.argmin((frr - far).abs()))                                       # :46 (first minimum, like np.argmin)
+    return float((frr[i] + far[i]) / 2), float(thr[i])
+
+
+def read_score_file(path: str) -> Tuple[List[str], np.ndarray]:
+    """Parses ``"{utt} {score}"`` lines (what evaluate_2021_DF.py:24 reads with pandas)."""
+    utts, vals = [], []
+    with open(path) as fh:
+        for line in fh:
+            u, v = line.split()
+            utts.append(u)
+            vals.append(float(v))
+    return utts, np.asarray(vals, dtype=np.float64)
+
+
 def gather_scores(local: torch.Tensor, n_total: int, rank: int, world: int) -> Optional[torch.Tensor]:
     """All-gather of per-rank score blocks (the only collective of the path).  Returns the [n_total] vector in
     protocol order on every rank.  Works with NCCL (GPU tensors) and gloo (CPU tensors, used by the CPU tests)."""

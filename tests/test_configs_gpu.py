@@ -1,0 +1,118 @@
+"""BASELINE configs 3-5 as parity-test cases on the GPU (small sizes + size-independent properties):
+config 3 utterance-sharded scoring is bit-identical for every sharding, config 4 length-bucketed variable-length clips
+match the oracle run one utterance at a time, config 5 the window-TopK head under sharding; plus the device EER."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _small(sls, head, precision="bf16", layers=2):
+    from oracle.heads import OracleModel
+    from oracle.trunk import TrunkConfig, seeded_init_
+    om = OracleModel(head=head, trunk_cfg=TrunkConfig(layers=layers), sae_window_size=8).eval()
+    seeded_init_(om, 4321)
+    cls = {"sls": sls.ModelSLS, "sae": sls.Model, "window": sls.ModelWindowTopK}[head]
+    m = cls(None, "cuda", cp_path=None, precision=precision, geometry=sls.TrunkGeometry(layers=layers))
+    m.load_state_dict(om.state_dict(), strict=False)
+    return om, m.to("cuda").eval()
+
+
+@pytest.mark.parametrize("head", ["sls", "window"])
+def test_sharded_scoring_is_bit_identical_for_every_sharding(sls, cuda, head):
+    """configs 3 / 5: scores keyed by utterance index do not depend on world size, shard boundaries or batch size."""
+    _, m = _small(sls, head)
+    n = 37
+    whole = sls.score_synthetic_shard(m, 0, n, batch=16)
+    for world in (2, 3, 8):
+        parts = [sls.score_synthetic_shard(m, *sls.shard_range(n, r, world), batch=5) for r in range(world)]
+        assert torch.equal(torch.cat(parts), whole), (head, world)
+    host = torch.stack([torch.from_numpy(sls.synth_clip_host(i)) for i in (0, 17, 36)])
+    dev = torch.cat([m.engine().synth_clips(i, 1) for i in (0, 17, 36)]).cpu()
+    assert torch.equal(host, dev)                                      # any rank can regenerate any clip, bit-exactly
+    assert torch.isfinite(whole).all() and float(whole.min()) > 0 and float(whole.max()) < 1
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_variable_length_buckets_match_per_utterance_oracle(sls, cuda, precision, tol):
+    """config 4: clips of 1-4 s, bucketed by frame count, right-padded + masked, vs the oracle on each clip alone."""
+    from oracle.trunk import synth_clips
+    om, m = _small(sls, "sae", precision)
+    lens = [16000, 16400, 23456, 33333, 40000, 47999, 52000, 64000, 64600]
+    clips = [synth_clips(100 + i, 1, n)[0] for i, n in enumerate(lens)]
+    got = sls.score_variable_length(m, clips, bucket_frames=64, max_batch=4)
+    with torch.no_grad():
+        ref = torch.stack([torch.exp(om(c[None])[0, 1]) for c in clips])
+    err = float((got - ref).abs().max())
+    print(f"[varlen buckets/{precision}] max|score err|={err:.3e} got={got.tolist()} ref={ref.tolist()}")
+    assert err <= tol
+    again = sls.score_variable_length(m, clips[::-1], bucket_frames=64, max_batch=4)
+    assert torch.equal(again.flip(0), got)                             # order / batch composition does not change a score
+
+
+def test_eer_on_device_matches_oracle(sls, cuda):
+    from oracle.eer import compute_eer
+    g = torch.Generator().manual_seed(5)
+    scores = torch.rand(20011, generator=g)
+    labels = torch.rand(20011, generator=g) < 0.1
+    scores[labels] += 0.15
+    got = sls.compute_eer(scores.to(cuda), labels.to(cuda))
+    want = compute_eer(scores[labels].double().numpy(), scores[~labels].double().numpy())
+    assert got == want
+
+
+def test_score_sharded_tool_single_gpu(sls, cuda, tmp_path):
+    out = str(tmp_path / "score.txt")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "score_sharded.py"), "--utts", "70", "--layers", "2", "--batch", "32",
+                        "--verify", "--out", out], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rep = json.loads(r.stdout.strip().splitlines()[-1])
+    assert rep["verify_bit_identical"] is True and rep["n"] == 70 and 0.0 <= rep["eer"] <= 1.0
+    utts, vals = sls.read_score_file(out)
+    assert len(utts) == 70 and utts[69] == "SYN_0000069" and np.isfinite(vals).all()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs on one node")
+def test_two_rank_nccl_gather_equals_single_rank(sls, cuda, tmp_path):
+    """config 3 on 2 GPUs: torchrun, NCCL all-gather; the gathered vector equals the 1-rank run bit for bit."""
+    tool = os.path.join(ROOT, "tools", "score_sharded.py")
+    one = subprocess.run([sys.executable, tool, "--utts", "50", "--layers", "2", "--batch", "16"], capture_output=True, text=True, timeout=600)
+    two = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29533", tool, "--utts", "50", "--layers", "2", "--batch", "16", "--verify"],
+                         capture_output=True, text=True, timeout=900)
+    assert one.returncode == 0 and two.returncode == 0, one.stderr + two.stderr
+    a = json.loads(one.stdout.strip().splitlines()[-1])
+    b = json.loads([l for l in two.stdout.strip().splitlines() if l.startswith("{")][-1])
+    assert a["checksum"] == b["checksum"] and a["first"] == b["first"] and b["verify_bit_identical"] is True and b["world"] == 2
+
+
+def test_pcm16_ingest_is_bit_exact_with_reference_pad(sls, cuda):
+    """next row N2: int16 -> float32 / 32768 + pad() on the device == numpy astype/divide + the reference's pad, bit for bit
+    (ragged clips: shorter than, equal to and longer than 64 600 samples, odd lengths, a 1-sample clip)."""
+    rs = np.random.RandomState(11)
+    lens = [1, 7, 16000, 32301, 64599, 64600, 64601, 100003]
+    clips = [rs.randint(-32768, 32768, size=n).astype(np.int16) for n in lens]
+    pcm = torch.from_numpy(np.concatenate(clips)).to(cuda)
+    off = torch.tensor(np.concatenate(([0], np.cumsum(lens)[:-1])), dtype=torch.int64, device=cuda)
+    ln = torch.tensor(lens, dtype=torch.int32, device=cuda)
+    _, m = _small(sls, "sae")
+    eng = m.engine()
+    for S in (64600, 1000, 3):
+        got = eng.ingest_pcm16(pcm, off, ln, S).cpu().numpy()
+        want = np.stack([sls.pad_clip(c.astype(np.float32) / np.float32(32768.0), S) for c in clips])
+        assert got.dtype == np.float32 and np.array_equal(got, want), S
+    # end to end from int16 host clips == the float path on the same padded clips
+    host16 = [torch.from_numpy(c) for c in clips[2:6]]
+    a = eng.score_pcm16_host(host16, sls.HEAD_SAE, sls.PREC_BF16)
+    wav = torch.from_numpy(np.stack([sls.pad_clip(c.astype(np.float32) / np.float32(32768.0), 64600) for c in clips[2:6]])).pin_memory()
+    b = eng.score_host(wav, sls.HEAD_SAE, sls.PREC_BF16)
+    assert torch.equal(a, b)
+    with pytest.raises(sls.SlsbError):
+        eng.score_pcm16_host([torch.zeros(0, dtype=torch.int16)], sls.HEAD_SAE, sls.PREC_BF16)

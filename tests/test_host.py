@@ -125,6 +125,44 @@ def test_score_file_format(sls, tmp_path):
     assert df.shape == (3, 2)
 
 
+def test_compute_eer_equals_oracle_on_golden(sls):
+    """scoring.compute_eer (torch, runs on the scores' device) == the reference algorithm, bit for bit, ties included."""
+    from oracle.eer import compute_eer as eer_ref
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "eer_cases.npz"))
+    for n in ("gauss", "ties", "tiny", "separable"):
+        t, s = fx[n + "_t"], fx[n + "_n"]
+        perm = np.random.RandomState(1).permutation(t.size + s.size)            # protocol order is arbitrary
+        scores = torch.from_numpy(np.concatenate((t, s))[perm])
+        labels = torch.from_numpy((np.arange(t.size + s.size) < t.size)[perm])
+        got = sls.compute_eer(scores, labels)
+        # targets-first STABLE order inside each class is what the reference sees after its own boolean masks
+        want = eer_ref(np.concatenate((t, s))[perm][labels.numpy()].astype(np.float64), np.concatenate((t, s))[perm][~labels.numpy()].astype(np.float64))
+        assert got == want, (n, got, want)
+    with pytest.raises(ValueError):
+        sls.compute_eer(torch.zeros(3), torch.ones(3, dtype=torch.bool))
+
+
+def test_bucket_by_frames_partitions_and_bounds(sls):
+    """BASELINE config 4 host logic: every index once, one 64-frame bucket per batch, longest first, <= max_batch."""
+    rs = np.random.RandomState(3)
+    lens = rs.randint(16000, 160001, size=500).tolist()
+    batches = sls.bucket_by_frames(lens, _frames, bucket_frames=64, max_batch=32)
+    flat = [i for b in batches for i in b]
+    assert sorted(flat) == list(range(500))
+    for b in batches:
+        assert 1 <= len(b) <= 32
+        fr = [_frames(lens[i]) for i in b]
+        assert len({(f - 1) // 64 for f in fr}) == 1
+        assert [lens[i] for i in b] == sorted((lens[i] for i in b), reverse=True)
+    assert sls.bucket_by_frames([], _frames) == []
+
+
+def _frames(n):
+    for k, s in [(10, 5), (3, 2), (3, 2), (3, 2), (3, 2), (2, 2), (2, 2)]:
+        n = (n - k) // s + 1
+    return n
+
+
 def test_shard_ranges_cover_exactly(sls):
     for n, w in [(611829, 8), (10, 4), (3, 8), (0, 2)]:
         r = [sls.shard_range(n, k, w) for k in range(w)]

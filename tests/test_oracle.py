@@ -63,3 +63,24 @@ def test_canonical_topk_and_window_rule():
     out = window_topk(a, 8, 8)
     assert out.shape == a.shape and int((out > 0).sum(-1).max()) <= 8
     assert torch.equal(out * (out > 0), out) and torch.all((out == 0) | (out == a))
+
+
+def test_eer_matches_reference_code_and_golden():
+    """oracle.eer vs the reference's own eval_metrics_DF.compute_eer (where mounted) and the committed known answers."""
+    import os, sys
+    from oracle.eer import compute_eer
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "eer_cases.npz"))
+    names = sorted({k[:-2] for k in fx.files if k.endswith("_t")})
+    assert names == ["gauss", "separable", "ties", "tiny"]
+    ref = None
+    if os.path.isdir("/root/reference"):
+        sys.path.insert(0, "/root/reference")
+        import eval_metrics_DF as ref
+    for n in names:
+        t, s = fx[n + "_t"].astype(np.float64), fx[n + "_n"].astype(np.float64)
+        e = compute_eer(t, s)
+        assert e[0] == fx[n + "_eer"][0] and e[1] == fx[n + "_eer"][1], n
+        if ref is not None:
+            e_ref = ref.compute_eer(t, s)
+            assert float(e_ref[0]) == e[0] and float(e_ref[1]) == e[1], n
+    assert fx["separable_eer"][0] == 0.0
