@@ -307,6 +307,17 @@ static int attention(slsb_engine* e, bool bf, const void* qkv, void* out, int B,
     return 0;
 }
 
+// fused conv/GEMM + LayerNorm(512) + GELU.  K >= 256 (conv1..6): CTA-pair kernel, whose double-buffered accumulators hide the
+// epilogue behind the next tile's MMAs (measured conv1..6: 1208 us vs 1571 us per 64-clip batch).  K = 64 (conv0) has no
+// mainloop to hide anything behind and pays the pair's statistics exchange on every tile (722 us vs 515 us): it stays on the
+// one-CTA-per-row-block kernel.  SLSB_LN_GEMM_V1=1 / =2 force the old / the pair kernel everywhere (A/B measurements).
+static int ln_gemm_dispatch(const TcLnGemmArgs& g, int num_sms, cudaStream_t st) {
+    static int force = -1;
+    if (force < 0) { const char* v = getenv("SLSB_LN_GEMM_V1"); force = v ? atoi(v) : 0; }
+    const bool pair = force == 2 || (force != 1 && g.K >= 256);
+    return pair ? tc_gemm_ln_gelu_pair(g, num_sms, st) : tc_gemm_ln_gelu(g, num_sms, st);
+}
+
 // LayerNorm launch with its algorithmic HBM bytes recorded (every operand is touched exactly once)
 static int layernorm_timed(slsb_engine* e, const LnArgs& a, cudaStream_t st) {
     const double n = (double)a.rows * a.C;
@@ -364,7 +375,7 @@ static int run_trunk(slsb_engine* e, const float* wav, const int* slens, int B, 
             TcLnGemmArgs g;
             g.a_mode = A_PLAIN; g.A = e->im2col.p; g.lda = 64; g.W = e->conv0_w64.p; g.M = B * L[0]; g.K = 64; g.batches = 1;
             g.out = e->fe[0].p; g.bias = W32("conv0.b"); g.ln_w = W32("conv0.ln.w"); g.ln_b = W32("conv0.ln.b");
-            LAUNCH(tc_gemm_ln_gelu(g, e->num_sms, st));
+            LAUNCH(ln_gemm_dispatch(g, e->num_sms, st));
         }
         for (int i = 1; i < c.n_conv; ++i) {
             const std::string p = "conv" + std::to_string(i);
@@ -374,7 +385,7 @@ static int run_trunk(slsb_engine* e, const float* wav, const int* slens, int B, 
             g.conv_cin = C; g.conv_stride = c.conv_stride[i]; g.conv_lin = L[i - 1];
             g.out = e->fe[i & 1].p; g.out_batch_stride = (long long)L[i] * C;
             g.bias = W32(p + ".b"); g.ln_w = W32(p + ".ln.w"); g.ln_b = W32(p + ".ln.b");
-            LAUNCH(tc_gemm_ln_gelu(g, e->num_sms, st));
+            LAUNCH(ln_gemm_dispatch(g, e->num_sms, st));
         }
     } else {
         LAUNCH(conv0_ln_gelu(wav, B, S, L[0], c.conv_kernel[0], c.conv_stride[0], W32("conv0.w"), W32("conv0.b"), W32("conv0.ln.w"),
@@ -942,7 +953,7 @@ int slsb_op_conv_ln_gelu(const void* x, const void* W, const float* bias, const 
     const int Lout = (L_in - k) / stride + 1;
     g.a_mode = A_CONV; g.A = x; g.W = W; g.M = Lout; g.K = k * C; g.batches = B; g.conv_cin = C; g.conv_stride = stride; g.conv_lin = L_in;
     g.out = out; g.out_batch_stride = (long long)Lout * 512; g.bias = bias; g.ln_w = ln_w; g.ln_b = ln_b;
-    return tc_gemm_ln_gelu(g, device_sms(), static_cast<cudaStream_t>(stream));
+    return ln_gemm_dispatch(g, device_sms(), static_cast<cudaStream_t>(stream));
 }
 
 int slsb_op_conv0_tc(const float* wav, const float* w, const float* bias, const float* ln_w, const float* ln_b, void* out, void* scratch,
@@ -956,7 +967,7 @@ int slsb_op_conv0_tc(const float* wav, const float* w, const float* bias, const 
     TcLnGemmArgs g;
     g.a_mode = A_PLAIN; g.A = cols; g.lda = 64; g.W = w64; g.M = B * L0; g.K = 64; g.batches = 1;
     g.out = out; g.bias = bias; g.ln_w = ln_w; g.ln_b = ln_b;
-    return tc_gemm_ln_gelu(g, device_sms(), st);
+    return ln_gemm_dispatch(g, device_sms(), st);
 }
 
 int slsb_op_posconv(int precision, const float* x, const void* W, const float* bias, float* out, void* scratch, int B, int T, int D, int K,
