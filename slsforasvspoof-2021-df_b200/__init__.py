@@ -12,14 +12,14 @@ imports ``oracle/``.
 """
 from ._lib import SlsbError, LIB_PATH, EXPORTED_SYMBOLS, load as load_library
 from .engine import Engine, make_config, PRECISIONS, HEAD_NONE, HEAD_SAE, HEAD_WINDOW, HEAD_SLS, PREC_FP32, PREC_BF16
-from .weights import TrunkGeometry, TrunkParams, pack_state_dict
+from .weights import TrunkGeometry, TrunkParams, pack_state_dict, load_checkpoint_tensors, load_model_checkpoint, fix_module_prefix
 from .model import Model, ModelWindowTopK, ModelSLS, SSLModel, AutoEncoderTopK, getAttenF
 from .scoring import (produce_evaluation_file, score_synthetic_shard, gather_scores, write_score_file, pad_clip,
                       SyntheticEvalSet, shard_range, bucket_by_frames, score_variable_length, compute_eer, read_score_file,
                       synth_clip_host)
 
 __all__ = ["Model", "ModelWindowTopK", "ModelSLS", "SSLModel", "AutoEncoderTopK", "getAttenF", "Engine", "make_config",
-           "TrunkGeometry", "TrunkParams", "pack_state_dict", "produce_evaluation_file", "score_synthetic_shard",
+           "TrunkGeometry", "TrunkParams", "pack_state_dict", "load_checkpoint_tensors", "load_model_checkpoint", "fix_module_prefix", "produce_evaluation_file", "score_synthetic_shard",
            "gather_scores", "write_score_file", "pad_clip", "SyntheticEvalSet", "shard_range", "bucket_by_frames",
            "score_variable_length", "compute_eer", "read_score_file", "synth_clip_host", "SlsbError",
            "load_library", "LIB_PATH", "EXPORTED_SYMBOLS", "PRECISIONS", "HEAD_NONE", "HEAD_SAE", "HEAD_WINDOW",

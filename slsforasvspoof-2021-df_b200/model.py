@@ -27,8 +27,8 @@ def _load_fairseq_checkpoint(trunk: TrunkParams, cp_path: str) -> None:
         raise RuntimeError(
             f"Could not load SSL checkpoint '{cp_path}' (file not found). Pass cp_path=None for a random-init trunk "
             "(synthetic benchmarks / parity tests).")
-    ckpt = torch.load(cp_path, map_location="cpu", weights_only=False)
-    sd = ckpt["model"] if isinstance(ckpt, dict) and "model" in ckpt else ckpt
+    from .weights import load_checkpoint_tensors
+    sd = load_checkpoint_tensors(cp_path)          # restricted unpickler: omegaconf / fairseq classes become inert stubs
     missing, unexpected = trunk.load_state_dict(sd, strict=False)
     hard = [k for k in missing if not k.startswith(("quantizer", "project_q", "final_proj"))]
     if hard:

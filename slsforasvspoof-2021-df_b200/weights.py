@@ -178,3 +178,77 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], geo: TrunkGeometry, prefix: str
         out["sls.fc1.b"] = h("fc1.bias")
         out["sls.fc3.w"], out["sls.fc3.b"] = h("fc3.weight"), h("fc3.bias")
     return {k: v.contiguous() for k, v in out.items()}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# checkpoints without fairseq (main.py:531-592, model.py:113-115)
+# ---------------------------------------------------------------------------------------------------------------------
+_SAFE_PICKLE_ROOTS = ("torch", "collections", "numpy", "builtins", "_codecs", "argparse", "copyreg", "typing", "enum", "functools")
+
+
+def _stub_class(module: str, name: str):
+    """Stand-in for a class that only matters to fairseq (omegaconf configs, task / criterion objects): constructible
+    with anything, absorbs any pickled state, never executes foreign code."""
+    def _init(self, *a, **k):
+        self.__dict__["_args"] = (a, k)
+
+    def _setstate(self, state):
+        self.__dict__["_state"] = state
+
+    return type(name, (), {"__module__": module, "__init__": _init, "__setstate__": _setstate, "__call__": lambda self, *a, **k: self,
+                           "__getattr__": lambda self, k: None, "__reduce__": lambda self: (dict, ())})
+
+
+class _TensorOnlyUnpickler:
+    """``pickle_module`` for ``torch.load``: tensors / containers load normally, every class outside torch, numpy and the
+    standard containers becomes an inert stub, so a fairseq ``xlsr2_300m.pt`` (``cfg`` = omegaconf objects) or a training
+    checkpoint written by ``main.py`` loads on a box that has neither fairseq nor omegaconf."""
+    import pickle as _pickle
+    __name__ = "pickle"
+
+    class Unpickler(_pickle.Unpickler):
+        def find_class(self, module, name):
+            if module.split(".")[0] in _SAFE_PICKLE_ROOTS:
+                return super().find_class(module, name)
+            return _stub_class(module, name)
+
+    @classmethod
+    def load(cls, f, **kw):
+        return cls.Unpickler(f, **kw).load()
+
+
+def load_checkpoint_tensors(path: str) -> Dict[str, torch.Tensor]:
+    """Returns the state_dict stored in ``path``: a fairseq checkpoint (``ckpt['model']``), a ``main.py`` checkpoint
+    (a bare state_dict, keys possibly prefixed with ``module.``) or ``{'state_dict': ...}``.  No fairseq import."""
+    ckpt = torch.load(path, map_location="cpu", weights_only=False, pickle_module=_TensorOnlyUnpickler)
+    if isinstance(ckpt, dict):
+        for key in ("model_state_dict", "state_dict", "model"):          # main.py:531-536 _get_state_dict order
+            if key in ckpt and isinstance(ckpt[key], dict):
+                ckpt = ckpt[key]
+                break
+    if not isinstance(ckpt, dict) or not any(torch.is_tensor(v) for v in ckpt.values()):
+        raise RuntimeError(f"'{path}' holds no state_dict")
+    return {k: v for k, v in ckpt.items() if torch.is_tensor(v)}
+
+
+def fix_module_prefix(state_dict: Dict[str, torch.Tensor], model_is_wrapped: bool) -> Dict[str, torch.Tensor]:
+    """main.py:542-560: add / strip the ``module.`` prefix so the keys match the model's DataParallel wrapping."""
+    if not state_dict:
+        return state_dict
+    has = all(isinstance(k, str) and k.startswith("module.") for k in state_dict)
+    if model_is_wrapped and not has:
+        return {"module." + k: v for k, v in state_dict.items()}
+    if not model_is_wrapped and has:
+        return {k[len("module."):]: v for k, v in state_dict.items()}
+    return state_dict
+
+
+def load_model_checkpoint(model: nn.Module, path: str):
+    """main.py:576-592 without fairseq: locate the state_dict, fix the prefix, strict load with the reference's
+    non-strict fallback.  Returns ``load_state_dict``'s result."""
+    sd = fix_module_prefix(load_checkpoint_tensors(path), isinstance(model, nn.DataParallel))
+    try:
+        return model.load_state_dict(sd, strict=True)
+    except RuntimeError as e:
+        print("Strict load failed; retrying with strict=False.\n    Reason: {}".format(str(e)[:300]))
+        return model.load_state_dict(sd, strict=False)

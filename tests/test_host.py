@@ -163,6 +163,45 @@ def _frames(n):
     return n
 
 
+def test_checkpoint_loads_without_fairseq_or_omegaconf(sls, tmp_path):
+    """next row N3: a fairseq-style checkpoint whose ``cfg`` pickles classes of modules that are NOT importable here
+    (omegaconf / fairseq stand-ins) still yields its tensors; ``module.``-prefixed main.py checkpoints load into Model."""
+    import pickle, types
+    fake = types.ModuleType("omegaconf_standin.dictconfig")
+    class DictConfig:                                   # pickled by reference: module + qualname
+        def __init__(self, d): self.d = d
+    DictConfig.__module__, DictConfig.__qualname__ = "omegaconf_standin.dictconfig", "DictConfig"
+    fake.DictConfig = DictConfig
+    sys.modules["omegaconf_standin"] = types.ModuleType("omegaconf_standin")
+    sys.modules["omegaconf_standin.dictconfig"] = fake
+    geo = sls.TrunkGeometry(layers=1)
+    trunk = sls.TrunkParams(geo)
+    sd = {k: torch.randn_like(v) for k, v in trunk.state_dict().items()}
+    path = str(tmp_path / "xlsr_like.pt")
+    torch.save({"args": None, "cfg": DictConfig({"model": {"encoder_layers": 1}}), "model": sd, "extra_state": {"epoch": 3}}, path)
+    del sys.modules["omegaconf_standin"], sys.modules["omegaconf_standin.dictconfig"]
+    with pytest.raises(Exception):
+        torch.load(path, map_location="cpu", weights_only=False)                      # what a plain load does without the module
+    got = sls.load_checkpoint_tensors(path)
+    assert set(got) == set(sd) and all(torch.equal(got[k], sd[k]) for k in sd)
+    ssl = sls.SSLModel("cpu", cp_path=path, geometry=geo)                              # model.py:113-115 replacement
+    assert torch.equal(ssl.model.state_dict()["post_extract_proj.weight"], sd["post_extract_proj.weight"])
+    # main.py:542-560 checkpoints: bare state_dict with the DataParallel prefix
+    m = sls.Model(None, "cpu", cp_path=None, geometry=geo)
+    full = {"module." + k: torch.randn_like(v) if v.is_floating_point() else v.clone() for k, v in m.state_dict().items()}
+    p2 = str(tmp_path / "best.pth")
+    torch.save(full, p2)
+    res = sls.load_model_checkpoint(m, p2)                                            # un-wrapped model: prefix stripped
+    assert not res.missing_keys and not res.unexpected_keys
+    assert torch.equal(m.state_dict()["classifier.1.weight"], full["module.classifier.1.weight"])
+    dp = torch.nn.DataParallel(sls.Model(None, "cpu", cp_path=None, geometry=geo))    # main.py:518 wrapping: prefix kept
+    res = sls.load_model_checkpoint(dp, p2)
+    assert not res.missing_keys and torch.equal(dp.module.state_dict()["sae.b_dec"], full["module.sae.b_dec"])
+    assert sls.fix_module_prefix({"a": 1}, True) == {"module.a": 1} and sls.fix_module_prefix({"module.a": 1}, False) == {"a": 1}
+    with pytest.raises(RuntimeError):
+        torch.save({"note": "no tensors"}, p2); sls.load_checkpoint_tensors(p2)
+
+
 def test_shard_ranges_cover_exactly(sls):
     for n, w in [(611829, 8), (10, 4), (3, 8), (0, 2)]:
         r = [sls.shard_range(n, k, w) for k in range(w)]
