@@ -91,6 +91,11 @@ int slsb_extract_feat(slsb_engine* e, const float* wav_dev, const int32_t* sampl
  *   "acts" [B,T,dict] post-ReLU pre-top-k | "encoded" [B,T,dict] | "pooled" [B,cls_in] | "sls_weights" [B,n_layers] */
 int slsb_get_tensor(slsb_engine* e, const char* name, float* dst_dev, int64_t numel, void* stream);
 
+/* Sparse form of the last forward's SAE code (model.py:236-240 `last_sparse_features`, what the 13 analyze_*.py readers
+ * consume) without materialising the dense [B,T,dict] tensor: idx_dev int32 [B*T, sae_k] feature indices in ascending
+ * order (-1 = unused slot), val_dev fp32 [B*T, sae_k], count_dev int32 [B*T] (may be NULL). */
+int slsb_get_sparse(slsb_engine* e, int32_t* idx_dev, float* val_dev, int32_t* count_dev, void* stream);
+
 /* AutoEncoderTopK.encode / decode on caller activations: x_dev fp32 [rows, embed_dim] with rows = B*T.
  * window > 1 applies the window top-k over T frames per utterance (rows must be a multiple of T). */
 int slsb_sae_encode(slsb_engine* e, const float* x_dev, int64_t rows, int T, int window, int precision,

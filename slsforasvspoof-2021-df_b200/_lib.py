@@ -48,6 +48,7 @@ _SIGNATURES = {
     "slsb_forward": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "slsb_extract_feat": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "slsb_get_tensor": (C.c_int, [_P, C.c_char_p, _P, C.c_int64, _P]),
+    "slsb_get_sparse": (C.c_int, [_P, _P, _P, _P, _P]),
     "slsb_sae_encode": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, _P]),
     "slsb_sae_decode": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, _P]),
     "slsb_sae_loss": (C.c_int, [_P, C.c_int, _P, _P]),

@@ -738,6 +738,17 @@ int slsb_get_tensor(slsb_engine* e, const char* name, float* dst, int64_t numel,
     return 0;
 }
 
+int slsb_get_sparse(slsb_engine* e, int32_t* idx_dev, float* val_dev, int32_t* count_dev, void* stream) {
+    if (!e || !idx_dev || !val_dev) { set_error("slsb_get_sparse: null argument"); return -1; }
+    if (!e->have_sel) { set_error("slsb_get_sparse: last forward ran no SAE head"); return -1; }
+    const slsb_config& c = e->cfg;
+    const long long M = (long long)e->B * e->T;
+    const float* sel = (e->head == SLSB_HEAD_WINDOW && c.sae_window > 1) ? e->votes.as<float>() : e->acts.as<float>();
+    LAUNCH(votes_compact(e->acts.as<float>(), sel, e->thr.as<float>(), e->cut.as<int>(), idx_dev, val_dev, count_dev, M, c.sae_dict, c.sae_k,
+                         static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
 int slsb_sae_encode(slsb_engine* e, const float* x_dev, int64_t rows, int T, int window, int precision, float* encoded_dev, void* stream) {
     if (check_ready(e)) return -1;
     const slsb_config& c = e->cfg;

@@ -120,6 +120,28 @@ __global__ void densify_kernel(const float* __restrict__ acts, const float* __re
     *reinterpret_cast<float4*>(out + i4) = o;
 }
 
+// compact form of the kept activations: one warp per row, ascending feature index, slots past the row's count get idx -1
+__global__ void __launch_bounds__(256) compact_kept_kernel(const float* __restrict__ acts, const float* __restrict__ sel, const float* __restrict__ thr,
+                                                           const int* __restrict__ cut, int* __restrict__ idx_out, float* __restrict__ val_out,
+                                                           int* __restrict__ count_out, long long rows, int D, int k) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float t = thr[row]; const int ct = cut[row];
+    int n = 0;
+    for (int c0 = 0; c0 < D; c0 += 32) {
+        const int c = c0 + lane;
+        const bool keep = kept(sel[row * D + c], c, t, ct);
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        const int pos = n + __popc(m & ((1u << lane) - 1u));
+        if (keep && pos < k) { idx_out[row * k + pos] = c; val_out[row * k + pos] = acts[row * D + c]; }
+        n += __popc(m);
+    }
+    if (n > k) n = k;
+    for (int j = n + lane; j < k; j += 32) { idx_out[row * k + j] = -1; val_out[row * k + j] = 0.f; }
+    if (lane == 0 && count_out) count_out[row] = n;
+}
+
 __global__ void mean_pool_kept_kernel(const float* __restrict__ acts, const float* __restrict__ sel, const float* __restrict__ thr,
                                       const int* __restrict__ cut, float* __restrict__ pooled, int T, int D, const int* __restrict__ lens) {
     const int b = blockIdx.y;
@@ -389,6 +411,14 @@ int votes_densify(const float* acts, const float* votes, const float* thr, const
     if (rows <= 0) return 0;
     const long long n4 = rows * D / 4;
     densify_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(acts, votes, thr, tie_cut, encoded, rows, D);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+int votes_compact(const float* acts, const float* votes, const float* thr, const int* tie_cut, int* idx_out, float* val_out, int* count_out,
+                  long long rows, int D, int k, cudaStream_t stream) {
+    if (rows <= 0) return 0;
+    if (D % 32 != 0) { set_error("votes_compact: D=%d must be a multiple of 32", D); return -1; }
+    compact_kept_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(acts, votes, thr, tie_cut, idx_out, val_out, count_out, rows, D, k);
     SLSB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -116,6 +116,9 @@ int window_votes(const float* acts, const float* sums, const float* thr_w, const
 // keep-by-votes: encoded = acts * mask(votes) ; pooled likewise
 int votes_densify(const float* acts, const float* votes, const float* thr, const int* tie_cut, float* encoded, long long rows, int D, cudaStream_t stream);
 int votes_mean_pool(const float* acts, const float* votes, const float* thr, const int* tie_cut, float* pooled, int B, int T, int D, const int* lens, cudaStream_t stream);
+// compact (index, value) form of the kept entries, ascending feature index, k slots per row (unused: idx -1, val 0)
+int votes_compact(const float* acts, const float* votes, const float* thr, const int* tie_cut, int* idx_out, float* val_out, int* count_out,
+                  long long rows, int D, int k, cudaStream_t stream);
 // classifier: LN(D) -> Linear(D,Hd) -> ReLU -> Linear(Hd,2) -> log_softmax   (model.py:183-189, :246-247)
 int classifier_head(const float* pooled, int B, int D, int Hd, const float* ln_w, const float* ln_b, const float* w1, const float* b1,
                     const float* w2, const float* b2, float* hidden /*[B, Hd] scratch*/, float* logprob, cudaStream_t stream);

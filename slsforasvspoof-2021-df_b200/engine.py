@@ -86,6 +86,15 @@ class Engine:
         check(self.lib.slsb_get_tensor(self._h, name.encode(), ptr(t), t.numel(), stream_ptr(self.device)), f"get_tensor({name})")
         return t
 
+    def get_sparse(self, rows: int):
+        """(indices int32 [rows, k], values fp32 [rows, k], counts int32 [rows]) of the last forward's SAE code."""
+        k = self.cfg.sae_k
+        idx = torch.empty(rows, k, device=self.device, dtype=torch.int32)
+        val = torch.empty(rows, k, device=self.device, dtype=torch.float32)
+        cnt = torch.empty(rows, device=self.device, dtype=torch.int32)
+        check(self.lib.slsb_get_sparse(self._h, ptr(idx), ptr(val), ptr(cnt), stream_ptr(self.device)), "slsb_get_sparse")
+        return idx, val, cnt
+
     def sae_encode(self, x: torch.Tensor, T: int, window: int, precision: int) -> torch.Tensor:
         rows = x.shape[0]
         out = torch.empty(rows, self.cfg.sae_dict, device=x.device, dtype=torch.float32)

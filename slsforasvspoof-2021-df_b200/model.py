@@ -223,6 +223,16 @@ class Model(_EngineOwner, nn.Module):
             return output, sae_loss
         return output
 
+    def last_sparse_code(self, batch: int, samples: int):
+        """Compact form of the last forward's SAE code: ``(indices int32 [B, T, k], values fp32 [B, T, k], counts int32
+        [B, T])``, indices ascending, unused slots -1.  ``last_sparse_features`` (dense, model.py:236-240) is its scatter;
+        the analysis scripts can consume this instead of the 4096-wide dense tensor."""
+        eng = self.engine()
+        T = eng.frames(samples)
+        idx, val, cnt = eng.get_sparse(batch * T)
+        k = idx.shape[-1]
+        return idx.view(batch, T, k), val.view(batch, T, k), cnt.view(batch, T)
+
     def get_interpretability_info(self, pooled_features):
         """model.py:262-293 (offline analysis surface; plain torch ops on the engine's sparse features)."""
         if self.last_sparse_features is None:

@@ -116,3 +116,23 @@ def test_pcm16_ingest_is_bit_exact_with_reference_pad(sls, cuda):
     assert torch.equal(a, b)
     with pytest.raises(sls.SlsbError):
         eng.score_pcm16_host([torch.zeros(0, dtype=torch.int16)], sls.HEAD_SAE, sls.PREC_BF16)
+
+
+@pytest.mark.parametrize("head", ["sae", "window"])
+def test_sparse_code_is_the_compact_form_of_the_dense_code(sls, cuda, head):
+    """next row N4: (indices, values) emitted by slsb_get_sparse scatter back to exactly the dense encoded tensor."""
+    from oracle.trunk import synth_clips
+    _, m = _small(sls, head, "fp32")
+    x = synth_clips(3, 2).to(cuda)
+    with torch.no_grad():
+        out = m(x, return_sae_loss=False, return_interpretability=True)
+    dense = m.last_sparse_features
+    idx, val, cnt = m.last_sparse_code(2, x.shape[1])
+    assert idx.shape == (2, 201, 128) and idx.dtype == torch.int32
+    valid = idx >= 0
+    assert torch.equal(valid.sum(-1).to(torch.int32), cnt) and int(cnt.max()) <= 128
+    scat = torch.zeros_like(dense)
+    scat.view(-1, dense.shape[-1]).scatter_add_(1, idx.view(-1, 128).clamp(min=0).long(), (val * valid).view(-1, 128))
+    assert torch.equal(scat, dense)
+    srt = torch.where(valid, idx, torch.full_like(idx, 1 << 30))
+    assert bool((srt[..., 1:] >= srt[..., :-1]).all())                          # ascending feature index
