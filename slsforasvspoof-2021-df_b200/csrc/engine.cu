@@ -428,29 +428,45 @@ static int run_trunk(slsb_engine* e, const float* wav, const int* slens, int B, 
             dots = e->sls_dots.as<float>();
             e->have_dots = true;
         }
+        // SLSB_RES_IN_GEMM (default 1): out_proj / fc2 add the fp32 residual stream in their epilogue (residual tile in and sum tile
+        // out through TMA, gemm_tc.cu::epilogue_tile_res_tma) and the LayerNorm kernels only read the stream (4 B) and write bf16.
+        // 0: the GEMMs write bf16 branch outputs and the LayerNorm kernels advance the stream (4 + 2 B read, 4 + 2 B written).
+        static int res_in_gemm = -1;
+        if (res_in_gemm < 0) { const char* v = getenv("SLSB_RES_IN_GEMM"); res_in_gemm = v ? atoi(v) : 1; }
         for (int l = 0; l < c.n_layers; ++l) {
             const std::string p = "L" + std::to_string(l);
             LnArgs a;
             a.out = e->lnbuf.p; a.out_bf16 = 1; a.w = W32(p + ".ln1.w"); a.b = W32(p + ".ln1.b"); a.rows = M; a.C = D;
             if (l == 0) a.in = e->X[0].p;
             else {
-                a.in = e->xmid.p; a.add = e->ybuf.p; a.sum_out = e->X[l].as<float>();
+                if (res_in_gemm) a.in = e->X[l].p;
+                else { a.in = e->xmid.p; a.add = e->ybuf.p; a.sum_out = e->X[l].as<float>(); }
                 if (want_dots) { a.dot_w = W32("sls.fc0.w"); a.dot_out = dots + (long long)(l - 1) * M; }
             }
             if (layernorm_timed(e, a, st)) return -1;
             if (linear(e, true, e->lnbuf.p, D, p + ".qkv.w", 3 * D, D, M, W32(p + ".qkv.b"), nullptr, 0, e->qkv.p, 3 * D, 1, ACT_NONE, st, PK_ENC_QKV)) return -1;
             if (attention(e, true, e->qkv.p, e->attn.p, B, T, H, flens, st)) return -1;
-            if (linear(e, true, e->attn.p, D, p + ".out.w", D, D, M, W32(p + ".out.b"), nullptr, 0, e->ybuf.p, D, 1, ACT_NONE, st, PK_ENC_OUT)) return -1;
             LnArgs a2;
-            a2.in = e->X[l].p; a2.add = e->ybuf.p; a2.sum_out = e->xmid.as<float>();
+            if (res_in_gemm) {
+                if (linear(e, true, e->attn.p, D, p + ".out.w", D, D, M, W32(p + ".out.b"), e->X[l].as<float>(), D, e->xmid.p, D, 0, ACT_NONE, st, PK_ENC_OUT)) return -1;
+                a2.in = e->xmid.p;
+            } else {
+                if (linear(e, true, e->attn.p, D, p + ".out.w", D, D, M, W32(p + ".out.b"), nullptr, 0, e->ybuf.p, D, 1, ACT_NONE, st, PK_ENC_OUT)) return -1;
+                a2.in = e->X[l].p; a2.add = e->ybuf.p; a2.sum_out = e->xmid.as<float>();
+            }
             a2.out = e->lnbuf.p; a2.out_bf16 = 1; a2.w = W32(p + ".ln2.w"); a2.b = W32(p + ".ln2.b"); a2.rows = M; a2.C = D;
             if (layernorm_timed(e, a2, st)) return -1;
             if (linear(e, true, e->lnbuf.p, D, p + ".fc1.w", F, D, M, W32(p + ".fc1.b"), nullptr, 0, e->ffn.p, F, 1, ACT_GELU, st, PK_ENC_FC1)) return -1;
-            if (linear(e, true, e->ffn.p, F, p + ".fc2.w", D, F, M, W32(p + ".fc2.b"), nullptr, 0, e->ybuf.p, D, 1, ACT_NONE, st, PK_ENC_FC2)) return -1;
+            if (res_in_gemm) {
+                if (linear(e, true, e->ffn.p, F, p + ".fc2.w", D, F, M, W32(p + ".fc2.b"), e->xmid.as<float>(), D, e->X[l + 1].p, D, 0, ACT_NONE, st, PK_ENC_FC2)) return -1;
+            } else {
+                if (linear(e, true, e->ffn.p, F, p + ".fc2.w", D, F, M, W32(p + ".fc2.b"), nullptr, 0, e->ybuf.p, D, 1, ACT_NONE, st, PK_ENC_FC2)) return -1;
+            }
         }
         // 5. X_n = xmid + fc2_{n-1}; final LayerNorm on x only (wav2vec2.py:905-906); xc = x - b_dec feeds the SAE (model.py:70)
         LnArgs a;
-        a.in = e->xmid.p; a.add = e->ybuf.p; a.sum_out = e->X[c.n_layers].as<float>();
+        if (res_in_gemm) a.in = e->X[c.n_layers].p;
+        else { a.in = e->xmid.p; a.add = e->ybuf.p; a.sum_out = e->X[c.n_layers].as<float>(); }
         a.out = e->xfinal.p; a.w = W32("enc_ln.w"); a.b = W32("enc_ln.b"); a.rows = M; a.C = D;
         if (want_xc && c.sae_dict > 0) { a.out2 = e->xc.p; a.out2_bf16 = 1; a.sub = W32("sae.b_dec"); }
         if (want_dots) { a.dot_w = W32("sls.fc0.w"); a.dot_out = dots + (long long)(c.n_layers - 1) * M; }

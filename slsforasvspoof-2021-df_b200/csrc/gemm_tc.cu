@@ -24,6 +24,9 @@ namespace slsb {
 
 namespace {
 
+#ifndef SLSB_STAGES256
+#define SLSB_STAGES256 4
+#endif
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;       // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
@@ -34,7 +37,7 @@ template <int BLOCK_N> struct SmemPlan {
     static constexpr int kStageA = BLOCK_M * BLOCK_K * 2;
     static constexpr int kStageB = BLOCK_N * BLOCK_K * 2;
     static constexpr int kStage = kStageA + kStageB;
-    static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+    static constexpr int kStages = (BLOCK_N == 256) ? SLSB_STAGES256 : (BLOCK_N == 128 ? 6 : 8);
     static constexpr int kStoreOffset = kStages * kStage;           // 2 x [128 rows x 64 bf16] SWIZZLE_128B staging tiles for TMA stores
     static constexpr int kStoreBytes = (BLOCK_N >= 128) ? 2 * 16384 : 0;
     static constexpr int kBiasOffset = kStoreOffset + kStoreBytes;    // this tile's bias slice
@@ -54,6 +57,7 @@ struct DevParams {
     int act, out_bf16;
     int kb_per_split;  // A_PLAIN split-K: batch index b selects k-blocks [b * kb_per_split, ...) and partial-output slab b (0 = off)
     int tma_store;     // bf16 output leaves through smem staging + cp.async.bulk.tensor stores
+    int res_tma;       // fp32 output = acc + bias + fp32 residual, residual tile fetched by TMA into the staging tile, summed in place, TMA-stored
     int debug_flags;   // bit0: epilogue does everything except the global stores / residual loads (mainloop ceiling measurements)
 };
 
@@ -201,10 +205,68 @@ __device__ __forceinline__ void epilogue_tile_tma(const DevParams& p, const CUte
     }
 }
 
+// fp32 residual stream through the GEMM epilogue without touching the LSU's global path: per 32-column chunk the issuer
+// TMA-loads the residual tile [128 rows x 32 fp32] into the half's staging tile, every thread adds its accumulator row + bias
+// IN PLACE (own row, SWIZZLE_128B chunk positions), and the same tile is TMA-stored as the new residual stream.
+// (out = x + branch(x), wav2vec2.py:1053 / :1058, with x kept in fp32.)
+template <int kCols>
+__device__ __forceinline__ void epilogue_tile_res_tma(const CUtensorMap* tmap_res, const CUtensorMap* tmap_out, uint32_t taddr, uint8_t* stage_tile,
+                                                      const float* bias_s, int half, int r, int col_base, int row0,
+                                                      uint64_t* full_bar, uint32_t full_parity, uint64_t* empty_bar,
+                                                      uint64_t* res_bar, uint32_t& res_phase) {
+    constexpr int kChunks = kCols / 32;
+    const int bar_id = 1 + half;
+    const bool issuer = r == 0;
+    if (issuer) {                                                    // residual chunk 0 travels while the MMAs of this tile still run
+        tma_store_wait_read<0>();
+        mbar_expect_tx(res_bar, 128 * 128);
+        tma_load_2d(stage_tile, tmap_res, res_bar, col_base, row0);
+    }
+    mbar_wait(full_bar, full_parity);
+    tc_fence_after();
+    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");      // this tile's bias slice (written by the caller) is visible
+    uint8_t* srow = stage_tile + r * 128;
+#pragma unroll 1
+    for (int c = 0; c < kChunks; ++c) {
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(taddr + c * 32, acc);
+        mbar_wait(res_bar, res_phase);
+        res_phase ^= 1u;
+        tmem_ld_wait();
+        if (c == kChunks - 1) {                                      // accumulator fully read: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if ((r & 31) == 0) mbar_arrive(empty_bar);
+        }
+        const float* bs = bias_s + half * kCols + c * 32;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float4* slot = reinterpret_cast<float4*>(srow + ((j ^ (r & 7)) << 4));
+            const float4 rv = *slot;
+            const float4 bb = *reinterpret_cast<const float4*>(bs + 4 * j);
+            float4 o;
+            o.x = __uint_as_float(acc[4 * j + 0]) + bb.x + rv.x; o.y = __uint_as_float(acc[4 * j + 1]) + bb.y + rv.y;
+            o.z = __uint_as_float(acc[4 * j + 2]) + bb.z + rv.z; o.w = __uint_as_float(acc[4 * j + 3]) + bb.w + rv.w;
+            *slot = o;
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (issuer) {
+            tma_store_2d(tmap_out, stage_tile, col_base + c * 32, row0);
+            tma_store_commit();
+            if (c + 1 < kChunks) {
+                tma_store_wait_read<0>();                             // the store has read the tile: it can take the next residual chunk
+                mbar_expect_tx(res_bar, 128 * 128);
+                tma_load_2d(stage_tile, tmap_res, res_bar, col_base + (c + 1) * 32, row0);
+            }
+        }
+    }
+}
+
 template <int BLOCK_N, int A_MODE>
 __global__ void __launch_bounds__(kNumThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const __grid_constant__ CUtensorMap tmap_out, const DevParams p) {
+               const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res, const DevParams p) {
     using Plan = SmemPlan<BLOCK_N>;
     constexpr int kStages = Plan::kStages;
     constexpr uint32_t kTmemCols = 2 * BLOCK_N;   // two accumulator stages (power of two >= 32 for BLOCK_N in {64,128,256})
@@ -216,7 +278,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tmem_full = empty_bar + kStages;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* res_bar = tmem_empty + 2;            // [2] residual chunk of column half h has landed in its staging tile
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -227,11 +290,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
-        if (p.tma_store) tma_prefetch_desc(&tmap_out);
+        if (p.tma_store || p.res_tma) tma_prefetch_desc(&tmap_out);
+        if (p.res_tma) tma_prefetch_desc(&tmap_res);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kNumEpiWarps); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kNumEpiWarps); mbar_init(&res_bar[s], 1); }
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr);
@@ -316,6 +380,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int half = (warp - 4) >> 2;          // column half
         constexpr int kColsPerWarp = BLOCK_N / 2;
         const int r = q * 32 + lane;
+        uint32_t res_phase = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             int t = tile;
@@ -330,6 +395,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const long long res_off = (long long)b * p.res_batch_stride + (long long)row * p.ldr;
             const uint32_t taddr0 = tmem_base + (uint32_t(q * 32) << 16) + acc * BLOCK_N + half * kColsPerWarp;
             const int col_base = n_blk * BLOCK_N + half * kColsPerWarp;
+            if constexpr (BLOCK_N == 256 && A_MODE == A_PLAIN) {
+                if (p.res_tma) {
+                    bias_s[half * kColsPerWarp + r] = __ldg(p.bias + col_base + r);       // visible after the first named barrier
+                    uint8_t* stage_tile = smem + Plan::kStoreOffset + half * 16384;
+                    epilogue_tile_res_tma<kColsPerWarp>(&tmap_res, &tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, m_blk * BLOCK_M,
+                                                        &tmem_full[acc], acc_phase, &tmem_empty[acc], &res_bar[half], res_phase);
+                    continue;
+                }
+            }
             if constexpr (BLOCK_N >= 128) {
                 if (p.tma_store) {
                     // this half's 128 bias values -> smem (visible after the first named barrier of the tile)
@@ -363,7 +437,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
-        if (p.tma_store && r == 0) tma_store_wait<0>();
+        if ((p.tma_store || p.res_tma) && r == 0) tma_store_wait<0>();
     }
 
     tc_fence_before();
@@ -385,7 +459,7 @@ bool epilogue_supported(int act, int out_bf16, bool has_res) {
 }
 
 template <int BLOCK_N, int A_MODE>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const DevParams& dp, int num_sms, cudaStream_t stream) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr, const DevParams& dp, int num_sms, cudaStream_t stream) {
     using Plan = SmemPlan<BLOCK_N>;
     static bool configured = false;
     auto kern = tc_gemm_kernel<BLOCK_N, A_MODE>;
@@ -395,7 +469,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, 
     }
     const int tiles = dp.batches * dp.m_tiles * dp.n_tiles;
     const int grid = tiles < num_sms ? tiles : num_sms;
-    SLSB_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(kNumThreads), Plan::kBytes, stream, ta, tb, to, dp));
+    SLSB_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(kNumThreads), Plan::kBytes, stream, ta, tb, to, tr, dp));
     return 0;
 }
 
@@ -433,8 +507,19 @@ int tc_gemm(const TcGemmArgs& g, int num_sms, cudaStream_t stream) {
     }
     { const char* dbg = getenv("SLSB_DEBUG_FLAGS"); dp.debug_flags = dbg ? atoi(dbg) : 0; }
 
-    CUtensorMap ta, tb, to;
+    CUtensorMap ta, tb, to, tr;
     memset(&to, 0, sizeof(to));
+    memset(&tr, 0, sizeof(tr));
+    // fp32 output with an fp32 residual of full-width tiles: residual in / sum out through TMA (epilogue_tile_res_tma)
+    dp.res_tma = (!g.out_bf16 && g.residual != nullptr && g.act == ACT_NONE && block_n == 256 && g.a_mode == A_PLAIN && g.k_splits <= 1 &&
+                  g.ldc % 4 == 0 && g.ldr % 4 == 0 && !getenv("SLSB_NO_RES_TMA")) ? 1 : 0;
+    if (dp.res_tma) {
+        uint64_t dims[2] = {(uint64_t)g.N, (uint64_t)g.M};
+        uint32_t box[2] = {32, BLOCK_M};
+        uint64_t so[1] = {(uint64_t)g.ldc * 4}, sr[1] = {(uint64_t)g.ldr * 4};
+        if (encode_tmap_f32(&to, g.out, 2, dims, so, box)) return -1;
+        if (encode_tmap_f32(&tr, g.residual, 2, dims, sr, box)) return -1;
+    }
     // bf16 outputs of full-width tiles leave through TMA stores (BLOCK_N = 256 -> two 128-column halves of two 64-column groups)
     dp.tma_store = (g.out_bf16 && g.residual == nullptr && block_n == 256 && g.a_mode != A_POS && g.k_splits <= 1 && !getenv("SLSB_NO_TMA_STORE")) ? 1 : 0;
     if (dp.tma_store) {
@@ -476,15 +561,15 @@ int tc_gemm(const TcGemmArgs& g, int num_sms, cudaStream_t stream) {
         if (encode_tmap_bf16(&ta, g.A, 3, dims, strides, box)) return -1;
     }
     if (g.a_mode == A_PLAIN) {
-        if (block_n == 256) return launch<256, A_PLAIN>(ta, tb, to, dp, num_sms, stream);
-        if (block_n == 128) return launch<128, A_PLAIN>(ta, tb, to, dp, num_sms, stream);
-        return launch<64, A_PLAIN>(ta, tb, to, dp, num_sms, stream);
+        if (block_n == 256) return launch<256, A_PLAIN>(ta, tb, to, tr, dp, num_sms, stream);
+        if (block_n == 128) return launch<128, A_PLAIN>(ta, tb, to, tr, dp, num_sms, stream);
+        return launch<64, A_PLAIN>(ta, tb, to, tr, dp, num_sms, stream);
     } else if (g.a_mode == A_CONV) {
-        if (block_n == 256) return launch<256, A_CONV>(ta, tb, to, dp, num_sms, stream);
-        if (block_n == 128) return launch<128, A_CONV>(ta, tb, to, dp, num_sms, stream);
-        return launch<64, A_CONV>(ta, tb, to, dp, num_sms, stream);
+        if (block_n == 256) return launch<256, A_CONV>(ta, tb, to, tr, dp, num_sms, stream);
+        if (block_n == 128) return launch<128, A_CONV>(ta, tb, to, tr, dp, num_sms, stream);
+        return launch<64, A_CONV>(ta, tb, to, tr, dp, num_sms, stream);
     }
-    return launch<64, A_POS>(ta, tb, to, dp, num_sms, stream);
+    return launch<64, A_POS>(ta, tb, to, tr, dp, num_sms, stream);
 }
 
 }  // namespace slsb
