@@ -272,13 +272,19 @@ static int conv_layer(slsb_engine* e, bool bf, const void* x, const void* Wp, co
 // x_out = x + gelu(pos_conv(x) + b)  (wav2vec2.py:915-917); xpad is scratch [B, T + K, D]
 static int pos_conv(slsb_engine* e, bool bf, const float* x, const void* Wp, const float* bias, float* out, void* xpad, int B, int T, int D,
                     int K, int groups, const int* flens, cudaStream_t st) {
-    const int Tp = T + K, gw = D / groups;
+    const int gw = D / groups;
+    // bf16: Toeplitz GEMM with 128 x 256 tiles (A_POS4) unless SLSB_POS_V1=1 asks for the 128 x 64 kernel; the padded stream then
+    // has a multiple of 4 frames per utterance (the extra frames are zero like the rest of the padding)
+    static int pos_v1 = -1;
+    if (pos_v1 < 0) { const char* v = getenv("SLSB_POS_V1"); pos_v1 = (v && atoi(v) != 0) ? 1 : 0; }
+    const bool pos4 = bf && !pos_v1 && gw == 64;
+    const int Tp = pos4 ? (T + K + 3) / 4 * 4 : T + K;
     LAUNCH(pad_frames(x, xpad, bf ? 1 : 0, B, T, D, K / 2, Tp, flens, st));
     ProfScope ps(e, st, PK_POS_GEMM, 2.0 * (double)B * T * D * K * gw);
     if (bf) {
         if (gw != 64) { set_error("pos_conv (tcgen05): group width %d != 64", gw); return -1; }
         TcGemmArgs g;
-        g.a_mode = A_POS; g.A = xpad; g.W = Wp; g.ldw = (long long)K * gw; g.M = T; g.N = D; g.K = K * gw; g.batches = B;
+        g.a_mode = pos4 ? A_POS4 : A_POS; g.A = xpad; g.W = Wp; g.ldw = (long long)K * gw; g.M = T; g.N = D; g.K = K * gw; g.batches = B;
         g.pos_dim = D; g.pos_tp = Tp;
         g.out = out; g.ldc = D; g.out_batch_stride = (long long)T * D; g.out_bf16 = 0; g.bias = bias;
         g.residual = x; g.ldr = D; g.res_batch_stride = (long long)T * D; g.act = ACT_GELU;
@@ -353,7 +359,7 @@ static int run_trunk(slsb_engine* e, const float* wav, const int* slens, int B, 
     if (e->fe[1].reserve((size_t)B * (c.n_conv > 1 ? L[1] : 1) * C * es)) return -1;
     if (e->lnbuf.reserve((size_t)M * D * es) || e->qkv.reserve((size_t)M * 3 * D * es) || e->attn.reserve((size_t)M * D * es) ||
         e->ffn.reserve((size_t)M * F * es) || e->xmid.reserve((size_t)M * D * 4) || e->xfinal.reserve((size_t)M * D * 4) ||
-        e->xc.reserve((size_t)M * D * es) || e->xpad.reserve((size_t)B * Tp * D * es) || e->flens.reserve((size_t)B * 4)) return -1;
+        e->xc.reserve((size_t)M * D * es) || e->xpad.reserve((size_t)B * (Tp + 4) * D * es) || e->flens.reserve((size_t)B * 4)) return -1;
     if ((int)e->X.size() < c.n_layers + 1) e->X.resize(c.n_layers + 1);
     for (int l = 0; l <= c.n_layers; ++l) if (e->X[l].reserve((size_t)M * D * 4)) return -1;
 

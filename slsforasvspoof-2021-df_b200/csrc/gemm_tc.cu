@@ -15,6 +15,11 @@
 //             (replaces the cuDNN call behind wav2vec2.py:795, :824-841)
 //   A_POS   : grouped positional conv (wav2vec2.py:862-875): for group g and tap t the A box is rows
 //             [m0 + t, m0 + t + 128) x channels [64 g, 64 g + 64) of the zero-padded [B, T+128, 1024] stream.
+//             (128 x 64 tiles: the N = 64 MMA is shared-memory-bound; kept for A/B and odd geometries.)
+//   A_POS4  : the same convolution as a Toeplitz GEMM with full-width tiles: four consecutive output frames t = 4i + j share
+//             one accumulator row, column (j, n) = 64 j + n, so N = 256; k-block u (0 .. K+2) multiplies input frame 4i + u
+//             with weight tap u - j (zero outside [0, K): the 3-D weight map's out-of-range fill).  A rows = 2 utterances x 64
+//             slots of i through a 4-D map (c, t % 4, t / 4, b); B = four 64-row boxes of the un-expanded weights.
 #include "common.cuh"
 #include "kernels.h"
 #include <cstdlib>
@@ -49,6 +54,7 @@ struct DevParams {
     int M, N, K;
     int batches, m_tiles, n_tiles;
     int conv_cin, conv_stride;
+    int pos_T, pos_B;  // A_POS4: frames per utterance / utterances
     void* out;
     long long ldc, out_batch_stride;
     const float* bias;
@@ -205,6 +211,45 @@ __device__ __forceinline__ void epilogue_tile_tma(const DevParams& p, const CUte
     }
 }
 
+// A_POS4 epilogue: accumulator row r = (utterance bb, slot i), column (j, n): out[b, 4i + j, 64 g + n] = x + gelu(acc + bias)
+// (wav2vec2.py:915-917).  128 columns per warp = shifts j = 2 half, 2 half + 1.
+__device__ __forceinline__ void epilogue_tile_pos4(const DevParams& p, uint32_t taddr, int half, int r, int g, int pair,
+                                                   uint64_t* full_bar, uint32_t full_parity) {
+    const int bb = r >> 6, i = r & 63;
+    const int b = 2 * pair + bb;
+    mbar_wait(full_bar, full_parity);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+        const int j = half * 2 + (c >> 1), n0 = (c & 1) * 32;
+        const int t = 4 * i + j;
+        const bool ok = b < p.pos_B && t < p.pos_T && !(p.debug_flags & 1);
+        const long long off = ((long long)b * p.pos_T + t) * p.ldc + g * 64 + n0;
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(taddr + c * 32, acc);
+        float4 rv[8];
+        if (ok) {
+            const float4* r4 = reinterpret_cast<const float4*>(p.residual + off);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) rv[q] = __ldg(r4 + q);
+        }
+        tmem_ld_wait();
+        if (!ok) continue;
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + g * 64 + n0);
+        float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 bb4 = __ldg(b4 + q);
+            float4 o;
+            o.x = rv[q].x + gelu_fast(__uint_as_float(acc[4 * q + 0]) + bb4.x);
+            o.y = rv[q].y + gelu_fast(__uint_as_float(acc[4 * q + 1]) + bb4.y);
+            o.z = rv[q].z + gelu_fast(__uint_as_float(acc[4 * q + 2]) + bb4.z);
+            o.w = rv[q].w + gelu_fast(__uint_as_float(acc[4 * q + 3]) + bb4.w);
+            o4[q] = o;
+        }
+    }
+}
+
 // fp32 residual stream through the GEMM epilogue without touching the LSU's global path: per 32-column chunk the issuer
 // TMA-loads the residual tile [128 rows x 32 fp32] into the half's staging tile, every thread adds its accumulator row + bias
 // IN PLACE (own row, SWIZZLE_128B chunk positions), and the same tile is TMA-stored as the new residual stream.
@@ -329,10 +374,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         const int k0 = kb * BLOCK_K;
                         const int tap = k0 / p.conv_cin, c = k0 - tap * p.conv_cin;
                         tma_load_4d(sa, &tmap_a, &full_bar[stage], c, tap % p.conv_stride, m_blk * BLOCK_M + tap / p.conv_stride, b);
-                    } else {
+                    } else if constexpr (A_MODE == A_POS) {
                         tma_load_3d(sa, &tmap_a, &full_bar[stage], n_blk * BLOCK_K, m_blk * BLOCK_M + kb, b);
+                    } else {       // A_POS4: input frame 4i + kb of utterances 2 m_blk, 2 m_blk + 1, channels of group n_blk
+                        tma_load_4d(sa, &tmap_a, &full_bar[stage], n_blk * 64, kb & 3, kb >> 2, 2 * m_blk);
                     }
-                    tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+                    if constexpr (A_MODE == A_POS4) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) tma_load_3d(sb + j * 8192, &tmap_b, &full_bar[stage], 0, kb - j, n_blk * 64);
+                    } else {
+                        tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+                    }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -395,6 +447,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const long long res_off = (long long)b * p.res_batch_stride + (long long)row * p.ldr;
             const uint32_t taddr0 = tmem_base + (uint32_t(q * 32) << 16) + acc * BLOCK_N + half * kColsPerWarp;
             const int col_base = n_blk * BLOCK_N + half * kColsPerWarp;
+            if constexpr (A_MODE == A_POS4) {
+                epilogue_tile_pos4(p, taddr0, half, r, n_blk, m_blk, &tmem_full[acc], acc_phase);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                continue;
+            }
             if constexpr (BLOCK_N == 256 && A_MODE == A_PLAIN) {
                 if (p.res_tma) {
                     bias_s[half * kColsPerWarp + r] = __ldg(p.bias + col_base + r);       // visible after the first named barrier
@@ -482,7 +541,13 @@ int tc_gemm(const TcGemmArgs& g, int num_sms, cudaStream_t stream) {
         return -1;
     }
     int block_n;
-    if (g.a_mode == A_POS) block_n = 64;
+    if (g.a_mode == A_POS4) {
+        if (g.act != ACT_GELU || g.out_bf16 || g.residual == nullptr || g.pos_tp % 4 != 0 || g.N % 64 != 0 || g.K % 64 != 0) {
+            set_error("tc_gemm: A_POS4 needs fp32 out + residual + GELU, padded length %% 4 == 0 (got %d), N %% 64 == 0", g.pos_tp);
+            return -1;
+        }
+        block_n = 256;
+    } else if (g.a_mode == A_POS) block_n = 64;
     else if (g.N % 256 == 0) block_n = 256;
     else if (g.N % 128 == 0) block_n = 128;
     else if (g.N % 64 == 0) block_n = 64;
@@ -498,6 +563,11 @@ int tc_gemm(const TcGemmArgs& g, int num_sms, cudaStream_t stream) {
     dp.out = g.out; dp.ldc = g.ldc; dp.out_batch_stride = g.out_batch_stride;
     dp.bias = g.bias; dp.residual = g.residual; dp.ldr = g.ldr; dp.res_batch_stride = g.res_batch_stride;
     dp.act = g.act; dp.out_bf16 = g.out_bf16;
+    if (g.a_mode == A_POS4) {       // tiles: (utterance pair, group); k-blocks: taps + 3 input frames
+        dp.pos_T = g.M; dp.pos_B = g.batches;
+        dp.batches = 1; dp.m_tiles = (g.batches + 1) / 2; dp.n_tiles = g.N / 64;
+        dp.K = g.K + 3 * BLOCK_K;
+    }
     if (g.k_splits > 1) {
         if (g.a_mode != A_PLAIN || g.batches != 1) { set_error("tc_gemm: split-K needs A_PLAIN and batches == 1"); return -1; }
         const int total_kb = g.K / BLOCK_K;
@@ -521,7 +591,8 @@ int tc_gemm(const TcGemmArgs& g, int num_sms, cudaStream_t stream) {
         if (encode_tmap_f32(&tr, g.residual, 2, dims, sr, box)) return -1;
     }
     // bf16 outputs of full-width tiles leave through TMA stores (BLOCK_N = 256 -> two 128-column halves of two 64-column groups)
-    dp.tma_store = (g.out_bf16 && g.residual == nullptr && block_n == 256 && g.a_mode != A_POS && g.k_splits <= 1 && !getenv("SLSB_NO_TMA_STORE")) ? 1 : 0;
+    dp.tma_store = (g.out_bf16 && g.residual == nullptr && block_n == 256 && g.a_mode != A_POS && g.a_mode != A_POS4 && g.k_splits <= 1 &&
+                    !getenv("SLSB_NO_TMA_STORE")) ? 1 : 0;
     if (dp.tma_store) {
         if (g.a_mode == A_CONV) {
             uint64_t dims[3] = {(uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.batches};
@@ -535,7 +606,13 @@ int tc_gemm(const TcGemmArgs& g, int num_sms, cudaStream_t stream) {
             if (encode_tmap_bf16(&to, g.out, 2, dims, strides, box)) return -1;
         }
     }
-    {   // W: [N, K] K-major
+    if (g.a_mode == A_POS4) {   // W [N][taps][64] viewed as (c, tap, n): one box = the 64 out-channels of a group at one tap
+        const uint64_t taps = (uint64_t)g.K / 64;
+        uint64_t dims[3] = {64, taps, (uint64_t)g.N};
+        uint64_t strides[2] = {128, taps * 128};
+        uint32_t box[3] = {64, 1, 64};
+        if (encode_tmap_bf16(&tb, g.W, 3, dims, strides, box)) return -1;
+    } else {   // W: [N, K] K-major
         uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.N};
         uint64_t strides[1] = {(uint64_t)g.ldw * 2};
         uint32_t box[2] = {BLOCK_K, (uint32_t)block_n};
@@ -553,6 +630,13 @@ int tc_gemm(const TcGemmArgs& g, int num_sms, cudaStream_t stream) {
         uint64_t strides[3] = {C * 2, s * C * 2, Lin * C * 2};
         uint32_t box[4] = {BLOCK_K, 1, BLOCK_M, 1};
         if (encode_tmap_bf16(&ta, g.A, 4, dims, strides, box)) return -1;
+    } else if (g.a_mode == A_POS4) {
+        // zero-padded stream [B, Tp, D] viewed as (c, t % 4, t / 4, b); box = 64 channels x 64 slots x 2 utterances
+        const uint64_t Dd = g.pos_dim, Tp = g.pos_tp;
+        uint64_t dims[4] = {Dd, 4, Tp / 4, (uint64_t)g.batches};
+        uint64_t strides[3] = {Dd * 2, 4 * Dd * 2, Tp * Dd * 2};
+        uint32_t box[4] = {BLOCK_K, 1, 64, 2};
+        if (encode_tmap_bf16(&ta, g.A, 4, dims, strides, box)) return -1;
     } else {
         // zero-padded stream [B, Tp, D]; box = 64 channels x 128 frames
         uint64_t dims[3] = {(uint64_t)g.pos_dim, (uint64_t)g.pos_tp, (uint64_t)g.batches};
@@ -569,6 +653,7 @@ int tc_gemm(const TcGemmArgs& g, int num_sms, cudaStream_t stream) {
         if (block_n == 128) return launch<128, A_CONV>(ta, tb, to, tr, dp, num_sms, stream);
         return launch<64, A_CONV>(ta, tb, to, tr, dp, num_sms, stream);
     }
+    if (g.a_mode == A_POS4) return launch<256, A_POS4>(ta, tb, to, tr, dp, num_sms, stream);
     return launch<64, A_POS>(ta, tb, to, tr, dp, num_sms, stream);
 }
 

@@ -5,7 +5,7 @@
 
 namespace slsb {
 
-enum AMode : int { A_PLAIN = 0, A_CONV = 1, A_POS = 2 };
+enum AMode : int { A_PLAIN = 0, A_CONV = 1, A_POS = 2, A_POS4 = 3 };
 
 // ---------------------------------------------------------------- tcgen05 bf16 GEMM (gemm_tc.cu)
 struct TcGemmArgs {
