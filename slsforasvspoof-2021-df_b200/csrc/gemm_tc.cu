@@ -151,7 +151,7 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, uint32_t taddr
 template <int ACT, int kCols, bool kConvOut>
 __device__ __forceinline__ void epilogue_tile_tma(const DevParams& p, const CUtensorMap* tmap_out, uint32_t taddr, uint8_t* stage_tile,
                                                   const float* bias_s, int half, int r, int col_base, int row0, int b,
-                                                  uint64_t* full_bar, uint32_t full_parity, uint64_t* empty_bar) {
+                                                  uint64_t* full_bar, uint32_t full_parity, uint32_t empty_bar_addr) {
     constexpr int kGroups = kCols / 64;
     const int bar_id = 1 + half;
     const bool issuer = r == 0;
@@ -168,7 +168,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const DevParams& p, const CUte
         if (g == kGroups - 1) {                                      // accumulator fully read: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if ((r & 31) == 0) mbar_arrive(empty_bar);
+            if ((r & 31) == 0) mbar_arrive_cluster(empty_bar_addr);
         }
         uint8_t* srow = stage_tile + r * 128;
 #pragma unroll
@@ -257,7 +257,7 @@ __device__ __forceinline__ void epilogue_tile_pos4(const DevParams& p, uint32_t 
 template <int kCols>
 __device__ __forceinline__ void epilogue_tile_res_tma(const CUtensorMap* tmap_res, const CUtensorMap* tmap_out, uint32_t taddr, uint8_t* stage_tile,
                                                       const float* bias_s, int half, int r, int col_base, int row0,
-                                                      uint64_t* full_bar, uint32_t full_parity, uint64_t* empty_bar,
+                                                      uint64_t* full_bar, uint32_t full_parity, uint32_t empty_bar_addr,
                                                       uint64_t* res_bar, uint32_t& res_phase) {
     constexpr int kChunks = kCols / 32;
     const int bar_id = 1 + half;
@@ -281,7 +281,7 @@ __device__ __forceinline__ void epilogue_tile_res_tma(const CUtensorMap* tmap_re
         if (c == kChunks - 1) {                                      // accumulator fully read: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if ((r & 31) == 0) mbar_arrive(empty_bar);
+            if ((r & 31) == 0) mbar_arrive_cluster(empty_bar_addr);
         }
         const float* bs = bias_s + half * kCols + c * 32;
 #pragma unroll
@@ -459,7 +459,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     bias_s[half * kColsPerWarp + r] = __ldg(p.bias + col_base + r);       // visible after the first named barrier
                     uint8_t* stage_tile = smem + Plan::kStoreOffset + half * 16384;
                     epilogue_tile_res_tma<kColsPerWarp>(&tmap_res, &tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, m_blk * BLOCK_M,
-                                                        &tmem_full[acc], acc_phase, &tmem_empty[acc], &res_bar[half], res_phase);
+                                                        &tmem_full[acc], acc_phase, smem_u32(&tmem_empty[acc]), &res_bar[half], res_phase);
                     continue;
                 }
             }
@@ -470,11 +470,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     uint8_t* stage_tile = smem + Plan::kStoreOffset + half * 16384;
                     constexpr bool kConvOut = (A_MODE == A_CONV);
                     if (p.act == ACT_GELU)
-                        epilogue_tile_tma<ACT_GELU, kColsPerWarp, kConvOut>(p, &tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, m_blk * BLOCK_M, b, &tmem_full[acc], acc_phase, &tmem_empty[acc]);
+                        epilogue_tile_tma<ACT_GELU, kColsPerWarp, kConvOut>(p, &tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, m_blk * BLOCK_M, b, &tmem_full[acc], acc_phase, smem_u32(&tmem_empty[acc]));
                     else if (p.act == ACT_RELU)
-                        epilogue_tile_tma<ACT_RELU, kColsPerWarp, kConvOut>(p, &tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, m_blk * BLOCK_M, b, &tmem_full[acc], acc_phase, &tmem_empty[acc]);
+                        epilogue_tile_tma<ACT_RELU, kColsPerWarp, kConvOut>(p, &tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, m_blk * BLOCK_M, b, &tmem_full[acc], acc_phase, smem_u32(&tmem_empty[acc]));
                     else
-                        epilogue_tile_tma<ACT_NONE, kColsPerWarp, kConvOut>(p, &tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, m_blk * BLOCK_M, b, &tmem_full[acc], acc_phase, &tmem_empty[acc]);
+                        epilogue_tile_tma<ACT_NONE, kColsPerWarp, kConvOut>(p, &tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, m_blk * BLOCK_M, b, &tmem_full[acc], acc_phase, smem_u32(&tmem_empty[acc]));
                     continue;
                 }
             }
@@ -505,6 +505,205 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tc_fence_after();
         tmem_dealloc<kTmemCols>(tmem_base);
     }
+}
+
+// =================================================================================================
+// CTA-pair version for the big plain GEMMs (A_PLAIN, 256-wide tiles): tcgen05.mma.cta_group::2
+//
+// A cluster of two CTAs (one TPC) computes a 256 x 256 tile: CTA r holds rows [128 r, 128 r + 128) of A and of the accumulator
+// and rows [128 r, 128 r + 128) of the 256 W rows (the N dimension): the pair's tensor cores read BOTH CTAs' shared memory, so
+// each SM stages 32 KB instead of 48 KB per 64-deep k-block (2/3 of the L2 -> SM operand traffic per FLOP) and 6 pipeline stages
+// fit where the single-CTA kernel has 4.  Only the leader (rank 0) issues MMAs; both CTAs' TMA loads complete on the leader's
+// `full` barrier; tcgen05.commit multicasts the `empty` / `tmem_full` arrivals to both CTAs; the epilogue warps of both CTAs
+// hand the accumulator back through the leader's `tmem_empty` barrier.  Epilogues are the ones of the single-CTA kernel.
+// =================================================================================================
+struct Plan2 {
+    static constexpr int kStageA = BLOCK_M * BLOCK_K * 2;            // this CTA's 128 rows of A
+    static constexpr int kStageB = 128 * BLOCK_K * 2;                // this CTA's 128 of the tile's 256 W rows
+    static constexpr int kStage = kStageA + kStageB;                 // 32 KB
+    static constexpr int kStages = 6;
+    static constexpr int kStoreOffset = kStages * kStage;
+    static constexpr int kStoreBytes = 2 * 16384;
+    static constexpr int kBiasOffset = kStoreOffset + kStoreBytes;
+    static constexpr int kBarOffset = kBiasOffset + 256 * 4;
+    static constexpr int kBytes = kBarOffset + 256;
+};
+
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_cluster(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+// TMA load whose completion is signalled on an mbarrier that may live in the peer CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// MMA completion -> arrive on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res, const DevParams p) {
+    constexpr int kStages = Plan2::kStages;
+    constexpr int BLOCK_N = 256;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) { if (threadIdx.x == 0) printf("slsb: dynamic smem base not 1024-aligned\n"); __trap(); }
+    float* bias_s = reinterpret_cast<float*>(smem + Plan2::kBiasOffset);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Plan2::kBarOffset);      // used in the leader CTA only
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full = empty_bar + kStages;
+    uint64_t* tmem_empty = tmem_full + 2;                                            // used in the leader CTA only (16 warp arrivals)
+    uint64_t* res_bar = tmem_empty + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_rank();
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const int m2_tiles = (p.M + 255) / 256;
+    const int num_tiles = m2_tiles * p.n_tiles;
+    const int num_kb = p.K / BLOCK_K;
+
+    griddep_launch();
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+        if (p.tma_store || p.res_tma) tma_prefetch_desc(&tmap_out);
+        if (p.res_tma) tma_prefetch_desc(&tmap_res);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 2 * kNumEpiWarps); mbar_init(&res_bar[s], 1); }
+        mbar_fence_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_barrier();                  // both CTAs' barriers and TMEM are ready before any cross-CTA traffic
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    griddep_wait();
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs; completion on the leader's barrier) =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+                const int n_blk = tile % p.n_tiles, m2 = tile / p.n_tiles;
+                const int row0 = m2 * 256 + (int)rank * 128;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Plan2::kStage;
+                    uint8_t* sb = sa + Plan2::kStageA;
+                    if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Plan2::kStage);
+                    const uint32_t bar = map_cluster(smem_u32(&full_bar[stage]), 0);
+                    tma_load_2d_pair(sa, &tmap_a, bar, kb * BLOCK_K, row0);
+                    tma_load_2d_pair(sb, &tmap_b, bar, kb * BLOCK_K, n_blk * BLOCK_N + (int)rank * 128);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread of the leader CTA) =====================
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Plan2::kStage);
+                    const uint64_t da = make_smem_desc_sw128(sa, 0, 1024);
+                    const uint64_t db = make_smem_desc_sw128(sa + Plan2::kStageA, 0, 1024);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                        tc_mma_f16_pair(d_tmem, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc_commit_pair(&empty_bar[stage]);     // both CTAs may refill this stage
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                tc_commit_pair(&tmem_full[acc]);           // both CTAs' epilogues may read their 128 rows
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue warps (both CTAs, own 128 rows) =====================
+        const int q = warp & 3, half = (warp - 4) >> 2;
+        constexpr int kColsPerWarp = BLOCK_N / 2;
+        const int r = q * 32 + lane;
+        uint32_t res_phase = 0;
+        int it = 0;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+            const int n_blk = tile % p.n_tiles, m2 = tile / p.n_tiles;
+            const int row0 = m2 * 256 + (int)rank * 128;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const uint32_t taddr0 = tmem_base + (uint32_t(q * 32) << 16) + acc * BLOCK_N + half * kColsPerWarp;
+            const int col_base = n_blk * BLOCK_N + half * kColsPerWarp;
+            const uint32_t free_bar = map_cluster(smem_u32(&tmem_empty[acc]), 0);
+            bias_s[half * kColsPerWarp + r] = __ldg(p.bias + col_base + r);       // visible after the first named barrier of the tile
+            uint8_t* stage_tile = smem + Plan2::kStoreOffset + half * 16384;
+            if (p.res_tma) {
+                epilogue_tile_res_tma<kColsPerWarp>(&tmap_res, &tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, row0,
+                                                    &tmem_full[acc], acc_phase, free_bar, &res_bar[half], res_phase);
+            } else if (p.act == ACT_GELU) {
+                epilogue_tile_tma<ACT_GELU, kColsPerWarp, false>(p, &tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, row0, 0, &tmem_full[acc], acc_phase, free_bar);
+            } else if (p.act == ACT_RELU) {
+                epilogue_tile_tma<ACT_RELU, kColsPerWarp, false>(p, &tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, row0, 0, &tmem_full[acc], acc_phase, free_bar);
+            } else {
+                epilogue_tile_tma<ACT_NONE, kColsPerWarp, false>(p, &tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, row0, 0, &tmem_full[acc], acc_phase, free_bar);
+            }
+        }
+        if (r == 0) tma_store_wait<0>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_barrier();                  // nobody frees TMEM / exits while the peer's tensor core may still touch this CTA
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    }
+}
+
+int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr, const DevParams& dp, int num_sms,
+                cudaStream_t stream) {
+    static bool configured = false;
+    static int max_pairs = 0;
+    if (!configured) {
+        SLSB_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan2::kBytes));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(num_sms & ~1); cfg.blockDim = dim3(kNumThreads); cfg.dynamicSmemBytes = Plan2::kBytes;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, tc_gemm_pair_kernel, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms / 2; }
+        max_pairs = n < num_sms / 2 ? n : num_sms / 2;
+        configured = true;
+    }
+    const int tiles = ((dp.M + 255) / 256) * dp.n_tiles;
+    const int pairs = tiles < max_pairs ? tiles : max_pairs;
+    SLSB_CUDA_CHECK(launch_pdl(tc_gemm_pair_kernel, dim3(2 * pairs), dim3(kNumThreads), Plan2::kBytes, stream, ta, tb, to, tr, dp));
+    return 0;
 }
 
 bool epilogue_supported(int act, int out_bf16, bool has_res) {
@@ -645,6 +844,16 @@ int tc_gemm(const TcGemmArgs& g, int num_sms, cudaStream_t stream) {
         if (encode_tmap_bf16(&ta, g.A, 3, dims, strides, box)) return -1;
     }
     if (g.a_mode == A_PLAIN) {
+        static int use_pair = -1;
+        if (use_pair < 0) { const char* v = getenv("SLSB_GEMM_PAIR"); use_pair = v ? atoi(v) : 1; }
+        if (block_n == 256 && use_pair && (dp.tma_store || dp.res_tma) && dp.kb_per_split == 0 && g.M >= 256) {
+            // CTA-pair kernel: the W map's box is this CTA's 128 of the tile's 256 rows
+            uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.N};
+            uint64_t strides[1] = {(uint64_t)g.ldw * 2};
+            uint32_t box[2] = {BLOCK_K, 128};
+            if (encode_tmap_bf16(&tb, g.W, 2, dims, strides, box)) return -1;
+            return launch_pair(ta, tb, to, tr, dp, num_sms, stream);
+        }
         if (block_n == 256) return launch<256, A_PLAIN>(ta, tb, to, tr, dp, num_sms, stream);
         if (block_n == 128) return launch<128, A_PLAIN>(ta, tb, to, tr, dp, num_sms, stream);
         return launch<64, A_PLAIN>(ta, tb, to, tr, dp, num_sms, stream);
