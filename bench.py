@@ -268,8 +268,8 @@ def main():
         hbm = {k: eng.profile_read(i) for i, k in ((8, "layernorm_residual"), (9, "sls_fuse_pool"), (10, "sls_fc1"))}
         eng.profile(False)
         ach = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
-        roof = {"bound": "tensor", "kernel": "tc_gemm_kernel (encoder qkv/out/fc1/fc2)", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
-                "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": _traffic("tc_gemm_kernel"),
+        roof = {"bound": "tensor", "kernel": "tc_gemm_pair_kernel (encoder qkv / out_proj+residual / fc1+GELU / fc2+residual, tcgen05 cta_group::2)", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
+                "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": _traffic("tc_gemm_pair_kernel"),
                 "peak_source": peaks["source"] + " (sustained)",
                 "launches": g_n, "avg_launch_ms": g_ms / max(g_n, 1), "flops_per_launch": g_fl / max(g_n, 1),
                 "share_of_step": (g_ms / psteps) / (ms / args.steps),

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Profiling visit (after the plain commands have exited 0 without ncu): launch list of the bench command + ncu --set full of
-# the dominant kernel (tcgen05 encoder GEMM: one launch each of qkv / out_proj / fc1 / fc2), the conv pair kernel and attention.
+# the dominant kernel (CTA-pair tcgen05 encoder GEMM: one launch each of qkv / out_proj / fc1 / fc2), the conv pair kernel, LayerNorm, attention.
 set -u
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
@@ -12,9 +12,9 @@ echo "launch list rc=$?"
 P="python tools/prof_step.py --steps 1 --warmup 1 --head sls"
 $P > gpurun_out/prof_plain.log 2>&1 || { echo "plain prof_step failed"; exit 1; }
 # launch order inside a step: ... LN, qkv GEMM, attention, out GEMM, LN, fc1, fc2 ... : skip the first step (warm-up) entirely
-ncu --set full --clock-control none --import-source on -k regex:tc_gemm_kernel -s 110 -c 4 -o gpurun_out/prof_gemm -f $P > gpurun_out/ncu_gemm.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:tc_gemm_pair_kernel -s 100 -c 4 -o gpurun_out/prof_gemm -f $P > gpurun_out/ncu_gemm.log 2>&1
 echo "gemm capture rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:tc_gemm_ln2_kernel -s 6 -c 2 -o gpurun_out/prof_ln2 -f $P > gpurun_out/ncu_ln2.log 2>&1
 echo "ln2 capture rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:"ln_kernel|sls_fuse_pool" -s 60 -c 3 -o gpurun_out/prof_hbm -f $P > gpurun_out/ncu_hbm.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"ln_kernel|sls_fuse_pool|attn_tc_kernel" -s 75 -c 4 -o gpurun_out/prof_hbm -f $P > gpurun_out/ncu_hbm.log 2>&1
 echo "hbm capture rc=$?"
