@@ -558,6 +558,13 @@ __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 
+// Static tile schedule of the pair kernel: round i hands tile i * P + p to pair p in even rounds and to pair P - 1 - p in odd
+// rounds (snake order).  Tiles are ordered n-fastest with the ragged last row block (M % 256 rows, cheaper) at the end, so the few
+// tiles of a partial last round land on pairs whose previous tile was a cheap one (fc1, M = 12864: 12 -> 11.25 rounds).
+__device__ __forceinline__ int pair_tile(int it, int pair, int num_pairs) {
+    return it * num_pairs + ((it & 1) ? (num_pairs - 1 - pair) : pair);
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
 tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res, const DevParams p) {
@@ -607,7 +614,9 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // ===================== TMA producer (both CTAs; completion on the leader's barrier) =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+            for (int it = 0;; ++it) {
+                const int tile = pair_tile(it, pair, num_pairs);
+                if (tile >= num_tiles) break;
                 const int n_blk = tile % p.n_tiles, m2 = tile / p.n_tiles;
                 const int row0 = m2 * 256 + (int)rank * 128;
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -627,8 +636,7 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (lane == 0 && rank == 0) {
             constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N);
             int stage = 0; uint32_t phase = 0;
-            int it = 0;
-            for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+            for (int it = 0; pair_tile(it, pair, num_pairs) < num_tiles; ++it) {
                 const int acc = it & 1;
                 mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -654,8 +662,9 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         constexpr int kColsPerWarp = BLOCK_N / 2;
         const int r = q * 32 + lane;
         uint32_t res_phase = 0;
-        int it = 0;
-        for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+        for (int it = 0;; ++it) {
+            const int tile = pair_tile(it, pair, num_pairs);
+            if (tile >= num_tiles) break;
             const int n_blk = tile % p.n_tiles, m2 = tile / p.n_tiles;
             const int row0 = m2 * 256 + (int)rank * 128;
             const int acc = it & 1;
