@@ -232,24 +232,31 @@ int launch_ln(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t
 }
 
 // raw audio -> hi/lo bf16 im2col rows for conv0: [x_hi(10) 0.. | x_hi(10) 0.. | x_lo(10) 0.. | 0 (16)]
-__global__ void conv0_im2col_kernel(const float* __restrict__ wav, bf16* __restrict__ out, int S, int L0, int k, int stride, long long rows) {
-    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// Eight threads build one 128-byte row, one 16-byte unit each (unit u holds elements [8u, 8u + 8)), so a warp writes 512
+// contiguous bytes per store instruction; the 10 audio samples of a row come from L1 (8 threads share them).
+__global__ void __launch_bounds__(256) conv0_im2col_kernel(const float* __restrict__ wav, bf16* __restrict__ out, int S, int L0, int k, int stride,
+                                                           long long rows) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long row = gid >> 3;
+    const int u = (int)(gid & 7);
     if (row >= rows) return;
     const int b = (int)(row / L0), f = (int)(row - (long long)b * L0);
     const float* x = wav + (long long)b * S + (long long)f * stride;
-    __align__(16) bf16 v[64];
+    const int seg = u >> 1;                  // 16-element segment: 0 = x_hi, 1 = x_hi, 2 = x_lo, 3 = zeros
+    const int t0 = (u & 1) * 8;              // first tap of this unit inside its segment
+    __align__(16) bf16 v[8];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) v[i] = __float2bfloat16_rn(0.f);
-    for (int t = 0; t < k; ++t) {
-        const float xv = __ldg(x + t);
-        const bf16 hi = __float2bfloat16_rn(xv);
-        const bf16 lo = __float2bfloat16_rn(xv - __bfloat162float(hi));
-        v[t] = hi; v[16 + t] = hi; v[32 + t] = lo;
+    for (int i = 0; i < 8; ++i) {
+        const int t = t0 + i;
+        float val = 0.f;
+        if (seg < 3 && t < k) {
+            const float xv = __ldg(x + t);
+            const bf16 hi = __float2bfloat16_rn(xv);
+            val = seg == 2 ? xv - __bfloat162float(hi) : __bfloat162float(hi);
+        }
+        v[i] = __float2bfloat16_rn(val);
     }
-    uint4* o = reinterpret_cast<uint4*>(out + row * 64);
-    const uint4* s4 = reinterpret_cast<const uint4*>(v);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = s4[i];
+    *reinterpret_cast<uint4*>(out + row * 64 + u * 8) = *reinterpret_cast<const uint4*>(v);
 }
 
 // conv0 weights [C, k] fp32 -> [C, 64] bf16: [w_hi | w_lo | w_hi | 0] so that A.W^T = x_hi w_hi + x_hi w_lo + x_lo w_hi
@@ -312,7 +319,7 @@ int tc_gemm_ln_gelu(const TcLnGemmArgs& g, int num_sms, cudaStream_t stream) {
 int conv0_im2col(const float* wav, void* out, int B, int S, int L0, int k, int stride, cudaStream_t stream) {
     if (k > 16) { set_error("conv0_im2col: k=%d > 16", k); return -1; }
     const long long rows = (long long)B * L0;
-    conv0_im2col_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, stream>>>(wav, static_cast<bf16*>(out), S, L0, k, stride, rows);
+    conv0_im2col_kernel<<<(unsigned)((rows * 8 + 255) / 256), 256, 0, stream>>>(wav, static_cast<bf16*>(out), S, L0, k, stride, rows);
     SLSB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

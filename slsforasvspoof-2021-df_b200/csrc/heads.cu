@@ -346,15 +346,16 @@ __global__ void __launch_bounds__(256) sls_fuse_pool_kernel(LayerPtrs L, int n_l
         for (int j = (int)gridDim.x * J + threadIdx.x; j < ldo; j += blockDim.x) out[(long long)b * ldo + j] = from_f32<TO>(0.f);
 }
 
-// partial sums [B][KS][N] -> h = selu(sum + bias) -> fc3 -> selu -> log_softmax ; one block per utterance
-__global__ void __launch_bounds__(256) sls_tail_kernel(const float* __restrict__ partial, int KS, int Hd, const float* __restrict__ b1,
-                                                       const float* __restrict__ w3, const float* __restrict__ b3, float* __restrict__ logprob) {
-    __shared__ float red0[8], red1[8];
-    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// partial sums [B][KS][N] -> h = selu(sum + bias) -> fc3 -> selu -> log_softmax ; one block of 1024 threads per utterance
+// (one hidden unit per thread: the KS partials of a unit are read by consecutive threads -> coalesced rows of the partial matrix)
+__global__ void __launch_bounds__(1024) sls_tail_kernel(const float* __restrict__ partial, int KS, int Hd, const float* __restrict__ b1,
+                                                        const float* __restrict__ w3, const float* __restrict__ b3, float* __restrict__ logprob) {
+    __shared__ float red0[32], red1[32];
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     float l0 = 0.f, l1 = 0.f;
-    for (int n = threadIdx.x; n < Hd; n += 256) {
+    for (int n = threadIdx.x; n < Hd; n += blockDim.x) {
         float s = 0.f;
-        for (int ks = 0; ks < KS; ++ks) s += partial[((long long)b * KS + ks) * Hd + n];
+        for (int ks = 0; ks < KS; ++ks) s += partial[((long long)b * KS + ks) * Hd + n];      // fixed order: bit-stable
         const float h = selu(s + b1[n]);
         l0 = fmaf(w3[n], h, l0); l1 = fmaf(w3[Hd + n], h, l1);
     }
@@ -363,7 +364,7 @@ __global__ void __launch_bounds__(256) sls_tail_kernel(const float* __restrict__
     __syncthreads();
     if (threadIdx.x == 0) {
         float a = b3[0], c = b3[1];
-        for (int w = 0; w < 8; ++w) { a += red0[w]; c += red1[w]; }
+        for (int w = 0; w < nwarps; ++w) { a += red0[w]; c += red1[w]; }
         a = selu(a); c = selu(c);
         const float m = fmaxf(a, c);
         const float lse = m + logf(expf(a - m) + expf(c - m));
@@ -488,7 +489,7 @@ int sls_fuse_pool(const float* const* layers, int n_layers, const float* layer_w
     return 0;
 }
 int sls_tail(const float* partial, int KS, int B, int Hd, const float* b1, const float* w3, const float* b3, float* logprob, cudaStream_t stream) {
-    sls_tail_kernel<<<B, 256, 0, stream>>>(partial, KS, Hd, b1, w3, b3, logprob);
+    sls_tail_kernel<<<B, 1024, 0, stream>>>(partial, KS, Hd, b1, w3, b3, logprob);
     SLSB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
