@@ -136,3 +136,30 @@ def test_sparse_code_is_the_compact_form_of_the_dense_code(sls, cuda, head):
     assert torch.equal(scat, dense)
     srt = torch.where(valid, idx, torch.full_like(idx, 1 << 30))
     assert bool((srt[..., 1:] >= srt[..., :-1]).all())                          # ascending feature index
+
+
+def test_full_size_batch64_properties(sls, cuda):
+    """BASELINE config 2 at its full size (24 layers, B = 64 x 64 600 samples, bf16, SLS head), through size-independent
+    properties: the first two clips reproduce the committed golden log-probs (oracle, 2e-2), every clip's score is bit-identical
+    to what it gets in a batch of 2 and under a permutation of the batch, and the scores are proper probabilities."""
+    from oracle.heads import OracleModel
+    from oracle.trunk import seeded_init_
+    om = OracleModel(head="sls").eval()
+    seeded_init_(om, 1234)
+    m = sls.ModelSLS(None, "cuda", cp_path=None, precision="bf16")
+    m.load_state_dict(om.state_dict(), strict=False)
+    m = m.to("cuda").eval()
+    eng = m.engine()
+    wav = eng.synth_clips(0, 64)
+    with torch.no_grad():
+        full = m(wav)
+        pair = m(wav[:2].contiguous())
+        tail = m(wav[62:].contiguous())
+        perm = torch.randperm(64, generator=torch.Generator().manual_seed(3)).to(cuda)
+        shuffled = m(wav[perm].contiguous())
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "xlsr300m_sls_b2.npz"))
+    assert float(np.abs(full[:2].cpu().numpy() - fx["logprob"]).max()) <= 2e-2
+    assert torch.equal(full[:2], pair) and torch.equal(full[62:], tail)
+    assert torch.equal(shuffled, full[perm])
+    p = torch.exp(full)
+    assert torch.isfinite(full).all() and float((p.sum(-1) - 1).abs().max()) < 1e-5
