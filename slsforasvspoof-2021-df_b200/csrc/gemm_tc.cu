@@ -258,11 +258,14 @@ template <int kCols>
 __device__ __forceinline__ void epilogue_tile_res_tma(const CUtensorMap* tmap_res, const CUtensorMap* tmap_out, uint32_t taddr, uint8_t* stage_tile,
                                                       const float* bias_s, int half, int r, int col_base, int row0,
                                                       uint64_t* full_bar, uint32_t full_parity, uint32_t empty_bar_addr,
-                                                      uint64_t* res_bar, uint32_t& res_phase) {
+                                                      uint64_t* res_bar, uint32_t& res_phase, int dbg = 0) {
+    // dbg (SLSB_DEBUG_FLAGS, measurements only): bit1 = no residual TMA loads (residual reads as whatever the tile holds),
+    // bit2 = no TMA stores
     constexpr int kChunks = kCols / 32;
     const int bar_id = 1 + half;
     const bool issuer = r == 0;
-    if (issuer) {                                                    // residual chunk 0 travels while the MMAs of this tile still run
+    const bool do_load = !(dbg & 2), do_store = !(dbg & 4);
+    if (issuer && do_load) {                                         // residual chunk 0 travels while the MMAs of this tile still run
         tma_store_wait_read<0>();
         mbar_expect_tx(res_bar, 128 * 128);
         tma_load_2d(stage_tile, tmap_res, res_bar, col_base, row0);
@@ -275,8 +278,10 @@ __device__ __forceinline__ void epilogue_tile_res_tma(const CUtensorMap* tmap_re
     for (int c = 0; c < kChunks; ++c) {
         uint32_t acc[32];
         tmem_ld_32x32b_x32(taddr + c * 32, acc);
-        mbar_wait(res_bar, res_phase);
-        res_phase ^= 1u;
+        if (do_load) {
+            mbar_wait(res_bar, res_phase);
+            res_phase ^= 1u;
+        }
         tmem_ld_wait();
         if (c == kChunks - 1) {                                      // accumulator fully read: hand it back to the MMA warp
             tc_fence_before();
@@ -297,9 +302,11 @@ __device__ __forceinline__ void epilogue_tile_res_tma(const CUtensorMap* tmap_re
         fence_proxy_async_smem();
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         if (issuer) {
-            tma_store_2d(tmap_out, stage_tile, col_base + c * 32, row0);
-            tma_store_commit();
-            if (c + 1 < kChunks) {
+            if (do_store) {
+                tma_store_2d(tmap_out, stage_tile, col_base + c * 32, row0);
+                tma_store_commit();
+            }
+            if (c + 1 < kChunks && do_load) {
                 tma_store_wait_read<0>();                             // the store has read the tile: it can take the next residual chunk
                 mbar_expect_tx(res_bar, 128 * 128);
                 tma_load_2d(stage_tile, tmap_res, res_bar, col_base + (c + 1) * 32, row0);
@@ -676,7 +683,7 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             uint8_t* stage_tile = smem + Plan2::kStoreOffset + half * 16384;
             if (p.res_tma) {
                 epilogue_tile_res_tma<kColsPerWarp>(&tmap_res, &tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, row0,
-                                                    &tmem_full[acc], acc_phase, free_bar, &res_bar[half], res_phase);
+                                                    &tmem_full[acc], acc_phase, free_bar, &res_bar[half], res_phase, p.debug_flags);
             } else if (p.act == ACT_GELU) {
                 epilogue_tile_tma<ACT_GELU, kColsPerWarp, false>(p, &tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, row0, 0, &tmem_full[acc], acc_phase, free_bar);
             } else if (p.act == ACT_RELU) {
