@@ -134,6 +134,10 @@ struct slsb_engine {
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_slot_free[2] = {nullptr, nullptr}, ev_done[4] = {nullptr, nullptr, nullptr, nullptr};
     int64_t submit_seq = 0;
     std::vector<Buf> X;
+    // in-place stream mode (bf16 path): ONE fp32 residual stream `X[0]` advanced by reduce-add GEMM epilogues, bf16 snapshots of the
+    // 24 layer results (`snap`) written by the LayerNorm kernel that reads them
+    std::vector<Buf> snap;
+    bool inplace = false;
     // last call
     int B = 0, S = 0, T = 0, prec = 0, head = 0;
     bool have_lens = false, have_acts = false, have_sel = false, have_dots = false;
@@ -360,8 +364,21 @@ static int run_trunk(slsb_engine* e, const float* wav, const int* slens, int B, 
     if (e->lnbuf.reserve((size_t)M * D * es) || e->qkv.reserve((size_t)M * 3 * D * es) || e->attn.reserve((size_t)M * D * es) ||
         e->ffn.reserve((size_t)M * F * es) || e->xmid.reserve((size_t)M * D * 4) || e->xfinal.reserve((size_t)M * D * 4) ||
         e->xc.reserve((size_t)M * D * es) || e->xpad.reserve((size_t)B * (Tp + 4) * D * es) || e->flens.reserve((size_t)B * 4)) return -1;
+    // SLSB_INPLACE (default 1, bf16 path): the residual stream lives in ONE fp32 buffer that out_proj / fc2 advance with TMA reduce-add
+    // stores (no residual loads); layer result l is snapshotted in bf16 by the LayerNorm that reads it (the SLS head then reads
+    // 2 B per element instead of 4).  0: one fp32 buffer per layer result, residual tiles loaded by TMA.
+    static int inplace_env = -1;
+    if (inplace_env < 0) { const char* v = getenv("SLSB_INPLACE"); inplace_env = v ? atoi(v) : 1; }
+    const bool inplace = bf && inplace_env != 0;
+    e->inplace = inplace;
     if ((int)e->X.size() < c.n_layers + 1) e->X.resize(c.n_layers + 1);
-    for (int l = 0; l <= c.n_layers; ++l) if (e->X[l].reserve((size_t)M * D * 4)) return -1;
+    if ((int)e->snap.size() < c.n_layers) e->snap.resize(c.n_layers);
+    if (inplace) {
+        if (e->X[0].reserve((size_t)M * D * 4)) return -1;
+        for (int l = 0; l < c.n_layers; ++l) if (e->snap[l].reserve((size_t)M * D * 2)) return -1;
+    } else {
+        for (int l = 0; l <= c.n_layers; ++l) if (e->X[l].reserve((size_t)M * D * 4)) return -1;
+    }
 
     int* flens = nullptr;
     if (slens) {
@@ -441,6 +458,25 @@ static int run_trunk(slsb_engine* e, const float* wav, const int* slens, int B, 
         if (res_in_gemm < 0) { const char* v = getenv("SLSB_RES_IN_GEMM"); res_in_gemm = v ? atoi(v) : 1; }
         for (int l = 0; l < c.n_layers; ++l) {
             const std::string p = "L" + std::to_string(l);
+            if (inplace) {
+                float* xs = e->X[0].as<float>();
+                LnArgs a;      // LN1 reads the stream = layer result l - 1: snapshot it (bf16) and emit the SLS fc0 dots on the way
+                a.in = xs; a.out = e->lnbuf.p; a.out_bf16 = 1; a.w = W32(p + ".ln1.w"); a.b = W32(p + ".ln1.b"); a.rows = M; a.C = D;
+                if (l > 0) {
+                    a.copy_out = e->snap[l - 1].p;
+                    if (want_dots) { a.dot_w = W32("sls.fc0.w"); a.dot_out = dots + (long long)(l - 1) * M; }
+                }
+                if (layernorm_timed(e, a, st)) return -1;
+                if (linear(e, true, e->lnbuf.p, D, p + ".qkv.w", 3 * D, D, M, W32(p + ".qkv.b"), nullptr, 0, e->qkv.p, 3 * D, 1, ACT_NONE, st, PK_ENC_QKV)) return -1;
+                if (attention(e, true, e->qkv.p, e->attn.p, B, T, H, flens, st)) return -1;
+                if (linear(e, true, e->attn.p, D, p + ".out.w", D, D, M, W32(p + ".out.b"), xs, D, xs, D, 0, ACT_NONE, st, PK_ENC_OUT)) return -1;
+                LnArgs a2;
+                a2.in = xs; a2.out = e->lnbuf.p; a2.out_bf16 = 1; a2.w = W32(p + ".ln2.w"); a2.b = W32(p + ".ln2.b"); a2.rows = M; a2.C = D;
+                if (layernorm_timed(e, a2, st)) return -1;
+                if (linear(e, true, e->lnbuf.p, D, p + ".fc1.w", F, D, M, W32(p + ".fc1.b"), nullptr, 0, e->ffn.p, F, 1, ACT_GELU, st, PK_ENC_FC1)) return -1;
+                if (linear(e, true, e->ffn.p, F, p + ".fc2.w", D, F, M, W32(p + ".fc2.b"), xs, D, xs, D, 0, ACT_NONE, st, PK_ENC_FC2)) return -1;
+                continue;
+            }
             LnArgs a;
             a.out = e->lnbuf.p; a.out_bf16 = 1; a.w = W32(p + ".ln1.w"); a.b = W32(p + ".ln1.b"); a.rows = M; a.C = D;
             if (l == 0) a.in = e->X[0].p;
@@ -471,7 +507,8 @@ static int run_trunk(slsb_engine* e, const float* wav, const int* slens, int B, 
         }
         // 5. X_n = xmid + fc2_{n-1}; final LayerNorm on x only (wav2vec2.py:905-906); xc = x - b_dec feeds the SAE (model.py:70)
         LnArgs a;
-        if (res_in_gemm) a.in = e->X[c.n_layers].p;
+        if (inplace) { a.in = e->X[0].p; a.copy_out = e->snap[c.n_layers - 1].p; }
+        else if (res_in_gemm) a.in = e->X[c.n_layers].p;
         else { a.in = e->xmid.p; a.add = e->ybuf.p; a.sum_out = e->X[c.n_layers].as<float>(); }
         a.out = e->xfinal.p; a.w = W32("enc_ln.w"); a.b = W32("enc_ln.b"); a.rows = M; a.C = D;
         if (want_xc && c.sae_dict > 0) { a.out2 = e->xc.p; a.out2_bf16 = 1; a.sub = W32("sae.b_dec"); }
@@ -593,13 +630,18 @@ static int run_head(slsb_engine* e, int head, int prec, float* logprob, cudaStre
         }
         if (e->sls_w.reserve((size_t)B * c.n_layers * 4) || e->sls_in.reserve((size_t)B * Kp * 4) ||
             e->sls_part.reserve((size_t)B * KS * Hs * 4) || e->zeros.reserve((size_t)(KS > 1 ? KS : 1) * Hs * 4)) return -1;
-        std::vector<const float*> layers(c.n_layers);
-        for (int l = 0; l < c.n_layers; ++l) layers[l] = e->X[l + 1].as<float>();
+        std::vector<const void*> layers(c.n_layers);
+        std::vector<const float*> layers_f32(c.n_layers);
+        for (int l = 0; l < c.n_layers; ++l) {
+            layers[l] = e->inplace ? e->snap[l].p : e->X[l + 1].p;
+            layers_f32[l] = e->inplace ? nullptr : e->X[l + 1].as<float>();
+        }
         if (e->have_dots) LAUNCH(sls_layer_weights_from_dots(e->sls_dots.as<float>(), c.n_layers, B, T, W32("sls.fc0.b"), e->sls_w.as<float>(), st));
-        else LAUNCH(sls_layer_weights(layers.data(), c.n_layers, B, T, D, W32("sls.fc0.w"), W32("sls.fc0.b"), e->sls_w.as<float>(), nullptr, st));
+        else if (e->inplace) { set_error("SLS head: the in-place stream needs the fused fc0 dots"); return -1; }
+        else LAUNCH(sls_layer_weights(layers_f32.data(), c.n_layers, B, T, D, W32("sls.fc0.w"), W32("sls.fc0.b"), e->sls_w.as<float>(), nullptr, st));
         {   // every fp32 layer output is read once; the pooled [B, 67*341] matrix is written once
-            ProfScope ps(e, st, PK_SLS_POOL, (double)c.n_layers * M * D * 4 + (double)B * Kp * (bf ? 2 : 4));
-            LAUNCH(sls_fuse_pool(layers.data(), c.n_layers, e->sls_w.as<float>(), B, T, D, W32("sls.bn"), 1e-5f, e->sls_in.p, bf ? 1 : 0, Kp, st));
+            ProfScope ps(e, st, PK_SLS_POOL, (double)c.n_layers * M * D * (e->inplace ? 2 : 4) + (double)B * Kp * (bf ? 2 : 4));
+            LAUNCH(sls_fuse_pool(layers.data(), e->inplace ? 1 : 0, c.n_layers, e->sls_w.as<float>(), B, T, D, W32("sls.bn"), 1e-5f, e->sls_in.p, bf ? 1 : 0, Kp, st));
         }
         if (bf) {   // fc1 weight [1024, 22848] bf16 streamed once per batch; fp32 partials [B][KS][Hs]
             ProfScope ps(e, st, PK_SLS_FC1, (double)Hs * Kp * 2 + (double)B * Kp * 2 + (double)B * KS * Hs * 4);
@@ -668,6 +710,7 @@ int slsb_destroy(slsb_engine* e) {
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     for (auto& r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto& b : e->X) b.release();
+    for (auto& b : e->snap) b.release();
     delete e;
     return 0;
 }
@@ -737,8 +780,19 @@ int slsb_get_tensor(slsb_engine* e, const char* name, float* dst, int64_t numel,
     else if (n.rfind("layer_results.", 0) == 0) {
         const int i = atoi(n.c_str() + 14);
         if (i < 0 || i >= c.n_layers) { set_error("slsb_get_tensor: layer %d out of range", i); return -1; }
-        src = e->X[i + 1].p; want = M * c.embed_dim;
-    } else if (n == "pos_out") { src = e->X[0].p; want = M * c.embed_dim; }
+        want = M * c.embed_dim;
+        if (e->inplace) {      // bf16 snapshot of the layer result -> fp32
+            if (numel != want) { set_error("slsb_get_tensor: '%s' has %lld elements, caller gave %lld", name, (long long)want, (long long)numel); return -1; }
+            ++e->launches;
+            bf16_to_f32_kernel<<<(unsigned)((want + 255) / 256), 256, 0, st>>>(e->snap[i].as<bf16>(), dst, want);
+            SLSB_CUDA_CHECK(cudaGetLastError());
+            return 0;
+        }
+        src = e->X[i + 1].p;
+    } else if (n == "pos_out") {
+        if (e->inplace) { set_error("slsb_get_tensor: 'pos_out' is not retained by the in-place stream (SLSB_INPLACE=0 keeps it)"); return -1; }
+        src = e->X[0].p; want = M * c.embed_dim;
+    }
     else if (n == "acts") { if (!e->have_acts) { set_error("no SAE activations: last forward ran no SAE head"); return -1; } src = e->acts.p; want = M * c.sae_dict; }
     else if (n == "pooled") { src = e->pooled.p; want = (int64_t)e->B * c.cls_in; }
     else if (n == "sls_weights") { src = e->sls_w.p; want = (int64_t)e->B * c.n_layers; }

@@ -95,7 +95,7 @@ template <typename TI, typename TO, typename TO2, int NV, bool GELU, bool EXACT,
 __global__ void __launch_bounds__(256, 4) ln_kernel(const TI* __restrict__ in, const bf16* __restrict__ add, float* __restrict__ sum_out,
                                                  TO* __restrict__ out, TO2* __restrict__ out2,
                                                  const float* __restrict__ sub, const float* __restrict__ w, const float* __restrict__ b,
-                                                 const float* __restrict__ dot_w, float* __restrict__ dot_out,
+                                                 const float* __restrict__ dot_w, float* __restrict__ dot_out, bf16* __restrict__ copy_out,
                                                  long long rows, float eps) {
     constexpr int C = NV * 128;
     const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(256, 4) ln_kernel(const TI* __restrict__ in, c
             v[i][0] += y[0]; v[i][1] += y[1]; v[i][2] += y[2]; v[i][3] += y[3];
             if (sum_out) store4<float>(sum_out + row * C + (i * 32 + lane) * 4, v[i]);
         }
+        if (copy_out) store4<bf16>(copy_out + row * C + (i * 32 + lane) * 4, v[i]);     // bf16 snapshot of the (pre-norm) stream row
         if constexpr (DOT) {   // SLS layer weighting: fc0 . x_row of the (pre-norm) residual stream
             const float4 dw = __ldg(reinterpret_cast<const float4*>(dot_w + (i * 32 + lane) * 4));
             dot = fmaf(v[i][0], dw.x, dot); dot = fmaf(v[i][1], dw.y, dot); dot = fmaf(v[i][2], dw.z, dot); dot = fmaf(v[i][3], dw.w, dot);
@@ -161,12 +162,12 @@ int ln_launch(const LnArgs& a, cudaStream_t stream) {
     const bf16* add = static_cast<const bf16*>(a.add);
     if (a.gelu) {
         if (a.dot_out) { set_error("layernorm: dot_out is not combined with gelu"); return -1; }
-        if (a.exact_gelu) SLSB_CUDA_CHECK(launch_pdl(ln_kernel<TI, TO, TO2, NV, true, true, false>, dim3(grid), dim3(256), 0, stream, in, add, a.sum_out, out, out2, a.sub, a.w, a.b, a.dot_w, a.dot_out, a.rows, a.eps));
-        else SLSB_CUDA_CHECK(launch_pdl(ln_kernel<TI, TO, TO2, NV, true, false, false>, dim3(grid), dim3(256), 0, stream, in, add, a.sum_out, out, out2, a.sub, a.w, a.b, a.dot_w, a.dot_out, a.rows, a.eps));
+        if (a.exact_gelu) SLSB_CUDA_CHECK(launch_pdl(ln_kernel<TI, TO, TO2, NV, true, true, false>, dim3(grid), dim3(256), 0, stream, in, add, a.sum_out, out, out2, a.sub, a.w, a.b, a.dot_w, a.dot_out, static_cast<bf16*>(a.copy_out), a.rows, a.eps));
+        else SLSB_CUDA_CHECK(launch_pdl(ln_kernel<TI, TO, TO2, NV, true, false, false>, dim3(grid), dim3(256), 0, stream, in, add, a.sum_out, out, out2, a.sub, a.w, a.b, a.dot_w, a.dot_out, static_cast<bf16*>(a.copy_out), a.rows, a.eps));
     } else if (a.dot_out) {
-        SLSB_CUDA_CHECK(launch_pdl(ln_kernel<TI, TO, TO2, NV, false, true, true>, dim3(grid), dim3(256), 0, stream, in, add, a.sum_out, out, out2, a.sub, a.w, a.b, a.dot_w, a.dot_out, a.rows, a.eps));
+        SLSB_CUDA_CHECK(launch_pdl(ln_kernel<TI, TO, TO2, NV, false, true, true>, dim3(grid), dim3(256), 0, stream, in, add, a.sum_out, out, out2, a.sub, a.w, a.b, a.dot_w, a.dot_out, static_cast<bf16*>(a.copy_out), a.rows, a.eps));
     } else {
-        SLSB_CUDA_CHECK(launch_pdl(ln_kernel<TI, TO, TO2, NV, false, true, false>, dim3(grid), dim3(256), 0, stream, in, add, a.sum_out, out, out2, a.sub, a.w, a.b, a.dot_w, a.dot_out, a.rows, a.eps));
+        SLSB_CUDA_CHECK(launch_pdl(ln_kernel<TI, TO, TO2, NV, false, true, false>, dim3(grid), dim3(256), 0, stream, in, add, a.sum_out, out, out2, a.sub, a.w, a.b, a.dot_w, a.dot_out, static_cast<bf16*>(a.copy_out), a.rows, a.eps));
     }
     SLSB_CUDA_CHECK(cudaGetLastError());
     return 0;

@@ -63,6 +63,7 @@ struct DevParams {
     int act, out_bf16;
     int kb_per_split;  // A_PLAIN split-K: batch index b selects k-blocks [b * kb_per_split, ...) and partial-output slab b (0 = off)
     int tma_store;     // bf16 output leaves through smem staging + cp.async.bulk.tensor stores
+    int red_add;       // fp32 output aliases the fp32 residual: out += acc + bias through TMA reduce-add stores (no residual loads)
     int res_tma;       // fp32 output = acc + bias + fp32 residual, residual tile fetched by TMA into the staging tile, summed in place, TMA-stored
     int debug_flags;   // bit0: epilogue does everything except the global stores / residual loads (mainloop ceiling measurements)
 };
@@ -250,6 +251,48 @@ __device__ __forceinline__ void epilogue_tile_pos4(const DevParams& p, uint32_t 
     }
 }
 
+// In-place residual stream: out[tile] += acc + bias with cp.reduce.async.bulk.tensor (fp32 add performed at the L2): store-only
+// epilogue, 32 fp32 columns (one 16 KB SWIZZLE_128B staging tile) at a time.  Used when the caller passes residual == out
+// (x += branch(x), wav2vec2.py:1053 / :1058 with the stream updated in place).
+template <int kCols>
+__device__ __forceinline__ void epilogue_tile_red_tma(const CUtensorMap* tmap_out, uint32_t taddr, uint8_t* stage_tile, const float* bias_s,
+                                                      int half, int r, int col_base, int row0, uint64_t* full_bar, uint32_t full_parity,
+                                                      uint32_t empty_bar_addr, int dbg) {
+    constexpr int kChunks = kCols / 32;
+    const int bar_id = 1 + half;
+    const bool issuer = r == 0;
+    mbar_wait(full_bar, full_parity);
+    tc_fence_after();
+    uint8_t* srow = stage_tile + r * 128;
+#pragma unroll 1
+    for (int c = 0; c < kChunks; ++c) {
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(taddr + c * 32, acc);
+        if (issuer) tma_store_wait_read<0>();                        // the previous reduce-store no longer reads the staging tile
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // (also publishes this tile's bias slice on the first pass)
+        tmem_ld_wait();
+        if (c == kChunks - 1) {                                      // accumulator fully read: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if ((r & 31) == 0) mbar_arrive_cluster(empty_bar_addr);
+        }
+        const float* bs = bias_s + half * kCols + c * 32;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 bb = *reinterpret_cast<const float4*>(bs + 4 * j);
+            *reinterpret_cast<float4*>(srow + ((j ^ (r & 7)) << 4)) =
+                make_float4(__uint_as_float(acc[4 * j + 0]) + bb.x, __uint_as_float(acc[4 * j + 1]) + bb.y,
+                            __uint_as_float(acc[4 * j + 2]) + bb.z, __uint_as_float(acc[4 * j + 3]) + bb.w);
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (issuer && !(dbg & 4)) {
+            tma_reduce_add_2d(tmap_out, stage_tile, col_base + c * 32, row0);
+            tma_store_commit();
+        }
+    }
+}
+
 // fp32 residual stream through the GEMM epilogue without touching the LSU's global path: per 32-column chunk the issuer
 // TMA-loads the residual tile [128 rows x 32 fp32] into the half's staging tile, every thread adds its accumulator row + bias
 // IN PLACE (own row, SWIZZLE_128B chunk positions), and the same tile is TMA-stored as the new residual stream.
@@ -342,7 +385,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
-        if (p.tma_store || p.res_tma) tma_prefetch_desc(&tmap_out);
+        if (p.tma_store || p.res_tma || p.red_add) tma_prefetch_desc(&tmap_out);
         if (p.res_tma) tma_prefetch_desc(&tmap_res);
     }
     if (warp == 1 && lane == 0) {
@@ -462,6 +505,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 continue;
             }
             if constexpr (BLOCK_N == 256 && A_MODE == A_PLAIN) {
+                if (p.red_add) {
+                    bias_s[half * kColsPerWarp + r] = __ldg(p.bias + col_base + r);       // visible after the first named barrier
+                    uint8_t* stage_tile = smem + Plan::kStoreOffset + half * 16384;
+                    epilogue_tile_red_tma<kColsPerWarp>(&tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, m_blk * BLOCK_M,
+                                                        &tmem_full[acc], acc_phase, smem_u32(&tmem_empty[acc]), p.debug_flags);
+                    continue;
+                }
                 if (p.res_tma) {
                     bias_s[half * kColsPerWarp + r] = __ldg(p.bias + col_base + r);       // visible after the first named barrier
                     uint8_t* stage_tile = smem + Plan::kStoreOffset + half * 16384;
@@ -503,7 +553,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
-        if ((p.tma_store || p.res_tma) && r == 0) tma_store_wait<0>();
+        if ((p.tma_store || p.res_tma || p.red_add) && r == 0) tma_store_wait<0>();
     }
 
     tc_fence_before();
@@ -598,7 +648,7 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
-        if (p.tma_store || p.res_tma) tma_prefetch_desc(&tmap_out);
+        if (p.tma_store || p.res_tma || p.red_add) tma_prefetch_desc(&tmap_out);
         if (p.res_tma) tma_prefetch_desc(&tmap_res);
     }
     if (warp == 1 && lane == 0) {
@@ -681,7 +731,10 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint32_t free_bar = map_cluster(smem_u32(&tmem_empty[acc]), 0);
             bias_s[half * kColsPerWarp + r] = __ldg(p.bias + col_base + r);       // visible after the first named barrier of the tile
             uint8_t* stage_tile = smem + Plan2::kStoreOffset + half * 16384;
-            if (p.res_tma) {
+            if (p.red_add) {
+                epilogue_tile_red_tma<kColsPerWarp>(&tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, row0, &tmem_full[acc], acc_phase, free_bar,
+                                                    p.debug_flags);
+            } else if (p.res_tma) {
                 epilogue_tile_res_tma<kColsPerWarp>(&tmap_res, &tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, row0,
                                                     &tmem_full[acc], acc_phase, free_bar, &res_bar[half], res_phase, p.debug_flags);
             } else if (p.act == ACT_GELU) {
@@ -798,6 +851,15 @@ int tc_gemm(const TcGemmArgs& g, int num_sms, cudaStream_t stream) {
     // fp32 output with an fp32 residual of full-width tiles: residual in / sum out through TMA (epilogue_tile_res_tma)
     dp.res_tma = (!g.out_bf16 && g.residual != nullptr && g.act == ACT_NONE && block_n == 256 && g.a_mode == A_PLAIN && g.k_splits <= 1 &&
                   g.ldc % 4 == 0 && g.ldr % 4 == 0 && !getenv("SLSB_NO_RES_TMA")) ? 1 : 0;
+    // residual == out: the stream is advanced in place by reduce-add stores, no residual tile is loaded at all
+    dp.red_add = (dp.res_tma && static_cast<const void*>(g.residual) == g.out && g.ldr == g.ldc && !getenv("SLSB_NO_RED_ADD")) ? 1 : 0;
+    if (dp.red_add) dp.res_tma = 0;
+    if (dp.red_add) {
+        uint64_t dims[2] = {(uint64_t)g.N, (uint64_t)g.M};
+        uint32_t box[2] = {32, BLOCK_M};
+        uint64_t so[1] = {(uint64_t)g.ldc * 4};
+        if (encode_tmap_f32(&to, g.out, 2, dims, so, box)) return -1;
+    }
     if (dp.res_tma) {
         uint64_t dims[2] = {(uint64_t)g.N, (uint64_t)g.M};
         uint32_t box[2] = {32, BLOCK_M};
@@ -862,7 +924,7 @@ int tc_gemm(const TcGemmArgs& g, int num_sms, cudaStream_t stream) {
     if (g.a_mode == A_PLAIN) {
         static int use_pair = -1;
         if (use_pair < 0) { const char* v = getenv("SLSB_GEMM_PAIR"); use_pair = v ? atoi(v) : 1; }
-        if (block_n == 256 && use_pair && (dp.tma_store || dp.res_tma) && dp.kb_per_split == 0 && g.M >= 256) {
+        if (block_n == 256 && use_pair && (dp.tma_store || dp.res_tma || dp.red_add) && dp.kb_per_split == 0 && g.M >= 256) {
             // CTA-pair kernel: the W map's box is this CTA's 128 of the tile's 256 rows
             uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.N};
             uint64_t strides[1] = {(uint64_t)g.ldw * 2};

@@ -250,7 +250,7 @@ __global__ void classifier_out_kernel(const float* __restrict__ hidden, int Hd, 
 }
 
 // ---- SLS
-struct LayerPtrs { const float* p[32]; };
+struct LayerPtrs { const void* p[32]; };
 
 // grid (n_layers, B), 256 threads x 4 channels: layer mean over frames, dot with fc0, sigmoid
 __global__ void __launch_bounds__(256) sls_weights_kernel(LayerPtrs L, int T, int D, const float* __restrict__ fc0_w, const float* __restrict__ fc0_b,
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(256) sls_weights_kernel(LayerPtrs L, int T, in
     __shared__ float red[8];
     const int l = blockIdx.x, b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int len = lens ? min(lens[b], T) : T;
-    const float* x = L.p[l] + (long long)b * T * D;
+    const float* x = static_cast<const float*>(L.p[l]) + (long long)b * T * D;
     float dot = 0.f;
     for (int c = threadIdx.x * 4; c < D; c += 1024) {
         float4 s = make_float4(0, 0, 0, 0);
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(32) sls_weights_from_dots_kernel(const float* 
 
 // grid (T/3, B), D/4 threads x 4 channels: weighted layer sum for 3 frames (12 independent 16-byte loads in flight per
 // layer group), BN (eval affine) + SELU, then 3x3 max pool -> out[b][i*(D/3)+j].  Every layer output is read exactly once.
-template <typename TO>
+template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) sls_fuse_pool_kernel(LayerPtrs L, int n_layers, const float* __restrict__ layer_w, int T, int D,
                                                             const float* __restrict__ bn, float bn_eps, TO* __restrict__ out, int ldo) {
     extern __shared__ float fp_smem[];   // [3][D]
@@ -316,10 +316,17 @@ __global__ void __launch_bounds__(256) sls_fuse_pool_kernel(LayerPtrs L, int n_l
 #pragma unroll 4
         for (int l = 0; l < n_layers; ++l) {
             const float w = lw[l];
-            const float* base = L.p[l] + off;
+            const TI* base = static_cast<const TI*>(L.p[l]) + off;
 #pragma unroll
             for (int di = 0; di < 3; ++di) {
-                const float4 v = __ldcs(reinterpret_cast<const float4*>(base + (long long)di * D));
+                float4 v;
+                if constexpr (sizeof(TI) == 2) {
+                    const uint2 t = __ldcs(reinterpret_cast<const uint2*>(base + (long long)di * D));
+                    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&t.x), bq = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+                    v = make_float4(__low2float(a), __high2float(a), __low2float(bq), __high2float(bq));
+                } else {
+                    v = __ldcs(reinterpret_cast<const float4*>(base + (long long)di * D));
+                }
                 s[di].x = fmaf(v.x, w, s[di].x); s[di].y = fmaf(v.y, w, s[di].y);
                 s[di].z = fmaf(v.z, w, s[di].z); s[di].w = fmaf(v.w, w, s[di].w);
             }
@@ -476,15 +483,17 @@ int sls_layer_weights_from_dots(const float* dots, int n_layers, int B, int T, c
     SLSB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
-int sls_fuse_pool(const float* const* layers, int n_layers, const float* layer_w, int B, int T, int D, const float* bn, float bn_eps,
+int sls_fuse_pool(const void* const* layers, int layers_bf16, int n_layers, const float* layer_w, int B, int T, int D, const float* bn, float bn_eps,
                   void* out, int out_bf16, int ldo, cudaStream_t stream) {
     if (n_layers > 32 || D > 1024) { set_error("sls_fuse_pool: n_layers<=32, D<=1024"); return -1; }
     LayerPtrs L{};
     for (int i = 0; i < n_layers; ++i) L.p[i] = layers[i];
     if (D % 4 != 0) { set_error("sls_fuse_pool: D must be a multiple of 4"); return -1; }
     dim3 grid(T / 3, B);
-    if (out_bf16) sls_fuse_pool_kernel<bf16><<<grid, 256, 3 * D * sizeof(float), stream>>>(L, n_layers, layer_w, T, D, bn, bn_eps, static_cast<bf16*>(out), ldo);
-    else sls_fuse_pool_kernel<float><<<grid, 256, 3 * D * sizeof(float), stream>>>(L, n_layers, layer_w, T, D, bn, bn_eps, static_cast<float*>(out), ldo);
+    if (layers_bf16 && out_bf16) sls_fuse_pool_kernel<bf16, bf16><<<grid, 256, 3 * D * sizeof(float), stream>>>(L, n_layers, layer_w, T, D, bn, bn_eps, static_cast<bf16*>(out), ldo);
+    else if (layers_bf16) sls_fuse_pool_kernel<bf16, float><<<grid, 256, 3 * D * sizeof(float), stream>>>(L, n_layers, layer_w, T, D, bn, bn_eps, static_cast<float*>(out), ldo);
+    else if (out_bf16) sls_fuse_pool_kernel<float, bf16><<<grid, 256, 3 * D * sizeof(float), stream>>>(L, n_layers, layer_w, T, D, bn, bn_eps, static_cast<bf16*>(out), ldo);
+    else sls_fuse_pool_kernel<float, float><<<grid, 256, 3 * D * sizeof(float), stream>>>(L, n_layers, layer_w, T, D, bn, bn_eps, static_cast<float*>(out), ldo);
     SLSB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -77,6 +77,7 @@ struct LnArgs {
     void* out2 = nullptr; int out2_bf16 = 0; const float* sub = nullptr;   // out2 = y - sub
     const float* w = nullptr; const float* b = nullptr;
     const float* dot_w = nullptr; float* dot_out = nullptr;   // optional: dot_out[row] = sum_c (in + add)[row, c] * dot_w[c]
+    void* copy_out = nullptr;                                 // optional: bf16 copy of the (in + add) rows (layer-result snapshot)
     long long rows = 0; int C = 0; int gelu = 0; int exact_gelu = 1; float eps = 1e-5f;
 };
 int layernorm(const LnArgs& a, cudaStream_t stream);
@@ -129,7 +130,7 @@ int sls_layer_weights(const float* const* layers, int n_layers, int B, int T, in
                       float* layer_w /*[B, n_layers]*/, const int* lens, cudaStream_t stream);
 // same weights from dots[l][b*T + t] = fc0_w . x_l[b, t, :] (emitted by the LayerNorm kernels, LnArgs::dot_out)
 int sls_layer_weights_from_dots(const float* dots, int n_layers, int B, int T, const float* fc0_b, float* layer_w, cudaStream_t stream);
-int sls_fuse_pool(const float* const* layers, int n_layers, const float* layer_w, int B, int T, int D, const float* bn /*w,b,rm,rv*/,
+int sls_fuse_pool(const void* const* layers, int layers_bf16, int n_layers, const float* layer_w, int B, int T, int D, const float* bn /*w,b,rm,rv*/,
                   float bn_eps, void* out /*[B, (T/3)*(D/3) zero-padded to ldo], fp32 or bf16*/, int out_bf16, int ldo, cudaStream_t stream);
 // fc1 split-K partials [B][KS][Hd] -> selu(sum + b1) -> fc3 -> selu -> log_softmax
 int sls_tail(const float* partial, int KS, int B, int Hd, const float* b1, const float* w3, const float* b3, float* logprob, cudaStream_t stream);

@@ -66,6 +66,22 @@ def test_gemm_bf16_tc_epilogues(lib, cuda, act, out_bf16, res):
     report(f"gemm_tc epi act={act} bf16={out_bf16} res={res}", out, ref, atol=2e-3 if out_bf16 else 2e-4, rtol=8e-3 if out_bf16 else 1e-4)
 
 
+@pytest.mark.parametrize("M,N,K", [(1000, 1024, 512), (12864, 1024, 1024), (201, 1024, 4096), (300, 256, 64)])
+def test_gemm_bf16_tc_in_place_residual(lib, cuda, M, N, K):
+    """residual == out: the fp32 stream is advanced in place (TMA reduce-add epilogue); bit-stable, equals out-of-place."""
+    A, W, b = _rand((M, K), 14).bfloat16(), _rand((N, K), 15, 0.05).bfloat16(), _rand((N,), 16)
+    R = _rand((M, N), 17)
+    inplace = R.clone()
+    ok(lib, lib.slsb_op_gemm(BF16, P(A), P(W), P(b), P(inplace), P(inplace), M, N, K, ACT_NONE, 0, stream()), "gemm tc in place")
+    report(f"gemm_tc in-place {M}x{N}x{K}", inplace, A.float() @ W.float().T + b + R, atol=2e-4 * (K / 512) ** 0.5, rtol=1e-4)
+    separate = torch.empty_like(R)
+    ok(lib, lib.slsb_op_gemm(BF16, P(A), P(W), P(b), P(R), P(separate), M, N, K, ACT_NONE, 0, stream()), "gemm tc out of place")
+    assert torch.equal(inplace, separate)                      # same association: (acc + bias) + residual
+    again = R.clone()
+    ok(lib, lib.slsb_op_gemm(BF16, P(A), P(W), P(b), P(again), P(again), M, N, K, ACT_NONE, 0, stream()), "gemm tc in place")
+    assert torch.equal(inplace, again)
+
+
 def test_gemm_bf16_tc_deterministic(lib, cuda):
     M, N, K = 2000, 1024, 1024
     A, W, b = _rand((M, K), 9).bfloat16(), _rand((N, K), 10, 0.05).bfloat16(), _rand((N,), 11)
