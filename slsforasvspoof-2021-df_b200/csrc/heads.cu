@@ -302,42 +302,47 @@ __global__ void __launch_bounds__(32) sls_weights_from_dots_kernel(const float* 
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) sls_fuse_pool_kernel(LayerPtrs L, int n_layers, const float* __restrict__ layer_w, int T, int D,
                                                             const float* __restrict__ bn, float bn_eps, TO* __restrict__ out, int ldo) {
+    // grid (T/3, B); every thread owns VEC = 16 bytes / sizeof(TI) consecutive channels of the block's 3 frames (16-byte loads):
+    // weighted layer sum, BN (eval affine) + SELU into smem, then the 3x3 max pool -> out[b][i*(D/3)+j].  Each layer is read once.
+    constexpr int VEC = 16 / (int)sizeof(TI);
     extern __shared__ float fp_smem[];   // [3][D]
     __shared__ float lw[32];
-    const int i = blockIdx.x, b = blockIdx.y, c = threadIdx.x * 4;
+    const int i = blockIdx.x, b = blockIdx.y, c = threadIdx.x * VEC;
     if (threadIdx.x < n_layers) lw[threadIdx.x] = layer_w[b * n_layers + threadIdx.x];
     __syncthreads();
     const float g = bn[0] / sqrtf(bn[3] + bn_eps), beta = bn[1], rm = bn[2];
     if (c < D) {
         const long long off = ((long long)b * T + 3 * i) * D + c;
-        float4 s[3];
+        float s[3][VEC];
 #pragma unroll
-        for (int di = 0; di < 3; ++di) s[di] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int di = 0; di < 3; ++di)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) s[di][e] = 0.f;
 #pragma unroll 4
         for (int l = 0; l < n_layers; ++l) {
             const float w = lw[l];
             const TI* base = static_cast<const TI*>(L.p[l]) + off;
 #pragma unroll
             for (int di = 0; di < 3; ++di) {
-                float4 v;
+                const uint4 t = __ldcs(reinterpret_cast<const uint4*>(base + (long long)di * D));
                 if constexpr (sizeof(TI) == 2) {
-                    const uint2 t = __ldcs(reinterpret_cast<const uint2*>(base + (long long)di * D));
-                    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&t.x), bq = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
-                    v = make_float4(__low2float(a), __high2float(a), __low2float(bq), __high2float(bq));
+                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        s[di][2 * e] = fmaf(__low2float(h[e]), w, s[di][2 * e]);
+                        s[di][2 * e + 1] = fmaf(__high2float(h[e]), w, s[di][2 * e + 1]);
+                    }
                 } else {
-                    v = __ldcs(reinterpret_cast<const float4*>(base + (long long)di * D));
+                    const float* f = reinterpret_cast<const float*>(&t);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) s[di][e] = fmaf(f[e], w, s[di][e]);
                 }
-                s[di].x = fmaf(v.x, w, s[di].x); s[di].y = fmaf(v.y, w, s[di].y);
-                s[di].z = fmaf(v.z, w, s[di].z); s[di].w = fmaf(v.w, w, s[di].w);
             }
         }
 #pragma unroll
-        for (int di = 0; di < 3; ++di) {
-            float4 o;
-            o.x = selu((s[di].x - rm) * g + beta); o.y = selu((s[di].y - rm) * g + beta);
-            o.z = selu((s[di].z - rm) * g + beta); o.w = selu((s[di].w - rm) * g + beta);
-            *reinterpret_cast<float4*>(fp_smem + di * D + c) = o;
-        }
+        for (int di = 0; di < 3; ++di)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) fp_smem[di * D + c + e] = selu((s[di][e] - rm) * g + beta);
     }
     __syncthreads();
     const int J = D / 3;
@@ -488,10 +493,11 @@ int sls_fuse_pool(const void* const* layers, int layers_bf16, int n_layers, cons
     if (n_layers > 32 || D > 1024) { set_error("sls_fuse_pool: n_layers<=32, D<=1024"); return -1; }
     LayerPtrs L{};
     for (int i = 0; i < n_layers; ++i) L.p[i] = layers[i];
-    if (D % 4 != 0) { set_error("sls_fuse_pool: D must be a multiple of 4"); return -1; }
+    if (D % 8 != 0) { set_error("sls_fuse_pool: D must be a multiple of 8"); return -1; }
     dim3 grid(T / 3, B);
-    if (layers_bf16 && out_bf16) sls_fuse_pool_kernel<bf16, bf16><<<grid, 256, 3 * D * sizeof(float), stream>>>(L, n_layers, layer_w, T, D, bn, bn_eps, static_cast<bf16*>(out), ldo);
-    else if (layers_bf16) sls_fuse_pool_kernel<bf16, float><<<grid, 256, 3 * D * sizeof(float), stream>>>(L, n_layers, layer_w, T, D, bn, bn_eps, static_cast<float*>(out), ldo);
+    const int nt_b = D / 8 > 32 ? D / 8 : 32;       // bf16 layers: 8 channels per thread
+    if (layers_bf16 && out_bf16) sls_fuse_pool_kernel<bf16, bf16><<<grid, nt_b, 3 * D * sizeof(float), stream>>>(L, n_layers, layer_w, T, D, bn, bn_eps, static_cast<bf16*>(out), ldo);
+    else if (layers_bf16) sls_fuse_pool_kernel<bf16, float><<<grid, nt_b, 3 * D * sizeof(float), stream>>>(L, n_layers, layer_w, T, D, bn, bn_eps, static_cast<float*>(out), ldo);
     else if (out_bf16) sls_fuse_pool_kernel<float, bf16><<<grid, 256, 3 * D * sizeof(float), stream>>>(L, n_layers, layer_w, T, D, bn, bn_eps, static_cast<bf16*>(out), ldo);
     else sls_fuse_pool_kernel<float, float><<<grid, 256, 3 * D * sizeof(float), stream>>>(L, n_layers, layer_w, T, D, bn, bn_eps, static_cast<float*>(out), ldo);
     SLSB_CUDA_CHECK(cudaGetLastError());
