@@ -65,6 +65,7 @@ struct DevParams {
     int tma_store;     // bf16 output leaves through smem staging + cp.async.bulk.tensor stores
     int red_add;       // fp32 output aliases the fp32 residual: out += acc + bias through TMA reduce-add stores (no residual loads)
     int res_tma;       // fp32 output = acc + bias + fp32 residual, residual tile fetched by TMA into the staging tile, summed in place, TMA-stored
+    int tail_split;    // pair kernel: tiles of the partial last round are cut into this many column slices (1, 2 or 4)
     int debug_flags;   // bit0: epilogue does everything except the global stores / residual loads (mainloop ceiling measurements)
 };
 
@@ -152,12 +153,19 @@ __device__ __forceinline__ void epilogue_tile(const DevParams& p, uint32_t taddr
 template <int ACT, int kCols, bool kConvOut>
 __device__ __forceinline__ void epilogue_tile_tma(const DevParams& p, const CUtensorMap* tmap_out, uint32_t taddr, uint8_t* stage_tile,
                                                   const float* bias_s, int half, int r, int col_base, int row0, int b,
-                                                  uint64_t* full_bar, uint32_t full_parity, uint32_t empty_bar_addr) {
-    constexpr int kGroups = kCols / 64;
+                                                  uint64_t* full_bar, uint32_t full_parity, uint32_t empty_bar_addr,
+                                                  int kGroups = kCols / 64) {
+    // kGroups < kCols / 64: a column slice of a tile (pair kernel tail); 0 = this half has no columns, it only releases the accumulator
     const int bar_id = 1 + half;
     const bool issuer = r == 0;
     mbar_wait(full_bar, full_parity);
     tc_fence_after();
+    if (kGroups == 0) {
+        tc_fence_before();
+        __syncwarp();
+        if ((r & 31) == 0) mbar_arrive_cluster(empty_bar_addr);
+        return;
+    }
 #pragma unroll 1
     for (int g = 0; g < kGroups; ++g) {
         uint32_t acc[2][32];
@@ -615,11 +623,28 @@ __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 
-// Static tile schedule of the pair kernel: round i hands tile i * P + p to pair p in even rounds and to pair P - 1 - p in odd
-// rounds (snake order).  Tiles are ordered n-fastest with the ragged last row block (M % 256 rows, cheaper) at the end, so the few
-// tiles of a partial last round land on pairs whose previous tile was a cheap one (fc1, M = 12864: 12 -> 11.25 rounds).
-__device__ __forceinline__ int pair_tile(int it, int pair, int num_pairs) {
-    return it * num_pairs + ((it & 1) ? (num_pairs - 1 - pair) : pair);
+// Static schedule of the pair kernel.  Tiles are ordered n-fastest with the ragged last row block (M % 256 rows, cheaper) at the
+// end.  The floor(tiles / P) full rounds hand tile i * P + p to pair p in even rounds and to pair P - 1 - p in odd rounds (snake
+// order).  The tiles left for a partial last round are cut into `split` column slices of 256 / split columns (one MMA of that N,
+// same K order, so every output element is computed exactly as in a whole tile) and dealt round-robin, so the last round costs
+// ceil(rem * split / P) / split of a round instead of a whole one (qkv, M = 12864: 9 -> 8.5 rounds; fc1: 12 -> 11.25).
+struct PairItem { int m2, n0, width; };
+__device__ __forceinline__ bool pair_item(int it, int pair, int num_pairs, int num_tiles, int n_tiles, int split, PairItem& w) {
+    const int full_rounds = num_tiles / num_pairs;
+    int tile, sub = 0;
+    w.width = 256;
+    if (it < full_rounds) {
+        tile = it * num_pairs + ((it & 1) ? (num_pairs - 1 - pair) : pair);
+    } else {
+        const int j = (it - full_rounds) * num_pairs + pair;
+        if (j >= (num_tiles - full_rounds * num_pairs) * split) return false;
+        tile = full_rounds * num_pairs + j / split;
+        sub = j % split;
+        w.width = 256 / split;
+    }
+    w.m2 = tile / n_tiles;
+    w.n0 = (tile % n_tiles) * 256 + sub * w.width;
+    return true;
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
@@ -643,6 +668,7 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int m2_tiles = (p.M + 255) / 256;
     const int num_tiles = m2_tiles * p.n_tiles;
     const int num_kb = p.K / BLOCK_K;
+    const int split = p.tail_split;
 
     griddep_launch();
     if (warp == 0 && lane == 0) {
@@ -671,11 +697,10 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // ===================== TMA producer (both CTAs; completion on the leader's barrier) =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int it = 0;; ++it) {
-                const int tile = pair_tile(it, pair, num_pairs);
-                if (tile >= num_tiles) break;
-                const int n_blk = tile % p.n_tiles, m2 = tile / p.n_tiles;
-                const int row0 = m2 * 256 + (int)rank * 128;
+            PairItem w;
+            for (int it = 0; pair_item(it, pair, num_pairs, num_tiles, p.n_tiles, split, w); ++it) {
+                const int row0 = w.m2 * 256 + (int)rank * 128;
+                const int wrow0 = w.n0 + (int)rank * (w.width >> 1);       // this CTA's half of the slice's W rows (box: 128 rows)
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Plan2::kStage;
@@ -683,7 +708,7 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Plan2::kStage);
                     const uint32_t bar = map_cluster(smem_u32(&full_bar[stage]), 0);
                     tma_load_2d_pair(sa, &tmap_a, bar, kb * BLOCK_K, row0);
-                    tma_load_2d_pair(sb, &tmap_b, bar, kb * BLOCK_K, n_blk * BLOCK_N + (int)rank * 128);
+                    tma_load_2d_pair(sb, &tmap_b, bar, kb * BLOCK_K, wrow0);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -691,9 +716,10 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread of the leader CTA) =====================
         if (lane == 0 && rank == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N);
             int stage = 0; uint32_t phase = 0;
-            for (int it = 0; pair_tile(it, pair, num_pairs) < num_tiles; ++it) {
+            PairItem w;
+            for (int it = 0; pair_item(it, pair, num_pairs, num_tiles, p.n_tiles, split, w); ++it) {
+                const uint32_t idesc = w.width == 256 ? make_idesc_bf16(256, 256) : w.width == 128 ? make_idesc_bf16(256, 128) : make_idesc_bf16(256, 64);
                 const int acc = it & 1;
                 mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -719,17 +745,18 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         constexpr int kColsPerWarp = BLOCK_N / 2;
         const int r = q * 32 + lane;
         uint32_t res_phase = 0;
-        for (int it = 0;; ++it) {
-            const int tile = pair_tile(it, pair, num_pairs);
-            if (tile >= num_tiles) break;
-            const int n_blk = tile % p.n_tiles, m2 = tile / p.n_tiles;
-            const int row0 = m2 * 256 + (int)rank * 128;
+        PairItem w;
+        for (int it = 0; pair_item(it, pair, num_pairs, num_tiles, p.n_tiles, split, w); ++it) {
+            const int row0 = w.m2 * 256 + (int)rank * 128;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const uint32_t taddr0 = tmem_base + (uint32_t(q * 32) << 16) + acc * BLOCK_N + half * kColsPerWarp;
-            const int col_base = n_blk * BLOCK_N + half * kColsPerWarp;
+            // this half-warpgroup's columns of the slice: 2 / 1 groups of 64 columns; a 64-column slice belongs to half 0 alone
+            const int groups = w.width == 256 ? 2 : (w.width == 128 || half == 0) ? 1 : 0;
+            const int col_off = w.width == 64 ? 0 : half * (w.width >> 1);
+            const uint32_t taddr0 = tmem_base + (uint32_t(q * 32) << 16) + acc * BLOCK_N + col_off;
+            const int col_base = w.n0 + col_off;
             const uint32_t free_bar = map_cluster(smem_u32(&tmem_empty[acc]), 0);
-            bias_s[half * kColsPerWarp + r] = __ldg(p.bias + col_base + r);       // visible after the first named barrier of the tile
+            if (r < groups * 64) bias_s[half * kColsPerWarp + r] = __ldg(p.bias + col_base + r);   // visible after the first named barrier of the tile
             uint8_t* stage_tile = smem + Plan2::kStoreOffset + half * 16384;
             if (p.red_add) {
                 epilogue_tile_red_tma<kColsPerWarp>(&tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, row0, &tmem_full[acc], acc_phase, free_bar,
@@ -738,11 +765,11 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 epilogue_tile_res_tma<kColsPerWarp>(&tmap_res, &tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, row0,
                                                     &tmem_full[acc], acc_phase, free_bar, &res_bar[half], res_phase, p.debug_flags);
             } else if (p.act == ACT_GELU) {
-                epilogue_tile_tma<ACT_GELU, kColsPerWarp, false>(p, &tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, row0, 0, &tmem_full[acc], acc_phase, free_bar);
+                epilogue_tile_tma<ACT_GELU, kColsPerWarp, false>(p, &tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, row0, 0, &tmem_full[acc], acc_phase, free_bar, groups);
             } else if (p.act == ACT_RELU) {
-                epilogue_tile_tma<ACT_RELU, kColsPerWarp, false>(p, &tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, row0, 0, &tmem_full[acc], acc_phase, free_bar);
+                epilogue_tile_tma<ACT_RELU, kColsPerWarp, false>(p, &tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, row0, 0, &tmem_full[acc], acc_phase, free_bar, groups);
             } else {
-                epilogue_tile_tma<ACT_NONE, kColsPerWarp, false>(p, &tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, row0, 0, &tmem_full[acc], acc_phase, free_bar);
+                epilogue_tile_tma<ACT_NONE, kColsPerWarp, false>(p, &tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, row0, 0, &tmem_full[acc], acc_phase, free_bar, groups);
             }
         }
         if (r == 0) tma_store_wait<0>();
@@ -771,7 +798,18 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     }
     const int tiles = ((dp.M + 255) / 256) * dp.n_tiles;
     const int pairs = tiles < max_pairs ? tiles : max_pairs;
-    SLSB_CUDA_CHECK(launch_pdl(tc_gemm_pair_kernel, dim3(2 * pairs), dim3(kNumThreads), Plan2::kBytes, stream, ta, tb, to, tr, dp));
+    DevParams q = dp;
+    q.tail_split = 1;
+    static const bool tail_on = !(getenv("SLSB_NO_TAIL_SPLIT") && atoi(getenv("SLSB_NO_TAIL_SPLIT")) != 0);
+    const int rem = tiles % pairs;
+    if (tail_on && rem != 0 && dp.tma_store && !dp.red_add && !dp.res_tma) {       // bf16 TMA-store epilogue handles column slices
+        int best_num = 1, best_den = 1;                                            // cost of the last round = ceil(rem * s / P) / s
+        for (int s = 2; s <= 4; s *= 2) {
+            const int num = (rem * s + pairs - 1) / pairs;
+            if (num * best_den < best_num * s) { best_num = num; best_den = s; q.tail_split = s; }
+        }
+    }
+    SLSB_CUDA_CHECK(launch_pdl(tc_gemm_pair_kernel, dim3(2 * pairs), dim3(kNumThreads), Plan2::kBytes, stream, ta, tb, to, tr, q));
     return 0;
 }
 

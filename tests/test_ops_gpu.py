@@ -82,6 +82,22 @@ def test_gemm_bf16_tc_in_place_residual(lib, cuda, M, N, K):
     assert torch.equal(inplace, again)
 
 
+@pytest.mark.parametrize("M,N,K,act", [(4864, 1024, 512, ACT_NONE), (6221, 1024, 256, ACT_GELU), (12864, 3072, 256, ACT_NONE),
+                                       (12864, 4096, 128, ACT_GELU), (9000, 768 + 256, 192, ACT_RELU)])
+def test_gemm_bf16_tc_tail_slices(lib, cuda, M, N, K, act):
+    """Tile counts that leave a partial last round on 74 CTA pairs: its tiles are cut into 128/64-column slices.  Same result
+    as the torch product, and bit-identical to the same rows computed by a launch small enough to have no partial round."""
+    A, W, b = _rand((M, K), 31).bfloat16(), _rand((N, K), 32, 0.05).bfloat16(), _rand((N,), 33)
+    out = torch.full((M, N), float("nan"), device=cuda, dtype=torch.bfloat16)
+    ok(lib, lib.slsb_op_gemm(BF16, P(A), P(W), P(b), None, P(out), M, N, K, act, 1, stream()), "gemm tc tail")
+    report(f"gemm_tc tail {M}x{N}x{K}", out, _act(A.float() @ W.float().T + b, act), atol=2e-3, rtol=8e-3)
+    rows = slice(M - 300, M)                                   # the ragged end of the matrix: always inside the last round
+    At = A[rows].contiguous()
+    small = torch.empty(300, N, device=cuda, dtype=torch.bfloat16)
+    ok(lib, lib.slsb_op_gemm(BF16, P(At), P(W), P(b), None, P(small), 300, N, K, act, 1, stream()), "gemm tc small")
+    assert torch.equal(out[rows], small)
+
+
 def test_gemm_bf16_tc_deterministic(lib, cuda):
     M, N, K = 2000, 1024, 1024
     A, W, b = _rand((M, K), 9).bfloat16(), _rand((N, K), 10, 0.05).bfloat16(), _rand((N,), 11)
