@@ -165,6 +165,11 @@ int slsb_op_conv0(int out_bf16, const float* wav, const float* w, const float* b
                   void* out, int B, int S, int exact_gelu, void* stream);
 int slsb_op_layernorm(const void* in, int in_bf16, void* out, int out_bf16, const float* w, const float* b,
                       int64_t rows, int C, int gelu, int exact_gelu, void* stream);
+/* the encoder's LayerNorm as the layer loop uses it (wav2vec2.py:1045 / :1055 on the fp32 stream): bf16 normalised rows, and
+ * optionally a bf16 copy of the un-normalised rows (the layer_results snapshot, wav2vec2.py:958) and dot_out[row] =
+ * <row, dot_w> (SLS fc0 before the mean over frames, model_backup.py:186-202 getAttenF). */
+int slsb_op_layernorm_taps(const float* in, void* out_bf16, const float* w, const float* b, const float* dot_w, float* dot_out,
+                           void* copy_out_bf16, int64_t rows, int C, void* stream);
 int slsb_op_attention(int impl, int io_bf16, const void* qkv, void* out, int B, int T, int H,
                       const int32_t* frame_lens_dev, void* stream);
 /* tcgen05 attention with a pipeline timeline: trace_dev int64 [64 units][16 events] of CTA 0, SM clock64 stamps

@@ -168,7 +168,7 @@ struct ProfScope {
 
 static int conv_len(const slsb_config& c, int n, int upto = -1) {
     const int last = upto < 0 ? c.n_conv : upto;
-    for (int i = 0; i < last; ++i) n = (n - c.conv_kernel[i]) / c.conv_stride[i] + 1;
+    for (int i = 0; i < last; ++i) n = n < c.conv_kernel[i] ? 0 : (n - c.conv_kernel[i]) / c.conv_stride[i] + 1;   // C division truncates: no frames below the kernel width
     return n;
 }
 
@@ -1074,6 +1074,15 @@ int slsb_op_layernorm(const void* in, int in_bf16, void* out, int out_bf16, cons
                       int exact_gelu, void* stream) {
     LnArgs a;
     a.in = in; a.in_bf16 = in_bf16; a.out = out; a.out_bf16 = out_bf16; a.w = w; a.b = b; a.rows = rows; a.C = C; a.gelu = gelu; a.exact_gelu = exact_gelu;
+    return layernorm(a, static_cast<cudaStream_t>(stream));
+}
+
+int slsb_op_layernorm_taps(const float* in, void* out_bf16, const float* w, const float* b, const float* dot_w, float* dot_out,
+                           void* copy_out_bf16, int64_t rows, int C, void* stream) {
+    LnArgs a;
+    a.in = in; a.in_bf16 = 0; a.out = out_bf16; a.out_bf16 = 1; a.w = w; a.b = b; a.rows = rows; a.C = C;
+    a.dot_w = dot_w; a.dot_out = dot_out; a.copy_out = copy_out_bf16;
+    if (!in || !out_bf16 || !w || !b || (dot_out && !dot_w)) { set_error("slsb_op_layernorm_taps: null buffer"); return -1; }
     return layernorm(a, static_cast<cudaStream_t>(stream));
 }
 

@@ -33,7 +33,7 @@ class TrunkGeometry:
 
     def frames(self, samples: int) -> int:
         for _, k, s in self.conv_layers:        # wav2vec2.py:523-538
-            samples = (samples - k) // s + 1
+            samples = max(0, (samples - k) // s + 1)
         return samples
 
 

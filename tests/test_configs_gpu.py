@@ -163,3 +163,29 @@ def test_full_size_batch64_properties(sls, cuda):
     assert torch.equal(shuffled, full[perm])
     p = torch.exp(full)
     assert torch.isfinite(full).all() and float((p.sum(-1) - 1).abs().max()) < 1e-5
+
+
+def test_edge_cases_empty_short_and_minimal_clips(sls, cuda):
+    """Empty batch / clips shorter than the conv stack's receptive field fail loudly (the reference dies inside conv1d
+    there); the shortest legal clips (1, 2, 9 frames) and odd batch sizes match the oracle; [B, S, 1] input is accepted
+    (model.py:130-134)."""
+    from oracle.trunk import synth_clips
+    om, m = _small(sls, "sae", "fp32")
+    with pytest.raises(sls.SlsbError, match="empty batch"):
+        m(torch.zeros(0, 64600, device=cuda), return_sae_loss=False)
+    with pytest.raises(sls.SlsbError, match="too short"):
+        m(torch.zeros(2, 399, device=cuda), return_sae_loss=False)
+    for samples, batch in ((400, 1), (720, 3), (3200, 5)):             # 1, 2 and 9 frames
+        clips = synth_clips(500, batch, samples)
+        with torch.no_grad():
+            ref = om(clips)
+            got = m(clips.to(cuda), return_sae_loss=False).cpu()
+            got3 = m(clips.to(cuda).unsqueeze(-1), return_sae_loss=False).cpu()
+        err = float((got - ref).abs().max())
+        print(f"[minimal clips] S={samples} B={batch} frames={m.engine().frames(samples)} max|err|={err:.2e}")
+        assert err <= 1e-4 and torch.equal(got, got3)
+    _, mb = _small(sls, "sae", "bf16")
+    clips = synth_clips(600, 7, 3200)
+    with torch.no_grad():
+        err = float((mb(clips.to(cuda), return_sae_loss=False).cpu() - om(clips)).abs().max())
+    assert err <= 2e-2

@@ -237,6 +237,30 @@ def test_layernorm(lib, cuda, C, in_bf16, out_bf16, gelu):
     report(f"ln C={C}", out, ref, atol=2e-2 if out_bf16 else 1e-5, rtol=8e-3 if out_bf16 else 1e-5)
 
 
+@pytest.mark.parametrize("rows", [63, 64, 1003, 12864])
+@pytest.mark.parametrize("taps", [False, True])
+def test_layernorm_stream_taps(lib, cuda, rows, taps):
+    """Encoder LayerNorm(1024) fp32 -> bf16 (bulk-copy fed persistent kernel from 64 rows up, one-warp-per-row kernel below):
+    normalised rows vs torch, bf16 snapshot == the input rounded to bf16 (bit-exact), fc0 dots vs float64, bit-stable."""
+    C = 1024
+    x = _rand((rows, C), 53, 2.0) + 0.5
+    g, b, dw = 1 + _rand((C,), 54, 0.1), _rand((C,), 55, 0.05), _rand((C,), 56, 0.05)
+    outs = []
+    for _ in range(2):
+        out = torch.full((rows, C), float("nan"), device=cuda, dtype=torch.bfloat16)
+        snap = torch.full((rows, C), float("nan"), device=cuda, dtype=torch.bfloat16)
+        dots = torch.full((rows,), float("nan"), device=cuda)
+        ok(lib, lib.slsb_op_layernorm_taps(P(x), P(out), P(g), P(b), P(dw) if taps else None, P(dots) if taps else None,
+                                           P(snap) if taps else None, rows, C, stream()), "ln taps")
+        outs.append((out, snap, dots))
+    out, snap, dots = outs[0]
+    report(f"ln stream rows={rows}", out, F.layer_norm(x, (C,), g, b, 1e-5), atol=2e-2, rtol=8e-3)
+    if taps:
+        assert torch.equal(snap, x.bfloat16())
+        report("ln stream dots", dots.double(), x.double() @ dw.double(), atol=1e-4, rtol=1e-5)
+    assert all(torch.equal(a, c) for a, c in zip(outs[0][:3 if taps else 1], outs[1][:3 if taps else 1]))
+
+
 # ------------------------------------------------------------------------------------------ attention
 def _attn_ref(qkv, B, T, H, lens):
     D = H * 64

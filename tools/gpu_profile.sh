@@ -16,5 +16,8 @@ ncu --set full --clock-control none --import-source on -k regex:tc_gemm_pair_ker
 echo "gemm capture rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:tc_gemm_ln2_kernel -s 6 -c 2 -o gpurun_out/prof_ln2 -f $P > gpurun_out/ncu_ln2.log 2>&1
 echo "ln2 capture rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:"ln_kernel|sls_fuse_pool|attn_tc_kernel" -s 75 -c 4 -o gpurun_out/prof_hbm -f $P > gpurun_out/ncu_hbm.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"ln_stream_kernel|attn_tc_kernel" -s 80 -c 4 -o gpurun_out/prof_hbm -f $P > gpurun_out/ncu_hbm.log 2>&1
 echo "hbm capture rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:"sls_fuse_pool" -s 1 -c 1 -o gpurun_out/prof_pool -f $P > gpurun_out/ncu_pool.log 2>&1
+echo "pool capture rc=$?"
+# then, in the repo: python tools/ncu_summarize.py --round rNN  (writes profiles/)
