@@ -9,7 +9,7 @@ T=1500 TAILN=4 run parity python -m pytest tests/test_parity_gpu.py -q -m gpu --
 grep -E "^\.?\[|max\|err" gpurun_out/parity.log | cut -c1-160
 T=900 TAILN=1 run bench python bench.py --steps 20 --warmup 3 ${BENCH_ARGS:-}
 if [ "${AB_PDL:-0}" = "1" ]; then
-  SLSB_NO_PDL=1 T=900 TAILN=1 run bench_nopdl python bench.py --steps 20 --warmup 3 --no-cpu-baseline
+  SLSB_NO_PDL=1 T=900 TAILN=1 run bench_nopdl python bench.py --steps 20 --warmup 3 --no-cpu-baseline --sustained-steps 0
 fi
 if [ "${NCU_LIST:-0}" = "1" ]; then
   CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
