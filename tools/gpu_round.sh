@@ -12,7 +12,7 @@ if [ "${AB_PDL:-0}" = "1" ]; then
   SLSB_NO_PDL=1 T=900 TAILN=1 run bench_nopdl python bench.py --steps 20 --warmup 3 --no-cpu-baseline --sustained-steps 0
 fi
 if [ "${NCU_LIST:-0}" = "1" ]; then
-  CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+  CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --sustained-steps 0"
   ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_bench.csv $CMD > gpurun_out/ncu_list.log 2>&1
   echo "launch list rc=$?"
 fi
