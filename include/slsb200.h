@@ -165,6 +165,11 @@ int slsb_op_conv0(int out_bf16, const float* wav, const float* w, const float* b
                   void* out, int B, int S, int exact_gelu, void* stream);
 int slsb_op_layernorm(const void* in, int in_bf16, void* out, int out_bf16, const float* w, const float* b,
                       int64_t rows, int C, int gelu, int exact_gelu, void* stream);
+/* Host-side replay (no GPU needed) of the static tile schedule of the CTA-pair tcgen05 GEMM for an M x N output on num_pairs
+ * CTA pairs: items int32 [max_items][5] = {pair, round, first row, first column, columns}; *split_out = column slices per tile
+ * of the partial last round (1, 2 or 4).  Returns the number of items (may exceed max_items) or -1.  Test hook, no reference
+ * counterpart: the schedule must produce every output element exactly once. */
+int slsb_debug_pair_schedule(int M, int N, int num_pairs, int32_t* items, int max_items, int32_t* split_out);
 /* the encoder's LayerNorm as the layer loop uses it (wav2vec2.py:1045 / :1055 on the fp32 stream): bf16 normalised rows, and
  * optionally a bf16 copy of the un-normalised rows (the layer_results snapshot, wav2vec2.py:958) and dot_out[row] =
  * <row, dot_w> (SLS fc0 before the mean over frames, model_backup.py:186-202 getAttenF). */

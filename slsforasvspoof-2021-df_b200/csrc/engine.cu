@@ -1077,6 +1077,11 @@ int slsb_op_layernorm(const void* in, int in_bf16, void* out, int out_bf16, cons
     return layernorm(a, static_cast<cudaStream_t>(stream));
 }
 
+int slsb_debug_pair_schedule(int M, int N, int num_pairs, int32_t* items, int max_items, int32_t* split_out) {
+    if (!items && max_items > 0) { set_error("slsb_debug_pair_schedule: null items"); return -1; }
+    return pair_schedule(M, N, num_pairs, items, max_items, split_out);
+}
+
 int slsb_op_layernorm_taps(const float* in, void* out_bf16, const float* w, const float* b, const float* dot_w, float* dot_out,
                            void* copy_out_bf16, int64_t rows, int C, void* stream) {
     LnArgs a;

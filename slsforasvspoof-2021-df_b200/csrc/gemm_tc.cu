@@ -629,7 +629,7 @@ __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
 // same K order, so every output element is computed exactly as in a whole tile) and dealt round-robin, so the last round costs
 // ceil(rem * split / P) / split of a round instead of a whole one (qkv, M = 12864: 9 -> 8.5 rounds; fc1: 12 -> 11.25).
 struct PairItem { int m2, n0, width; };
-__device__ __forceinline__ bool pair_item(int it, int pair, int num_pairs, int num_tiles, int n_tiles, int split, PairItem& w) {
+__host__ __device__ __forceinline__ bool pair_item(int it, int pair, int num_pairs, int num_tiles, int n_tiles, int split, PairItem& w) {
     const int full_rounds = num_tiles / num_pairs;
     int tile, sub = 0;
     w.width = 256;
@@ -783,6 +783,18 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
 }
 
+// column slices per tile of the partial last round: the s in {1, 2, 4} with the smallest cost ceil(rem * s / P) / s (ties -> smaller s)
+int pair_tail_split(int tiles, int pairs) {
+    const int rem = tiles % pairs;
+    int best_num = 1, best_den = 1, split = 1;
+    if (rem == 0) return 1;
+    for (int s = 2; s <= 4; s *= 2) {
+        const int num = (rem * s + pairs - 1) / pairs;
+        if (num * best_den < best_num * s) { best_num = num; best_den = s; split = s; }
+    }
+    return split;
+}
+
 int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr, const DevParams& dp, int num_sms,
                 cudaStream_t stream) {
     static bool configured = false;
@@ -801,14 +813,7 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     DevParams q = dp;
     q.tail_split = 1;
     static const bool tail_on = !(getenv("SLSB_NO_TAIL_SPLIT") && atoi(getenv("SLSB_NO_TAIL_SPLIT")) != 0);
-    const int rem = tiles % pairs;
-    if (tail_on && rem != 0 && dp.tma_store && !dp.red_add && !dp.res_tma) {       // bf16 TMA-store epilogue handles column slices
-        int best_num = 1, best_den = 1;                                            // cost of the last round = ceil(rem * s / P) / s
-        for (int s = 2; s <= 4; s *= 2) {
-            const int num = (rem * s + pairs - 1) / pairs;
-            if (num * best_den < best_num * s) { best_num = num; best_den = s; q.tail_split = s; }
-        }
-    }
+    if (tail_on && dp.tma_store && !dp.red_add && !dp.res_tma) q.tail_split = pair_tail_split(tiles, pairs);   // bf16 TMA-store epilogue handles column slices
     SLSB_CUDA_CHECK(launch_pdl(tc_gemm_pair_kernel, dim3(2 * pairs), dim3(kNumThreads), Plan2::kBytes, stream, ta, tb, to, tr, q));
     return 0;
 }
@@ -839,6 +844,25 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, 
 }
 
 }  // namespace
+
+// Host-side replay of the pair kernel's static schedule (same pair_item() the device roles call): rows of
+// (pair, round, first row, first column, columns).  Test hook: every output column block must be produced exactly once.
+int pair_schedule(int M, int N, int num_pairs, int* items, int max_items, int* split_out) {
+    if (M < 1 || N < 256 || N % 256 != 0 || num_pairs < 1) { set_error("pair_schedule: M >= 1, N %% 256 == 0, num_pairs >= 1"); return -1; }
+    const int n_tiles = N / 256, tiles = ((M + 255) / 256) * n_tiles;
+    const int pairs = tiles < num_pairs ? tiles : num_pairs;
+    const int split = pair_tail_split(tiles, pairs);
+    if (split_out) *split_out = split;
+    int n = 0;
+    for (int p = 0; p < pairs; ++p) {
+        PairItem w;
+        for (int it = 0; pair_item(it, p, pairs, tiles, n_tiles, split, w); ++it) {
+            if (n < max_items) { int* r = items + 5 * n; r[0] = p; r[1] = it; r[2] = w.m2 * 256; r[3] = w.n0; r[4] = w.width; }
+            ++n;
+        }
+    }
+    return n;
+}
 
 int tc_gemm(const TcGemmArgs& g, int num_sms, cudaStream_t stream) {
     if (g.K % BLOCK_K != 0 || g.K <= 0) { set_error("tc_gemm: K=%d must be a positive multiple of %d", g.K, BLOCK_K); return -1; }

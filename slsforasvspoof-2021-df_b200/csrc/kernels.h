@@ -28,6 +28,8 @@ struct TcGemmArgs {
     int act = 0;
 };
 int tc_gemm(const TcGemmArgs& g, int num_sms, cudaStream_t stream);
+// host replay of the CTA-pair kernel's static tile schedule: items[5 * i] = {pair, round, row0, col0, cols}; returns the item count
+int pair_schedule(int M, int N, int num_pairs, int* items, int max_items, int* split_out);
 
 // ---------------------------------------------------------------- tcgen05 GEMM + LayerNorm(512) + GELU epilogue (gemm_tc_ln.cu)
 struct TcLnGemmArgs {

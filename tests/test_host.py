@@ -95,6 +95,7 @@ def test_pack_shapes_and_folds(sls):
 def test_frames_formula(sls):
     geo = sls.TrunkGeometry()
     assert geo.frames(64600) == 201 and geo.frames(16000) == 49 and geo.frames(160000) == 499
+    assert geo.frames(400) == 1 and geo.frames(399) == 0 and geo.frames(0) == 0      # receptive field of the conv stack = 400 samples
 
 
 def test_pad_clip_matches_reference_semantics(sls):
@@ -235,3 +236,37 @@ def test_world_size_2_gather_gloo(tmp_path):
     assert all(p.wait(timeout=240) == 0 for p in procs)
     lines = open(out).read().splitlines()
     assert len(lines) == 11 and lines[3] == "u3 1.5"
+
+
+@pytest.mark.parametrize("M,N", [(12864, 3072), (12864, 4096), (12864, 1024), (4864, 1024), (6221, 1024), (300, 256), (201, 1024),
+                                 (256 * 74, 256), (256 * 75, 256), (1, 256), (64 * 499, 2048)])
+@pytest.mark.parametrize("pairs", [74, 66, 1, 7])
+def test_pair_gemm_schedule_covers_every_output_once(lib, M, N, pairs):
+    """Host replay of the CTA-pair GEMM's static schedule (full rounds in snake order + a column-sliced partial last round):
+    every 256-row x N output block is produced exactly once, slices are 256 / 128 / 64 columns wide and aligned, and no pair
+    works more than one (sliced) item longer than another."""
+    import ctypes as C
+    cap = 4 * ((M + 255) // 256) * (N // 256) + 8
+    items = (C.c_int32 * (5 * cap))()
+    split = C.c_int32(0)
+    n = lib.slsb_debug_pair_schedule(M, N, pairs, items, cap, C.byref(split))
+    assert 0 < n <= cap and split.value in (1, 2, 4)
+    rows = np.ctypeslib.as_array(items).reshape(cap, 5)[:n]
+    m_tiles = (M + 255) // 256
+    cover = np.zeros((m_tiles, N // 64), dtype=np.int32)
+    for pair, rnd, row0, col0, cols in rows:
+        assert cols in (256, 128, 64) and col0 % cols == 0 and row0 % 256 == 0 and col0 + cols <= N
+        cover[row0 // 256, col0 // 64:(col0 + cols) // 64] += 1
+    assert (cover == 1).all()
+    used = min(pairs, m_tiles * (N // 256))
+    cost = np.zeros(used)
+    for pair, rnd, row0, col0, cols in rows:
+        cost[pair] += cols / 256.0
+    full = (m_tiles * (N // 256)) // used
+    assert cost.min() >= full and cost.max() <= full + 1
+    if (m_tiles * (N // 256)) % used:
+        assert cost.max() - full <= max(0.25, -(-((m_tiles * (N // 256)) % used * split.value) // used) / split.value) + 1e-9
+    # rounds are consecutive per pair (the device roles walk `it` upwards until the schedule ends)
+    for p in range(used):
+        r = sorted(int(x[1]) for x in rows if x[0] == p)
+        assert r == list(range(len(r)))
