@@ -238,13 +238,17 @@ def main():
     for i in range(3):
         eng.score_submit(host[i % n_pool], head, prec, out=outs[i % 4])
     eng.score_wait()
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        eng.score_submit(host[i % n_pool], head, prec, out=outs[i % 4])
-    eng.score_wait()
-    torch.cuda.synchronize()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    # the loop is host-timed, so one host hiccup (scheduler, page fault) lands in it: two passes, both reported, the faster one is `value`
+    e2e_passes = []
+    for _ in range(2):
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            eng.score_submit(host[i % n_pool], head, prec, out=outs[i % 4])
+        eng.score_wait()
+        torch.cuda.synchronize()
+        e2e_passes.append(max_over_ranks((time.perf_counter() - t0) * 1e3))
+    e2e_ms = min(e2e_passes)
     assert all(bool(torch.isfinite(o).all()) for o in outs)
     # the un-pipelined loop (one synchronising slsb_score_host call per step) for comparison
     barrier()
@@ -332,7 +336,8 @@ def main():
                        "global_batch": B * world, "parallelism": f"utterance-sharded x{world}",
                        "l2": "per-step working set (631 MB bf16 weights + >2 GB activations) exceeds the 126 MB L2; 4 rotating input batches"},
             "e2e": {"value": utt / (e2e_ms * 1e-3), "unit": "utt/s", "h2d_bytes_per_step": B * S * 4, "d2h_bytes_per_step": B * 4,
-                    "api": "slsb_score_submit/slsb_score_wait (pipelined uploads)", "sync_value": utt / (e2e_sync_ms * 1e-3),
+                    "api": "slsb_score_submit/slsb_score_wait (pipelined uploads)",
+                    "passes": [utt / (t * 1e-3) for t in e2e_passes], "sync_value": utt / (e2e_sync_ms * 1e-3),
                     "sync_api": "slsb_score_host (one host sync per step)"},
             "gpu_launches": int(launches), "clocks": clocks, "sustained": sustained, "roofline": roof, "cpu_baseline": cpu,
             "tflops_per_gpu_whole_step": FLOP_PER_UTT_TOTAL[args.head] * B * args.steps / (ms * 1e-3) / 1e12,

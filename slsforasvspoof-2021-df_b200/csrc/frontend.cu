@@ -174,14 +174,16 @@ int ln_launch(const LnArgs& a, cudaStream_t stream) {
 }
 // ------------------------------------------------------------------------------------------------
 // Encoder LayerNorm(1024) of the fp32 residual stream -> bf16, persistent and fed by bulk async copies.
-// The one-warp-per-row kernel above keeps only as many bytes in flight as its registers hold and refills them wave by wave
-// (ncu: 33-40 % of the DRAM peak).  Here a producer warp streams 8-row blocks (32 KB, contiguous) into a 3-stage shared
-// memory ring with cp.async.bulk + mbarrier transaction counts; 8 consumer warps (one row each) read their row from shared
-// memory and do exactly the arithmetic of ln_kernel (same shuffle trees, same association => identical bits).
-// 2 CTAs / SM x 96 KB of ring = up to 192 KB of loads in flight per SM, independent of the register file.
+// The one-warp-per-row kernel above is latency-bound (ncu: 0.3 instructions / clk / scheduler, 33-40 % of the DRAM peak): a
+// warp walks ~340 dependent-ish instructions per row and the register file caps the SM at 32 such warps whose loads are all
+// issued wave by wave.  Here a producer warp streams 8-row blocks (32 KB, contiguous) into a 3-stage shared memory ring with
+// cp.async.bulk + mbarrier transaction counts, and TWO consumer warps share a row (512 channels each, 16 values per lane):
+// half the dependent chain per warp, 32 consumer warps per SM in 56 registers, partial sums exchanged through shared memory
+// with one 64-thread named barrier per row.  2 CTAs / SM x 96 KB of ring = up to 192 KB of loads in flight per SM.
 // ------------------------------------------------------------------------------------------------
 constexpr int kLsRows = 8, kLsC = 1024, kLsStages = 3, kLsStageBytes = kLsRows * kLsC * 4;
-constexpr int kLsSmem = kLsStages * kLsStageBytes + 2 * kLsC * 4 + 64;     // ring + LN weight / bias + barriers
+constexpr int kLsConsumers = 2 * kLsRows, kLsThreads = (kLsConsumers + 1) * 32;
+constexpr int kLsSmem = kLsStages * kLsStageBytes + 2 * kLsC * 4 + kLsRows * 2 * 16 + 64;     // ring + LN weight / bias + exchange + barriers
 
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -189,27 +191,28 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gmem_sr
 }
 
 template <bool DOT>
-__global__ void __launch_bounds__(288, 2) ln_stream_kernel(const float* __restrict__ in, bf16* __restrict__ out,
-                                                           const float* __restrict__ w, const float* __restrict__ b,
-                                                           const float* __restrict__ dot_w, float* __restrict__ dot_out,
-                                                           bf16* __restrict__ copy_out, long long rows, float eps) {
-    constexpr int C = kLsC, NV = C / 128;
+__global__ void __launch_bounds__(kLsThreads, 2) ln_stream_kernel(const float* __restrict__ in, bf16* __restrict__ out,
+                                                                  const float* __restrict__ w, const float* __restrict__ b,
+                                                                  const float* __restrict__ dot_w, float* __restrict__ dot_out,
+                                                                  bf16* __restrict__ copy_out, long long rows, float eps) {
+    constexpr int C = kLsC, NVH = C / 256;                              // float4 vectors per lane (half a row per warp)
     extern __shared__ __align__(128) uint8_t ls_smem[];
     float* w_s = reinterpret_cast<float*>(ls_smem + kLsStages * kLsStageBytes);
     float* b_s = w_s + C;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(b_s + C);
+    float4* xch = reinterpret_cast<float4*>(b_s + C);                   // [row][half] = {sum, dot, sum of squared deviations, -}
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(xch + kLsRows * 2);
     uint64_t* empty_bar = full_bar + kLsStages;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long num_blocks = (rows + kLsRows - 1) / kLsRows;
     griddep_launch();
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kLsStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kLsRows); }
+        for (int s = 0; s < kLsStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kLsConsumers); }
         mbar_fence_init();
     }
     for (int i = threadIdx.x; i < C; i += blockDim.x) { w_s[i] = __ldg(w + i); b_s[i] = __ldg(b + i); }   // parameters: not written by the previous kernel
     __syncthreads();
     griddep_wait();
-    if (warp == kLsRows) {
+    if (warp == kLsConsumers) {
         // ===================== producer: one bulk copy per 8-row block =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
@@ -224,49 +227,58 @@ __global__ void __launch_bounds__(288, 2) ln_stream_kernel(const float* __restri
         }
         return;
     }
-    // ===================== consumers: warp = row of the block =====================
+    // ===================== consumers: warps 2r, 2r + 1 = halves of row r of the block =====================
+    const int r = warp >> 1, h = warp & 1;
+    const int c0 = h * (C / 2) + lane * 4;                               // this lane's channels: c0 + 128 i, i < NVH
+    const int bar_id = 1 + r;
     int stage = 0; uint32_t phase = 0;
     for (long long blk = blockIdx.x; blk < num_blocks; blk += gridDim.x) {
-        const long long row = blk * kLsRows + warp;
+        const long long row = blk * kLsRows + r;
         mbar_wait(&full_bar[stage], phase);
-        float v[NV][4];
+        float v[NVH][4];
         if (row < rows) {
-            const float* x = reinterpret_cast<const float*>(ls_smem + stage * kLsStageBytes) + warp * C;
+            const float* x = reinterpret_cast<const float*>(ls_smem + stage * kLsStageBytes) + r * C + c0;
 #pragma unroll
-            for (int i = 0; i < NV; ++i) load4<float>(x + (i * 32 + lane) * 4, v[i]);
+            for (int i = 0; i < NVH; ++i) load4<float>(x + 128 * i, v[i]);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[stage]);                 // the row is in registers: the stage may be refilled
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);                 // the half row is in registers: the stage may be refilled
         if (++stage == kLsStages) { stage = 0; phase ^= 1; }
-        if (row >= rows) continue;
+        if (row >= rows) continue;                                      // both warps of the row skip together
         float s = 0.f, dot = 0.f;
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            if (copy_out) store4<bf16>(copy_out + row * C + (i * 32 + lane) * 4, v[i]);
+        for (int i = 0; i < NVH; ++i) {
+            if (copy_out) store4<bf16>(copy_out + row * C + c0 + 128 * i, v[i]);
             if constexpr (DOT) {
-                const float4 dw = __ldg(reinterpret_cast<const float4*>(dot_w + (i * 32 + lane) * 4));
+                const float4 dw = __ldg(reinterpret_cast<const float4*>(dot_w + c0 + 128 * i));
                 dot = fmaf(v[i][0], dw.x, dot); dot = fmaf(v[i][1], dw.y, dot); dot = fmaf(v[i][2], dw.z, dot); dot = fmaf(v[i][3], dw.w, dot);
             }
             s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
         }
+        s = warp_sum(s);                                                // fixed shuffle trees + fixed half order: bit-stable
+        if constexpr (DOT) dot = warp_sum(dot);
+        if (lane == 0) { xch[r * 2 + h].x = s; xch[r * 2 + h].y = dot; }
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        const float mean = (xch[r * 2].x + xch[r * 2 + 1].x) * (1.0f / C);
         if constexpr (DOT) {
-            dot = warp_sum(dot);
-            if (lane == 0) dot_out[row] = dot;
+            if (h == 0 && lane == 0) dot_out[row] = xch[r * 2].y + xch[r * 2 + 1].y;
         }
-        const float mean = warp_sum(s) * (1.0f / C);
         float q = 0.f;
 #pragma unroll
-        for (int i = 0; i < NV; ++i)
+        for (int i = 0; i < NVH; ++i)
 #pragma unroll
             for (int e = 0; e < 4; ++e) { const float d = v[i][e] - mean; q = fmaf(d, d, q); }
-        const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / C) + eps);
+        q = warp_sum(q);
+        if (lane == 0) xch[r * 2 + h].z = q;
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        const float rstd = 1.0f / sqrtf((xch[r * 2].z + xch[r * 2 + 1].z) * (1.0f / C) + eps);
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const float4 g = *reinterpret_cast<const float4*>(w_s + (i * 32 + lane) * 4), bb = *reinterpret_cast<const float4*>(b_s + (i * 32 + lane) * 4);
+        for (int i = 0; i < NVH; ++i) {
+            const float4 g = *reinterpret_cast<const float4*>(w_s + c0 + 128 * i), bb = *reinterpret_cast<const float4*>(b_s + c0 + 128 * i);
             float y[4];
             y[0] = (v[i][0] - mean) * rstd * g.x + bb.x; y[1] = (v[i][1] - mean) * rstd * g.y + bb.y;
             y[2] = (v[i][2] - mean) * rstd * g.z + bb.z; y[3] = (v[i][3] - mean) * rstd * g.w + bb.w;
-            store4<bf16>(out + row * C + (i * 32 + lane) * 4, y);
+            store4<bf16>(out + row * C + c0 + 128 * i, y);
         }
     }
 }
@@ -288,8 +300,8 @@ static int ln_stream_launch(const LnArgs& a, cudaStream_t stream) {
     const long long blocks = (a.rows + kLsRows - 1) / kLsRows;
     const unsigned grid = (unsigned)(blocks < 2ll * num_sms ? blocks : 2ll * num_sms);
     const float* in = static_cast<const float*>(a.in);
-    if (a.dot_out) SLSB_CUDA_CHECK(launch_pdl(ln_stream_kernel<true>, dim3(grid), dim3(288), (size_t)kLsSmem, stream, in, static_cast<bf16*>(a.out), a.w, a.b, a.dot_w, a.dot_out, static_cast<bf16*>(a.copy_out), a.rows, a.eps));
-    else SLSB_CUDA_CHECK(launch_pdl(ln_stream_kernel<false>, dim3(grid), dim3(288), (size_t)kLsSmem, stream, in, static_cast<bf16*>(a.out), a.w, a.b, a.dot_w, a.dot_out, static_cast<bf16*>(a.copy_out), a.rows, a.eps));
+    if (a.dot_out) SLSB_CUDA_CHECK(launch_pdl(ln_stream_kernel<true>, dim3(grid), dim3(kLsThreads), (size_t)kLsSmem, stream, in, static_cast<bf16*>(a.out), a.w, a.b, a.dot_w, a.dot_out, static_cast<bf16*>(a.copy_out), a.rows, a.eps));
+    else SLSB_CUDA_CHECK(launch_pdl(ln_stream_kernel<false>, dim3(grid), dim3(kLsThreads), (size_t)kLsSmem, stream, in, static_cast<bf16*>(a.out), a.w, a.b, a.dot_w, a.dot_out, static_cast<bf16*>(a.copy_out), a.rows, a.eps));
     SLSB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
