@@ -17,10 +17,13 @@ from .model import Model, ModelWindowTopK, ModelSLS, SSLModel, AutoEncoderTopK, 
 from .scoring import (produce_evaluation_file, score_synthetic_shard, gather_scores, write_score_file, pad_clip,
                       SyntheticEvalSet, shard_range, bucket_by_frames, score_variable_length, compute_eer, read_score_file,
                       synth_clip_host)
+from .ingest import (read_wav_pcm16, write_wav_pcm16, decode_wav_files, write_pcm_shard, wav_files_to_shard, PcmShard,
+                     score_pcm_shard, AudioFormatError)
 
 __all__ = ["Model", "ModelWindowTopK", "ModelSLS", "SSLModel", "AutoEncoderTopK", "getAttenF", "Engine", "make_config",
            "TrunkGeometry", "TrunkParams", "pack_state_dict", "load_checkpoint_tensors", "load_model_checkpoint", "fix_module_prefix", "produce_evaluation_file", "score_synthetic_shard",
            "gather_scores", "write_score_file", "pad_clip", "SyntheticEvalSet", "shard_range", "bucket_by_frames",
            "score_variable_length", "compute_eer", "read_score_file", "synth_clip_host", "SlsbError",
            "load_library", "LIB_PATH", "EXPORTED_SYMBOLS", "PRECISIONS", "HEAD_NONE", "HEAD_SAE", "HEAD_WINDOW",
-           "HEAD_SLS", "PREC_FP32", "PREC_BF16"]
+           "HEAD_SLS", "PREC_FP32", "PREC_BF16", "read_wav_pcm16", "write_wav_pcm16", "decode_wav_files", "write_pcm_shard",
+           "wav_files_to_shard", "PcmShard", "score_pcm_shard", "AudioFormatError"]

@@ -151,10 +151,20 @@ class Engine:
         lens = torch.tensor([int(c.numel()) for c in clips], dtype=torch.int32)
         offsets = torch.zeros(len(clips), dtype=torch.int64)
         offsets[1:] = torch.cumsum(lens[:-1].to(torch.int64), 0)
-        pcm = torch.cat([c.reshape(-1).to(torch.int16) for c in clips]).contiguous().pin_memory()
-        scores = torch.empty(len(clips), dtype=torch.float32, pin_memory=True)
-        check(self.lib.slsb_score_pcm16_host(self._h, ptr(pcm), pcm.numel(), ptr(offsets), ptr(lens), len(clips), samples, head, precision,
-                                             ptr(scores), stream_ptr(self.device)), "slsb_score_pcm16_host")
+        pcm = torch.cat([c.reshape(-1).to(torch.int16) for c in clips])
+        return self.score_pcm16_arrays(pcm, offsets, lens, head, precision, samples)
+
+    def score_pcm16_arrays(self, pcm: torch.Tensor, offsets: torch.Tensor, lens: torch.Tensor, head: int, precision: int,
+                           samples: int = 64600) -> torch.Tensor:
+        """``slsb_score_pcm16_host`` on host arrays: pcm int16 [total] (clips back to back), offsets int64 [B], lens int32 [B]."""
+        if pcm.dtype != torch.int16 or offsets.dtype != torch.int64 or lens.dtype != torch.int32:
+            raise TypeError("score_pcm16_arrays: pcm int16, offsets int64, lens int32")
+        B = lens.numel()
+        pcm = pcm.contiguous()
+        pcm = pcm if pcm.is_pinned() else pcm.pin_memory()
+        scores = torch.empty(B, dtype=torch.float32, pin_memory=True)
+        check(self.lib.slsb_score_pcm16_host(self._h, ptr(pcm), pcm.numel(), ptr(offsets.contiguous()), ptr(lens.contiguous()), B, samples, head,
+                                             precision, ptr(scores), stream_ptr(self.device)), "slsb_score_pcm16_host")
         return scores
 
     def synth_clips(self, first_utt: int, count: int, samples: int = 64600) -> torch.Tensor:

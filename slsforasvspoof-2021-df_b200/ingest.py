@@ -1,0 +1,137 @@
+"""Host side of the audio ingest: what replaces ``Dataset_*_eval.__getitem__`` + ``pad``
+(data_utils_SSL.py:96-135, :58-65) and the 6-worker DataLoader (main.py:161-165) in front of a scorer that consumes
+thousands of clips per second.
+
+The reference decodes one FLAC per ``__getitem__`` with librosa, converts to float32 and tile-pads on the host.  Here the host
+only ever handles **16-bit PCM**: clips are decoded once (a thread pool over RIFF/WAVE files - FLAC decoding needs
+libsndfile, which this image does not have, so FLAC corpora are converted off-line) into a *PCM shard* (all clips back to
+back as int16 + an offset table), shards are memory-mapped, and every batch travels to the device as 2 bytes per sample of
+the UN-padded clips; float conversion, truncation and tile-repeat padding happen in ``ingest_pcm16_kernel``
+(csrc/frontend.cu) through ``slsb_score_pcm16_host`` (include/slsb200.h).
+
+Pure host code: numpy + the standard library; the only GPU entry is ``score_pcm_shard``.
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import json
+import os
+import wave
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+SAMPLE_RATE = 16000          # ASVspoof audio; librosa.load(..., sr=16000) in the reference (data_utils_SSL.py:111)
+
+
+class AudioFormatError(ValueError):
+    pass
+
+
+def read_wav_pcm16(path: str, sample_rate: int = SAMPLE_RATE) -> np.ndarray:
+    """RIFF/WAVE, 16-bit PCM -> int16 [n].  Multi-channel files are averaged to mono (what ``librosa.load(mono=True)`` does,
+    here in integer arithmetic rounded half away from zero); other sample widths or rates are rejected - resampling is an
+    off-line step, the scorer never guesses."""
+    with wave.open(path, "rb") as w:
+        if w.getsampwidth() != 2 or w.getcomptype() != "NONE":
+            raise AudioFormatError(f"{path}: need 16-bit PCM, got sample width {w.getsampwidth()} / {w.getcomptype()}")
+        if w.getframerate() != sample_rate:
+            raise AudioFormatError(f"{path}: need {sample_rate} Hz, got {w.getframerate()} Hz")
+        ch = w.getnchannels()
+        pcm = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2")
+    if ch > 1:
+        s = pcm.reshape(-1, ch).astype(np.int32).sum(axis=1)
+        pcm = (np.sign(s) * ((np.abs(s) * 2 + ch) // (2 * ch))).astype(np.int16)
+    return np.ascontiguousarray(pcm, dtype=np.int16)
+
+
+def write_wav_pcm16(path: str, pcm: np.ndarray, sample_rate: int = SAMPLE_RATE) -> None:
+    with wave.open(path, "wb") as w:
+        w.setnchannels(1)
+        w.setsampwidth(2)
+        w.setframerate(sample_rate)
+        w.writeframes(np.ascontiguousarray(pcm, dtype="<i2").tobytes())
+
+
+def decode_wav_files(paths: Sequence[str], workers: int = 6) -> List[np.ndarray]:
+    """Thread pool over ``read_wav_pcm16`` (file reads and numpy release the GIL); order preserved."""
+    if workers <= 1 or len(paths) < 2:
+        return [read_wav_pcm16(p) for p in paths]
+    with cf.ThreadPoolExecutor(max_workers=workers) as ex:
+        return list(ex.map(read_wav_pcm16, paths))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# PCM shard: <dir>/pcm.npy (int16, all clips back to back), <dir>/offsets.npy (int64 [n + 1]), <dir>/utts.json (ids)
+# ------------------------------------------------------------------------------------------------------------------
+def write_pcm_shard(directory: str, utt_ids: Sequence[str], clips: Iterable[np.ndarray]) -> None:
+    clips = [np.ascontiguousarray(c, dtype=np.int16).reshape(-1) for c in clips]
+    if len(clips) != len(utt_ids):
+        raise ValueError(f"{len(utt_ids)} ids for {len(clips)} clips")
+    if any(c.size == 0 for c in clips):
+        raise AudioFormatError("empty clip (the reference's pad() would divide by zero, data_utils_SSL.py:62)")
+    os.makedirs(directory, exist_ok=True)
+    offsets = np.zeros(len(clips) + 1, dtype=np.int64)
+    np.cumsum([c.size for c in clips], out=offsets[1:])
+    np.save(os.path.join(directory, "pcm.npy"), np.concatenate(clips) if clips else np.zeros(0, np.int16))
+    np.save(os.path.join(directory, "offsets.npy"), offsets)
+    with open(os.path.join(directory, "utts.json"), "w") as f:
+        json.dump(list(utt_ids), f)
+
+
+def wav_files_to_shard(directory: str, utt_ids: Sequence[str], paths: Sequence[str], workers: int = 6) -> None:
+    write_pcm_shard(directory, utt_ids, decode_wav_files(paths, workers))
+
+
+class PcmShard:
+    """Memory-mapped shard; ``batch(lo, hi)`` returns the three arrays ``slsb_score_pcm16_host`` takes."""
+
+    def __init__(self, directory: str):
+        self.pcm = np.load(os.path.join(directory, "pcm.npy"), mmap_mode="r")
+        self.offsets = np.load(os.path.join(directory, "offsets.npy"))
+        with open(os.path.join(directory, "utts.json")) as f:
+            self.utt_ids: List[str] = json.load(f)
+        if self.pcm.dtype != np.int16 or self.offsets.dtype != np.int64 or len(self.offsets) != len(self.utt_ids) + 1 \
+                or int(self.offsets[-1]) != self.pcm.shape[0] or np.any(np.diff(self.offsets) <= 0):
+            raise AudioFormatError(f"{directory}: inconsistent shard")
+
+    def __len__(self) -> int:
+        return len(self.utt_ids)
+
+    def clip(self, i: int) -> np.ndarray:
+        return np.asarray(self.pcm[self.offsets[i]:self.offsets[i + 1]])
+
+    def batch(self, lo: int, hi: int, max_samples: Optional[int] = None) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """(pcm int16 [total], offsets int64 [B] relative to pcm, lens int32 [B]) of clips lo..hi-1.  With ``max_samples`` only
+        the first ``max_samples`` of a longer clip are taken (pad() truncates to the head, data_utils_SSL.py:60-61), so a
+        10-minute recording costs no more upload than a 4-second one."""
+        starts, ends = self.offsets[lo:hi], self.offsets[lo + 1:hi + 1]
+        lens = (ends - starts).astype(np.int64)
+        if max_samples is not None:
+            lens = np.minimum(lens, max_samples)
+        if max_samples is None or np.all(ends - starts == lens):
+            pcm = np.asarray(self.pcm[starts[0]:ends[-1]]) if hi > lo else np.zeros(0, np.int16)
+            rel = (starts - starts[0]).astype(np.int64) if hi > lo else np.zeros(0, np.int64)
+        else:
+            pcm = np.concatenate([np.asarray(self.pcm[s:s + n]) for s, n in zip(starts, lens)])
+            rel = np.zeros(hi - lo, dtype=np.int64)
+            np.cumsum(lens[:-1], out=rel[1:])
+        return np.ascontiguousarray(pcm), rel, lens.astype(np.int32)
+
+
+def score_pcm_shard(model, shard: PcmShard, batch: int = 64, samples: int = 64600, lo: int = 0, hi: Optional[int] = None) -> torch.Tensor:
+    """Scores clips lo..hi-1 of a shard (a rank's ``shard_range``) with ``model`` (a ``Model`` / ``ModelSLS`` of this
+    package): ``exp(logp[:, 1])`` per clip, float32 CPU tensor, protocol order (main.py:178-192)."""
+    hi = len(shard) if hi is None else hi
+    eng = model.engine()
+    head, prec = model._head(), model._prec()
+    out = torch.empty(max(hi - lo, 0), dtype=torch.float32)
+    stage = torch.empty(batch * samples, dtype=torch.int16, pin_memory=torch.cuda.is_available())     # one pinned upload buffer, re-used
+    for a in range(lo, hi, batch):
+        b = min(a + batch, hi)
+        pcm, off, lens = shard.batch(a, b, max_samples=samples)
+        up = stage[:pcm.size]
+        up.numpy()[:] = pcm                                       # the only host copy: memory-mapped shard -> pinned buffer
+        out[a - lo:b - lo] = eng.score_pcm16_arrays(up, torch.from_numpy(off), torch.from_numpy(lens), head, prec, samples)
+    return out

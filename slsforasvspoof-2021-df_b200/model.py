@@ -290,6 +290,9 @@ class ModelSLS(_EngineOwner, nn.Module):
         q = 64 * 17          # matches csrc/engine.cu: a multiple of the fp32 17-way split and of the 64-wide k-blocks
         return (self.fc1.in_features + q - 1) // q * q
 
+    def _head(self) -> int:
+        return HEAD_SLS
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return self.engine().forward(_prep_wav(x), HEAD_SLS, self._prec())
 

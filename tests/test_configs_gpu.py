@@ -189,3 +189,26 @@ def test_edge_cases_empty_short_and_minimal_clips(sls, cuda):
     with torch.no_grad():
         err = float((mb(clips.to(cuda), return_sae_loss=False).cpu() - om(clips)).abs().max())
     assert err <= 2e-2
+
+
+def test_score_pcm_shard_equals_float_host_path(sls, cuda, tmp_path):
+    """next row N2 end to end: WAV files -> PCM shard -> score_pcm_shard (2 bytes / sample uploaded, pad() on the device) gives
+    bit for bit the scores of the reference-shaped path (host float32 conversion + pad, then slsb_score_host), for any batch
+    size and for a rank's sub-range of the shard."""
+    rs = np.random.RandomState(3)
+    lens = [16000, 64600, 70001, 33000, 5, 64599, 129200]
+    clips = [(rs.randn(n) * 3000).clip(-32768, 32767).astype(np.int16) for n in lens]
+    paths = []
+    for i, c in enumerate(clips):
+        paths.append(str(tmp_path / f"c{i}.wav"))
+        sls.write_wav_pcm16(paths[-1], c)
+    sls.wav_files_to_shard(str(tmp_path / "shard"), [f"u{i}" for i in range(len(clips))], paths, workers=2)
+    shard = sls.PcmShard(str(tmp_path / "shard"))
+    _, m = _small(sls, "sls")
+    got = sls.score_pcm_shard(m, shard, batch=3)
+    wav = torch.from_numpy(np.stack([sls.pad_clip(c.astype(np.float32) / np.float32(32768.0), 64600) for c in clips])).pin_memory()
+    want = m.engine().score_host(wav, sls.HEAD_SLS, sls.PREC_BF16)
+    assert torch.equal(got, want.cpu())
+    assert torch.equal(sls.score_pcm_shard(m, shard, batch=64), got)
+    assert torch.equal(sls.score_pcm_shard(m, shard, batch=2, lo=2, hi=6), got[2:6])
+    assert torch.isfinite(got).all() and float(got.min()) > 0 and float(got.max()) < 1

@@ -270,3 +270,56 @@ def test_pair_gemm_schedule_covers_every_output_once(lib, M, N, pairs):
     for p in range(used):
         r = sorted(int(x[1]) for x in rows if x[0] == p)
         assert r == list(range(len(r)))
+
+
+def test_wav_decode_and_pcm_shard_roundtrip(sls, tmp_path):
+    """Ingest host side (next row N2): 16-bit WAV -> int16, stereo -> mono mean, wrong rate / width rejected; a PCM shard
+    returns exactly the clips it was built from, and batch() hands out the (pcm, offsets, lens) triple of the C ABI with
+    long clips truncated to their head (pad() keeps x[:max_len], data_utils_SSL.py:60-61)."""
+    import wave
+    rs = np.random.RandomState(5)
+    lens = [1, 900, 16000, 64600, 70001, 33]
+    clips = [rs.randint(-32768, 32768, size=n).astype(np.int16) for n in lens]
+    paths = []
+    for i, c in enumerate(clips):
+        p = str(tmp_path / f"u{i}.wav")
+        sls.write_wav_pcm16(p, c)
+        paths.append(p)
+        assert np.array_equal(sls.read_wav_pcm16(p), c)
+    assert all(np.array_equal(a, b) for a, b in zip(sls.decode_wav_files(paths, workers=3), clips))
+    st = str(tmp_path / "stereo.wav")
+    l, r = np.array([100, -3, 32767, -32768, 1], np.int16), np.array([101, -4, 32767, -32768, 2], np.int16)
+    with wave.open(st, "wb") as w:
+        w.setnchannels(2); w.setsampwidth(2); w.setframerate(16000)
+        w.writeframes(np.stack([l, r], 1).astype("<i2").tobytes())
+    assert sls.read_wav_pcm16(st).tolist() == [101, -4, 32767, -32768, 2]        # mean, halves rounded away from zero
+    bad = str(tmp_path / "bad.wav")
+    sls.write_wav_pcm16(bad, clips[1], sample_rate=8000)
+    with pytest.raises(sls.AudioFormatError):
+        sls.read_wav_pcm16(bad)
+    with wave.open(bad, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(1); w.setframerate(16000); w.writeframes(b"\\x00\\x01")
+    with pytest.raises(sls.AudioFormatError):
+        sls.read_wav_pcm16(bad)
+
+    d = str(tmp_path / "shard")
+    ids = [f"DF_E_{i:07d}" for i in range(len(clips))]
+    sls.wav_files_to_shard(d, ids, paths, workers=2)
+    sh = sls.PcmShard(d)
+    assert len(sh) == len(clips) and sh.utt_ids == ids
+    assert all(np.array_equal(sh.clip(i), c) for i, c in enumerate(clips))
+    pcm, off, ln = sh.batch(1, 4)
+    assert pcm.dtype == np.int16 and off.dtype == np.int64 and ln.dtype == np.int32
+    assert ln.tolist() == lens[1:4] and off.tolist() == [0, 900, 16900] and np.array_equal(pcm, np.concatenate(clips[1:4]))
+    pcm, off, ln = sh.batch(2, 6, max_samples=64600)
+    assert ln.tolist() == [16000, 64600, 64600, 33] and off.tolist() == [0, 16000, 80600, 145200]
+    for j, i in enumerate(range(2, 6)):
+        assert np.array_equal(pcm[off[j]:off[j] + ln[j]], clips[i][:64600])
+    # what the device computes from such a triple == the reference's host path on the same clip
+    want = sls.pad_clip(clips[4].astype(np.float32) / np.float32(32768.0), 64600)
+    assert np.array_equal(sls.pad_clip(pcm[off[2]:off[2] + ln[2]].astype(np.float32) / np.float32(32768.0), 64600), want)
+    with pytest.raises(sls.AudioFormatError):
+        sls.write_pcm_shard(str(tmp_path / "e"), ["a"], [np.zeros(0, np.int16)])
+    np.save(os.path.join(d, "offsets.npy"), np.array([0, 5, 5], np.int64))
+    with pytest.raises(sls.AudioFormatError):
+        sls.PcmShard(d)
