@@ -128,6 +128,20 @@ int slsb_ingest_pcm16(const int16_t* pcm_dev, const int64_t* offsets_dev, const 
 int slsb_score_pcm16_host(slsb_engine* e, const int16_t* pcm_host, int64_t total_samples, const int64_t* offsets_host,
                           const int32_t* lens_host, int B, int S, int head, int precision, float* scores_host, void* stream);
 
+/* Native FLAC decode (host code, no GPU): replaces librosa.load -> libsndfile in Dataset_*_eval.__getitem__
+ * (data_utils_SSL.py:109-113) for the FLAC corpora the reference scores.  data: a whole .flac file in memory.  max_samples > 0
+ * stops after that many samples per channel (pad() keeps only the first 64 600, data_utils_SSL.py:60-61).  Frame CRC-8 / CRC-16 are
+ * always checked; verify_md5 != 0 also checks STREAMINFO's MD5 when the stream is decoded completely.
+ *  slsb_flac_decode: interleaved int32 samples at the stream's own bit depth; info int32 [6] = {sample rate, channels, bits per
+ *    sample, total samples (low 31 bits), MD5 verified (0/1), total samples >> 31}.  pcm_out NULL: STREAMINFO only, returns 0.
+ *  slsb_flac_decode_mono16: 16-bit streams only, channels averaged to mono (halves away from zero), what the scorer ingests.
+ * Both return the samples per channel decoded, or < 0: -2 not FLAC, -3 truncated, -4 bad header, -5 CRC-8, -6 CRC-16, -7 reserved
+ * bit pattern, -8 MD5 mismatch, -9 unsupported (mid-stream format change, bit depth), -10 STREAMINFO, -11 bad argument. */
+int64_t slsb_flac_decode(const uint8_t* data, int64_t nbytes, int64_t max_samples, int verify_md5, int32_t* pcm_out,
+                         int64_t pcm_capacity, int32_t* info);
+int64_t slsb_flac_decode_mono16(const uint8_t* data, int64_t nbytes, int64_t max_samples, int verify_md5, int16_t* pcm_out,
+                                int64_t pcm_capacity, int32_t* sample_rate);
+
 /* synthetic clips keyed by utterance index, bit-identical to oracle.trunk.synth_clips */
 int slsb_synth_clips(float* wav_dev, int64_t first_utt, int count, int samples, void* stream);
 

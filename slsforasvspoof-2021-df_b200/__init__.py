@@ -18,7 +18,8 @@ from .scoring import (produce_evaluation_file, score_synthetic_shard, gather_sco
                       SyntheticEvalSet, shard_range, bucket_by_frames, score_variable_length, compute_eer, read_score_file,
                       synth_clip_host)
 from .ingest import (read_wav_pcm16, write_wav_pcm16, decode_wav_files, write_pcm_shard, wav_files_to_shard, PcmShard,
-                     score_pcm_shard, AudioFormatError)
+                     score_pcm_shard, AudioFormatError, decode_flac_bytes, read_flac_pcm16, read_audio_pcm16, decode_audio_files,
+                     audio_files_to_shard)
 
 __all__ = ["Model", "ModelWindowTopK", "ModelSLS", "SSLModel", "AutoEncoderTopK", "getAttenF", "Engine", "make_config",
            "TrunkGeometry", "TrunkParams", "pack_state_dict", "load_checkpoint_tensors", "load_model_checkpoint", "fix_module_prefix", "produce_evaluation_file", "score_synthetic_shard",
@@ -26,4 +27,5 @@ __all__ = ["Model", "ModelWindowTopK", "ModelSLS", "SSLModel", "AutoEncoderTopK"
            "score_variable_length", "compute_eer", "read_score_file", "synth_clip_host", "SlsbError",
            "load_library", "LIB_PATH", "EXPORTED_SYMBOLS", "PRECISIONS", "HEAD_NONE", "HEAD_SAE", "HEAD_WINDOW",
            "HEAD_SLS", "PREC_FP32", "PREC_BF16", "read_wav_pcm16", "write_wav_pcm16", "decode_wav_files", "write_pcm_shard",
-           "wav_files_to_shard", "PcmShard", "score_pcm_shard", "AudioFormatError"]
+           "wav_files_to_shard", "PcmShard", "score_pcm_shard", "AudioFormatError", "decode_flac_bytes", "read_flac_pcm16",
+           "read_audio_pcm16", "decode_audio_files", "audio_files_to_shard"]

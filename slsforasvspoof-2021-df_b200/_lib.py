@@ -69,6 +69,8 @@ _SIGNATURES = {
     "slsb_op_posconv": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "slsb_op_conv0": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "slsb_op_layernorm": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _P]),
+    "slsb_flac_decode": (C.c_int64, [_P, C.c_int64, C.c_int64, C.c_int, _P, C.c_int64, _P]),
+    "slsb_flac_decode_mono16": (C.c_int64, [_P, C.c_int64, C.c_int64, C.c_int, _P, C.c_int64, _P]),
     "slsb_debug_pair_schedule": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, C.c_int, _P]),
     "slsb_op_layernorm_taps": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, _P]),
     "slsb_op_attention": (C.c_int, [C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),

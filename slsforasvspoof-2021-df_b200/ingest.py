@@ -3,10 +3,10 @@
 thousands of clips per second.
 
 The reference decodes one FLAC per ``__getitem__`` with librosa, converts to float32 and tile-pads on the host.  Here the host
-only ever handles **16-bit PCM**: clips are decoded once (a thread pool over RIFF/WAVE files - FLAC decoding needs
-libsndfile, which this image does not have, so FLAC corpora are converted off-line) into a *PCM shard* (all clips back to
-back as int16 + an offset table), shards are memory-mapped, and every batch travels to the device as 2 bytes per sample of
-the UN-padded clips; float conversion, truncation and tile-repeat padding happen in ``ingest_pcm16_kernel``
+only ever handles **16-bit PCM**: clips are decoded once by a thread pool - FLAC with the library's own decoder
+(csrc/flac_decode.cpp, ``slsb_flac_decode_mono16``: CRC-8 / CRC-16 / MD5 checked, stops after the 64 600 samples ``pad`` keeps),
+RIFF/WAVE with the standard library - into a *PCM shard* (all clips back to back as int16 + an offset table), shards are
+memory-mapped, and every batch travels to the device as 2 bytes per sample of the UN-padded clips; float conversion, truncation and tile-repeat padding happen in ``ingest_pcm16_kernel``
 (csrc/frontend.cu) through ``slsb_score_pcm16_host`` (include/slsb200.h).
 
 Pure host code: numpy + the standard library; the only GPU entry is ``score_pcm_shard``.
@@ -54,6 +54,59 @@ def write_wav_pcm16(path: str, pcm: np.ndarray, sample_rate: int = SAMPLE_RATE) 
         w.writeframes(np.ascontiguousarray(pcm, dtype="<i2").tobytes())
 
 
+FLAC_ERRORS = {-2: "not a FLAC stream", -3: "truncated stream", -4: "bad frame header", -5: "frame header CRC-8 mismatch",
+               -6: "frame CRC-16 mismatch", -7: "reserved bit pattern", -8: "MD5 of the decoded audio differs from STREAMINFO",
+               -9: "unsupported stream (bit depth / mid-stream format change)", -10: "bad STREAMINFO", -11: "bad argument"}
+
+
+def decode_flac_bytes(data: bytes, max_samples: Optional[int] = None, verify_md5: bool = True, sample_rate: Optional[int] = SAMPLE_RATE) -> np.ndarray:
+    """A whole .flac file in memory -> mono int16 [n] (channels averaged like ``read_wav_pcm16``).  ``max_samples`` stops the
+    decode early (the MD5 is then not checked - it covers the whole stream; frame CRCs always are)."""
+    import ctypes as C
+    from ._lib import load
+    lib = load()
+    buf = np.frombuffer(data, dtype=np.uint8)
+    probe = (C.c_int32 * 6)()
+    rc = lib.slsb_flac_decode(buf.ctypes.data, buf.size, 1, 0, None, 0, probe)      # STREAMINFO + first frame only
+    if rc < 0:
+        raise AudioFormatError(f"FLAC: {FLAC_ERRORS.get(int(rc), rc)}")
+    total = int(probe[3]) | (int(probe[5]) << 31)
+    if sample_rate is not None and probe[0] != sample_rate:
+        raise AudioFormatError(f"FLAC: need {sample_rate} Hz, got {probe[0]} Hz")
+    if probe[2] != 16:
+        raise AudioFormatError(f"FLAC: need 16-bit samples, got {probe[2]}")
+    cap = total if total > 0 else 1 << 26
+    if max_samples:
+        cap = min(cap, int(max_samples))
+    out = np.empty(cap, dtype=np.int16)
+    rate = C.c_int32(0)
+    n = lib.slsb_flac_decode_mono16(buf.ctypes.data, buf.size, int(max_samples or 0), 1 if verify_md5 else 0, out.ctypes.data, cap, C.byref(rate))
+    if n < 0:
+        raise AudioFormatError(f"FLAC: {FLAC_ERRORS.get(int(n), n)}")
+    return out[:n]
+
+
+def read_flac_pcm16(path: str, max_samples: Optional[int] = None, verify_md5: bool = True, sample_rate: Optional[int] = SAMPLE_RATE) -> np.ndarray:
+    with open(path, "rb") as f:
+        return decode_flac_bytes(f.read(), max_samples, verify_md5, sample_rate)
+
+
+def read_audio_pcm16(path: str, max_samples: Optional[int] = None) -> np.ndarray:
+    """.flac (native decoder) or .wav by extension; ``max_samples`` keeps the head of the clip, which is all pad() uses."""
+    if path.lower().endswith(".flac"):
+        return read_flac_pcm16(path, max_samples)
+    pcm = read_wav_pcm16(path)
+    return pcm[:max_samples] if max_samples else pcm
+
+
+def decode_audio_files(paths: Sequence[str], workers: int = 6, max_samples: Optional[int] = None) -> List[np.ndarray]:
+    """Thread pool over ``read_audio_pcm16`` (the ctypes call into the FLAC decoder releases the GIL); order preserved."""
+    if workers <= 1 or len(paths) < 2:
+        return [read_audio_pcm16(p, max_samples) for p in paths]
+    with cf.ThreadPoolExecutor(max_workers=workers) as ex:
+        return list(ex.map(lambda p: read_audio_pcm16(p, max_samples), paths))
+
+
 def decode_wav_files(paths: Sequence[str], workers: int = 6) -> List[np.ndarray]:
     """Thread pool over ``read_wav_pcm16`` (file reads and numpy release the GIL); order preserved."""
     if workers <= 1 or len(paths) < 2:
@@ -82,6 +135,12 @@ def write_pcm_shard(directory: str, utt_ids: Sequence[str], clips: Iterable[np.n
 
 def wav_files_to_shard(directory: str, utt_ids: Sequence[str], paths: Sequence[str], workers: int = 6) -> None:
     write_pcm_shard(directory, utt_ids, decode_wav_files(paths, workers))
+
+
+def audio_files_to_shard(directory: str, utt_ids: Sequence[str], paths: Sequence[str], workers: int = 6,
+                         max_samples: Optional[int] = 64600) -> None:
+    """FLAC / WAV corpus -> PCM shard holding the head of every clip (``max_samples``; None keeps whole clips)."""
+    write_pcm_shard(directory, utt_ids, decode_audio_files(paths, workers, max_samples))
 
 
 class PcmShard:

@@ -323,3 +323,121 @@ def test_wav_decode_and_pcm_shard_roundtrip(sls, tmp_path):
     np.save(os.path.join(d, "offsets.npy"), np.array([0, 5, 5], np.int64))
     with pytest.raises(sls.AudioFormatError):
         sls.PcmShard(d)
+
+
+# ---------------------------------------------------------------------------------------------------------------- FLAC
+# The three worked examples of RFC 9639 (appendix D): complete files with their STREAMINFO MD5 - the third-party known
+# answers of the native decoder (frame CRC-8 / CRC-16 and the MD5 are verified by the decoder itself on every call).
+RFC9639_EXAMPLES = {
+    "d1_verbatim_wasted_bits": (
+        "664c6143 80000022 1000 1000 00000f 00000f 0ac442f0 00000001 3e84b41807dc690307586a3dad1a2e0f"
+        "fff869180000bf 0358fd 03128b aa9a", 44100, 2, 16, [[25588, 10416]]),
+    "d2_fixed_rice_side_right_two_frames": (
+        "664c6143 00000022 0010 0010 000017 000044 0ac442f0 00000013 d5b0564975e98b8d8b930422757b8103"
+        "03000012 0000000000000000 0000000000000000 0010"
+        "0400003a 20000000 7265666572656e6365206c6962464c414320312e332e33203230313930383034 01000000 0e000000 5449544c453dd7a9d79cd795d79d"
+        "81000006 000000000000"
+        "fff86998000f99 1208670162 3d1442998f5df70d6fe00c17caeb21000ee7a77a24a1590c1217b603097b784faa9a33d285e070ad5b1b4851b4010d99d2cd1a68f1e6 b810"
+        "fff869180102a4 02c382c40bc14a 03ee48dd03b67c 1330", 44100, 2, 16,
+        [[10372, 6070], [18041, 10545], [14942, 8743], [17876, 10449], [15627, 9143], [17899, 10463], [16242, 9502], [18077, 10569],
+         [16824, 9840], [18263, 10680], [17295, 10113], [-14418, -8428], [-15201, -8895], [-14508, -8476], [-15195, -8896],
+         [-14818, -8653], [-15486, -9072], [-15349, -8958], [-16054, -9410]]),
+    "d3_lpc_8bit": (
+        "664c6143 80000022 1000 1000 00001f 00001f 07d00070 00000018 f8f9e396f5cbcfc6dc807f9977906b32"
+        "fff868020017e9 44004f6f313d1047d227cb6d090831452bdc28222280 57a3", 32000, 1, 8,
+        [[v] for v in (0, 79, 111, 78, 8, -61, -90, -68, -13, 42, 67, 53, 13, -27, -46, -38, -12, 14, 24, 19, 6, -4, -5, 0)]),
+}
+
+
+def _flac_decode(lib, data, max_samples=0, verify=1):
+    import ctypes as C
+    buf = np.frombuffer(data, dtype=np.uint8)
+    info = (C.c_int32 * 6)()
+    cap = 1 << 21
+    out = np.empty(cap, dtype=np.int32)
+    n = lib.slsb_flac_decode(buf.ctypes.data, buf.size, max_samples, verify, out.ctypes.data, cap, info)
+    ch = max(int(info[1]), 1)
+    return int(n), list(info), (out[:n * ch].reshape(n, ch).copy() if n > 0 else None)
+
+
+@pytest.mark.parametrize("name", sorted(RFC9639_EXAMPLES))
+def test_flac_decoder_rfc9639_examples(lib, name):
+    hexs, rate, ch, bps, want = RFC9639_EXAMPLES[name]
+    data = bytes.fromhex(hexs.replace(" ", ""))
+    n, info, pcm = _flac_decode(lib, data)
+    assert n == len(want) and info[:4] == [rate, ch, bps, len(want)] and info[4] == 1        # MD5 of STREAMINFO verified
+    assert pcm.tolist() == want
+    bad = bytearray(data)
+    bad[-5] ^= 0x10                                                                            # a flipped payload bit
+    assert _flac_decode(lib, bytes(bad))[0] in (-6, -3, -4, -7)
+    assert _flac_decode(lib, data[:-3])[0] == -3
+    assert _flac_decode(lib, b"RIFF" + data[4:])[0] == -2
+
+
+def test_flac_decoder_every_syntax_element_against_test_encoder(sls, lib):
+    """CONSTANT / VERBATIM / FIXED 0-4 / LPC up to order 32, Rice methods 0 and 1, partition orders, escape partitions, wasted
+    bits, all four stereo modes, odd block sizes, multi-byte frame numbers: decode(encode(x)) == x with CRCs and MD5 verified;
+    early stop returns the head; corrupted streams are rejected."""
+    import flac_enc
+    rs = np.random.RandomState(0)
+    t = np.arange(20000)
+    mono = (8000 * np.sin(t * 0.05) + rs.randn(t.size) * 300).astype(np.int64)
+    stereo = np.stack([mono, (mono * 0.8 + rs.randn(t.size) * 100).astype(np.int64)], 1)
+    cases = [dict(kind="verbatim"), dict(kind="fixed0"), dict(kind="fixed1", porder=1), dict(kind="fixed2", porder=3),
+             dict(kind="fixed3", porder=4, method=1), dict(kind="fixed4", porder=2, escape_partitions=(1, 3)),
+             dict(kind="lpc8", porder=2), dict(kind="lpc32", porder=1, blocksize=1152), dict(kind="fixed2", blocksize=777),
+             dict(kind="fixed2", blocksize=16, extra_metadata=False), dict(kind="lpc4", with_md5=False)]
+    for kw in cases:
+        x = mono[:3000] if kw.get("blocksize") == 16 else mono                 # 188 frames: two-byte coded frame numbers
+        n, info, pcm = _flac_decode(lib, flac_enc.encode(x, **kw))
+        assert n == len(x) and np.array_equal(pcm[:, 0], x), kw
+        assert info[4] == (0 if kw.get("with_md5") is False else 1), kw
+    for mode in (None, 8, 9, 10):
+        n, info, pcm = _flac_decode(lib, flac_enc.encode(stereo, kind="lpc6", stereo=mode, porder=3))
+        assert n == len(stereo) and info[4] == 1 and np.array_equal(pcm, stereo), mode
+    # extremes: full-scale square wave (constant sub-blocks, large residuals), silence, wasted bits, 24-bit and 8-bit samples
+    sq = np.where((t // 50) % 2 == 0, 32767, -32768)
+    for x, kw in ((sq, dict(kind="fixed1", porder=2)), (np.zeros(5000, np.int64), dict(kind="constant")),
+                  ((mono >> 3) << 3, dict(kind="fixed2")), (mono * 200, dict(kind="lpc8", bps=24)), (mono >> 8, dict(kind="fixed2", bps=8))):
+        n, info, pcm = _flac_decode(lib, flac_enc.encode(x, **kw))
+        assert n == len(x) and info[4] == 1 and np.array_equal(pcm[:, 0], x), kw
+    data = flac_enc.encode(mono, kind="lpc8", porder=2)
+    n, info, pcm = _flac_decode(lib, data, max_samples=6460)
+    assert n == 6460 and info[4] == 0 and np.array_equal(pcm[:, 0], mono[:6460])            # early stop: head only, MD5 not checked
+    bad = bytearray(data)
+    bad[len(bad) // 2] ^= 0x01
+    assert _flac_decode(lib, bytes(bad))[0] < 0
+    md5_bad = bytearray(data)
+    md5_bad[4 + 4 + 18] ^= 0xFF                                                                # STREAMINFO MD5 field
+    assert _flac_decode(lib, bytes(md5_bad))[0] == -8 and _flac_decode(lib, bytes(md5_bad), verify=0)[0] == len(mono)
+
+
+def test_flac_files_to_shard_through_the_ingest_api(sls, tmp_path):
+    """read_flac_pcm16 / decode_audio_files / audio_files_to_shard: mono and stereo 16 kHz FLAC + a WAV, heads of 64 600 samples."""
+    import flac_enc
+    rs = np.random.RandomState(1)
+    clips = [(rs.randn(n) * 2000).astype(np.int16) for n in (70000, 12345, 64600)]
+    paths = []
+    for i, c in enumerate(clips[:2]):
+        paths.append(str(tmp_path / f"a{i}.flac"))
+        with open(paths[-1], "wb") as f:
+            f.write(flac_enc.encode(c.astype(np.int64), kind="fixed2", porder=2, rate=16000))
+    paths.append(str(tmp_path / "a2.wav"))
+    sls.write_wav_pcm16(paths[-1], clips[2])
+    assert np.array_equal(sls.read_flac_pcm16(paths[0]), clips[0])
+    assert np.array_equal(sls.read_flac_pcm16(paths[0], max_samples=64600), clips[0][:64600])
+    got = sls.decode_audio_files(paths, workers=3, max_samples=64600)
+    assert all(np.array_equal(g, c[:64600]) for g, c in zip(got, clips))
+    st = np.stack([clips[1].astype(np.int64), clips[1].astype(np.int64) + 3], 1)
+    mono = sls.decode_flac_bytes(flac_enc.encode(st, kind="fixed1", stereo=10))
+    tot = st.sum(1)
+    assert np.array_equal(mono, (np.sign(tot) * ((2 * np.abs(tot) + 2) // 4)).astype(np.int16))           # (2x + 3) / 2, halves away from zero
+    with pytest.raises(sls.AudioFormatError, match="16000 Hz"):
+        sls.decode_flac_bytes(flac_enc.encode(clips[1].astype(np.int64), rate=44100))
+    with pytest.raises(sls.AudioFormatError, match="16-bit"):
+        sls.decode_flac_bytes(flac_enc.encode(clips[1].astype(np.int64) >> 8, bps=8))
+    with pytest.raises(sls.AudioFormatError, match="not a FLAC"):
+        sls.decode_flac_bytes(b"OggS" + bytes(100))
+    sls.audio_files_to_shard(str(tmp_path / "sh"), ["a", "b", "c"], paths, workers=2)
+    sh = sls.PcmShard(str(tmp_path / "sh"))
+    assert [len(sh.clip(i)) for i in range(3)] == [64600, 12345, 64600] and np.array_equal(sh.clip(1), clips[1])
