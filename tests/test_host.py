@@ -1,6 +1,7 @@
 """CPU tests of the host side: C-ABI library loads and exports what include/slsb200.h declares, the drop-in
 ``Model`` has the reference's surface and state_dict keys, packing shapes, score-file format, sharding and the
 world_size-2 gather (gloo).  No compute entry point is called here (there is no GPU in the build container)."""
+import json
 import os
 import re
 import subprocess
@@ -441,3 +442,32 @@ def test_flac_files_to_shard_through_the_ingest_api(sls, tmp_path):
     sls.audio_files_to_shard(str(tmp_path / "sh"), ["a", "b", "c"], paths, workers=2)
     sh = sls.PcmShard(str(tmp_path / "sh"))
     assert [len(sh.clip(i)) for i in range(3)] == [64600, 12345, 64600] and np.array_equal(sh.clip(1), clips[1])
+
+
+def test_score_files_tool_decode_stage(sls, tmp_path):
+    """tools/score_files.py --shard-only (no GPU): trial list + <dir>/flac/<utt>.flac -> the rank's PCM shard, in protocol order,
+    heads of 64 600 samples; two ranks split the list like shard_range."""
+    import flac_enc
+    rs = np.random.RandomState(2)
+    utts = [f"DF_E_{2000011 + i}" for i in range(5)]
+    clips = [(rs.randn(n) * 1500).astype(np.int16) for n in (70000, 3000, 64600, 16000, 99)]
+    os.makedirs(tmp_path / "flac")
+    for u, c in zip(utts, clips):
+        with open(tmp_path / "flac" / f"{u}.flac", "wb") as f:
+            f.write(flac_enc.encode(c.astype(np.int64), kind="fixed2", porder=1, rate=16000))
+    (tmp_path / "trials.txt").write_text("\n".join(utts) + "\n")
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "score_files.py")
+    for world in (1, 2):
+        for rank in range(world):
+            env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+            r = subprocess.run([sys.executable, tool, "--protocol", str(tmp_path / "trials.txt"), "--audio-dir", str(tmp_path), "--shard-only",
+                                "--out", str(tmp_path / f"score{world}.txt"), "--workers", "2"], capture_output=True, text=True, env=env, timeout=300)
+            assert r.returncode == 0, r.stderr[-2000:]
+            rec = json.loads(r.stdout.strip().splitlines()[-1])
+            lo, hi = sls.shard_range(len(utts), rank, world)
+            sh = sls.PcmShard(rec["shard"])
+            assert rec["trials"] == hi - lo and sh.utt_ids == utts[lo:hi]
+            assert all(np.array_equal(sh.clip(i - lo), clips[i][:64600]) for i in range(lo, hi))
+    r = subprocess.run([sys.executable, tool, "--protocol", str(tmp_path / "trials.txt"), "--audio-dir", str(tmp_path / "nowhere"), "--shard-only",
+                        "--out", str(tmp_path / "x.txt")], capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "missing" in r.stderr
