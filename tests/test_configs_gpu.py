@@ -212,3 +212,33 @@ def test_score_pcm_shard_equals_float_host_path(sls, cuda, tmp_path):
     assert torch.equal(sls.score_pcm_shard(m, shard, batch=64), got)
     assert torch.equal(sls.score_pcm_shard(m, shard, batch=2, lo=2, hi=6), got[2:6])
     assert torch.isfinite(got).all() and float(got.min()) > 0 and float(got.max()) < 1
+
+
+def test_score_files_tool_end_to_end(sls, cuda, tmp_path):
+    """A1 -> A18 on files: FLAC corpus + trial list -> tools/score_files.py -> score.txt in protocol order with the scores of the
+    in-process path (same seed-1234 random-init 2-layer model), and an EER against a trial_metadata-style key file."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import flac_enc
+    rs = np.random.RandomState(4)
+    utts = [f"DF_E_{3000000 + i}" for i in range(6)]
+    clips = [(rs.randn(n) * 2500).astype(np.int16) for n in (64600, 70000, 8000, 32000, 64601, 500)]
+    os.makedirs(tmp_path / "flac")
+    for u, c in zip(utts, clips):
+        with open(tmp_path / "flac" / f"{u}.flac", "wb") as f:
+            f.write(flac_enc.encode(c.astype(np.int64), kind="fixed2", porder=2, rate=16000))
+    (tmp_path / "trials.txt").write_text("\n".join(utts) + "\n")
+    (tmp_path / "keys.txt").write_text("".join(f"LA_00{i} {u} nocodec asvspoof A14 {'bonafide' if i % 2 else 'spoof'} notrim eval\n"
+                                               for i, u in enumerate(utts)))
+    out = tmp_path / "score.txt"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "score_files.py"), "--protocol", str(tmp_path / "trials.txt"),
+                        "--audio-dir", str(tmp_path), "--head", "sls", "--layers", "2", "--batch", "4", "--out", str(out),
+                        "--keys", str(tmp_path / "keys.txt")], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    rec = json.loads(r.stdout.strip().splitlines()[-1])
+    ids, scores = sls.read_score_file(str(out))
+    assert ids == utts and rec["trials"] == 6 and rec["scored_with_keys"] == 6 and 0.0 <= rec["eer"] <= 1.0
+    torch.manual_seed(1234)
+    m = sls.ModelSLS(None, cuda, cp_path=None, precision="bf16", geometry=sls.TrunkGeometry(layers=2)).to(cuda).eval()
+    want = m.engine().score_pcm16_host([torch.from_numpy(c) for c in clips], sls.HEAD_SLS, sls.PREC_BF16)
+    assert np.array_equal(scores.astype(np.float32), want.numpy())           # repr(float) round-trips float32 exactly
