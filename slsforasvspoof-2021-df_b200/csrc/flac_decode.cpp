@@ -58,7 +58,7 @@ struct BitReader {
     inline void align() { const int r = cnt & 7; win <<= r; cnt -= r; }   // `next * 8` is byte aligned, so cnt mod 8 = bits left in the current byte
 };
 
-uint8_t crc8_table[256]; uint16_t crc16_table[256]; bool tables_ready = false;
+uint8_t crc8_table[256]; uint16_t crc16_table[256]; uint16_t crc16_slice[8][256]; bool tables_ready = false;
 void init_tables() {
     if (tables_ready) return;
     for (int i = 0; i < 256; ++i) {
@@ -66,10 +66,24 @@ void init_tables() {
         for (int b = 0; b < 8; ++b) { c = (uint8_t)((c & 0x80) ? ((c << 1) ^ 0x07) : (c << 1)); d = (uint16_t)((d & 0x8000) ? ((d << 1) ^ 0x8005) : (d << 1)); }
         crc8_table[i] = c; crc16_table[i] = d;
     }
+    // slicing-by-8: slice[k][b] = CRC of byte b followed by k zero bytes
+    for (int i = 0; i < 256; ++i) {
+        uint16_t c = crc16_table[i];
+        crc16_slice[0][i] = c;
+        for (int k = 1; k < 8; ++k) { c = (uint16_t)((c << 8) ^ crc16_table[c >> 8]); crc16_slice[k][i] = c; }
+    }
     tables_ready = true;
 }
 uint8_t crc8(const uint8_t* p, int64_t n) { uint8_t c = 0; for (int64_t i = 0; i < n; ++i) c = crc8_table[c ^ p[i]]; return c; }
-uint16_t crc16(const uint8_t* p, int64_t n) { uint16_t c = 0; for (int64_t i = 0; i < n; ++i) c = (uint16_t)((c << 8) ^ crc16_table[(c >> 8) ^ p[i]]); return c; }
+uint16_t crc16(const uint8_t* p, int64_t n) {
+    uint16_t c = 0;
+    int64_t i = 0;
+    for (; i + 8 <= n; i += 8)
+        c = (uint16_t)(crc16_slice[7][p[i] ^ (c >> 8)] ^ crc16_slice[6][p[i + 1] ^ (c & 0xFF)] ^ crc16_slice[5][p[i + 2]] ^ crc16_slice[4][p[i + 3]] ^
+                       crc16_slice[3][p[i + 4]] ^ crc16_slice[2][p[i + 5]] ^ crc16_slice[1][p[i + 6]] ^ crc16_slice[0][p[i + 7]]);
+    for (; i < n; ++i) c = (uint16_t)((c << 8) ^ crc16_table[(c >> 8) ^ p[i]]);
+    return c;
+}
 
 // ---- MD5 (RFC 1321) of the interleaved little-endian PCM, as STREAMINFO stores it ----
 struct Md5 {
@@ -100,6 +114,7 @@ struct Md5 {
     }
     void update(const uint8_t* p, size_t n) {
         len += n;
+        if (fill == 0) { while (n >= 64) { block(p); p += 64; n -= 64; } }
         while (n > 0) {
             const size_t take = (size_t)(64 - fill) < n ? (size_t)(64 - fill) : n;
             memcpy(buf + fill, p, take); fill += (int)take; p += take; n -= take;
@@ -138,8 +153,17 @@ int read_residual(BitReader& br, int32_t* res, int blocksize, int order) {
             for (int j = 0; j < count; ++j) res[i++] = raw ? br.sbits(raw) : 0;
         } else {
             for (int j = 0; j < count; ++j) {
-                const uint32_t q = br.unary();
-                const uint32_t u = (q << k) | (k ? br.bits(k) : 0u);
+                uint32_t u;
+                if (br.cnt < 48) br.refill();
+                const int lead = br.win ? __builtin_clzll(br.win) : 64;
+                if (lead + 1 + k <= br.cnt && lead + 1 + k < 64) {      // whole code word inside the window: one step
+                    const uint64_t w = br.win << (lead + 1);
+                    u = ((uint32_t)lead << k) | (k ? (uint32_t)(w >> (64 - k)) : 0u);
+                    br.win = w << k; br.cnt -= lead + 1 + k;
+                } else {
+                    const uint32_t q = br.unary();
+                    u = (q << k) | (k ? br.bits(k) : 0u);
+                }
                 res[i++] = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);       // zig-zag: even -> u / 2, odd -> -(u + 1) / 2
             }
         }
@@ -198,7 +222,10 @@ int read_subframe(BitReader& br, int64_t* out, int blocksize, int bps) {
     return FLAC_OK;
 }
 
-struct Decoded { StreamInfo si; std::vector<int32_t> pcm; int64_t samples = 0; bool md5_checked = false; };   // pcm interleaved
+struct Decoded {
+    StreamInfo si; std::vector<int32_t> pcm; int64_t samples = 0; bool md5_checked = false;   // pcm interleaved
+    int16_t* mono16 = nullptr; int64_t mono16_cap = 0;    // optional direct sink: channel mean as int16 (16-bit streams), `pcm` stays empty
+};
 
 int decode(const uint8_t* data, int64_t n, int64_t max_samples, bool verify_md5, Decoded& d, bool info_only = false) {
     init_tables();
@@ -233,9 +260,10 @@ int decode(const uint8_t* data, int64_t n, int64_t max_samples, bool verify_md5,
     const bool whole = d.si.total == 0 || want >= d.si.total;
     const size_t stride = (size_t)(d.si.max_block > 16 ? d.si.max_block : 16);
     std::vector<int64_t> chan((size_t)ch * stride);
-    if (want != INT64_MAX) d.pcm.reserve((size_t)want * ch);
+    if (want != INT64_MAX && !d.mono16) d.pcm.reserve((size_t)want * ch);
     if (info_only) return FLAC_OK;
     Md5 md5;
+    std::vector<uint8_t> md5_buf;
     d.pcm.clear();
     d.samples = 0;
     while (pos < n && d.samples < want) {
@@ -289,18 +317,38 @@ int decode(const uint8_t* data, int64_t n, int64_t max_samples, bool verify_md5,
         }
         // ---------------- output (+ MD5 over the whole stream when it is decoded completely) ----------------
         const int64_t take = blocksize < want - d.samples ? blocksize : want - d.samples;
-        const size_t base = d.pcm.size();
-        d.pcm.resize(base + (size_t)take * ch);
-        for (int64_t i = 0; i < take; ++i)
-            for (int c = 0; c < ch; ++c) d.pcm[base + (size_t)i * ch + c] = (int32_t)chan[(size_t)c * stride + i];
+        if (d.mono16) {
+            if (bps != 16) return FLAC_E_UNSUPPORTED;
+            if (d.samples + take > d.mono16_cap) return FLAC_E_ARG;
+            int16_t* o = d.mono16 + d.samples;
+            if (ch == 1) {
+                for (int64_t i = 0; i < take; ++i) o[i] = (int16_t)chan[(size_t)i];
+            } else {
+                for (int64_t i = 0; i < take; ++i) {
+                    int64_t sum = 0;
+                    for (int c = 0; c < ch; ++c) sum += chan[(size_t)c * stride + i];
+                    const int64_t a = sum < 0 ? -sum : sum, r = (2 * a + ch) / (2 * ch);     // mean over channels, halves away from zero (as ingest.read_wav_pcm16)
+                    o[i] = (int16_t)(sum < 0 ? -r : r);
+                }
+            }
+        } else {
+            const size_t base = d.pcm.size();
+            d.pcm.resize(base + (size_t)take * ch);
+            for (int64_t i = 0; i < take; ++i)
+                for (int c = 0; c < ch; ++c) d.pcm[base + (size_t)i * ch + c] = (int32_t)chan[(size_t)c * stride + i];
+        }
         if (whole && verify_md5) {
             const int bytes = (bps + 7) / 8;
-            uint8_t tmp[8 * 4];
-            for (int64_t i = 0; i < take; ++i) {
-                int k = 0;
-                for (int c = 0; c < ch; ++c) { const int32_t v = (int32_t)chan[(size_t)c * stride + i]; for (int b = 0; b < bytes; ++b) tmp[k++] = (uint8_t)((uint32_t)v >> (8 * b)); }
-                md5.update(tmp, (size_t)k);
+            md5_buf.resize((size_t)take * ch * bytes);
+            uint8_t* t = md5_buf.data();
+            if (bytes == 2 && ch == 1) {
+                for (int64_t i = 0; i < take; ++i) { const uint32_t v = (uint32_t)chan[(size_t)i]; t[2 * i] = (uint8_t)v; t[2 * i + 1] = (uint8_t)(v >> 8); }
+            } else {
+                size_t k = 0;
+                for (int64_t i = 0; i < take; ++i)
+                    for (int c = 0; c < ch; ++c) { const uint32_t v = (uint32_t)chan[(size_t)c * stride + i]; for (int b = 0; b < bytes; ++b) t[k++] = (uint8_t)(v >> (8 * b)); }
             }
+            md5.update(md5_buf.data(), md5_buf.size());
         }
         d.samples += take;
     }
@@ -340,21 +388,12 @@ int64_t slsb_flac_decode(const uint8_t* data, int64_t nbytes, int64_t max_sample
 
 int64_t slsb_flac_decode_mono16(const uint8_t* data, int64_t nbytes, int64_t max_samples, int verify_md5, int16_t* pcm_out,
                                 int64_t pcm_capacity, int32_t* sample_rate) {
-    if (!data || nbytes <= 0 || !pcm_out) return FLAC_E_ARG;
+    if (!data || nbytes <= 0 || !pcm_out || pcm_capacity < 0) return FLAC_E_ARG;
     Decoded d;
+    d.mono16 = pcm_out; d.mono16_cap = pcm_capacity;
     const int rc = decode(data, nbytes, max_samples, verify_md5 != 0, d);
     if (sample_rate) *sample_rate = d.si.rate;
     if (rc != FLAC_OK) return rc;
-    if (d.si.bps != 16) return FLAC_E_UNSUPPORTED;
-    if (d.samples > pcm_capacity) return FLAC_E_ARG;
-    const int ch = d.si.channels;
-    for (int64_t i = 0; i < d.samples; ++i) {
-        if (ch == 1) { pcm_out[i] = (int16_t)d.pcm[(size_t)i]; continue; }
-        int64_t s = 0;
-        for (int c = 0; c < ch; ++c) s += d.pcm[(size_t)i * ch + c];
-        const int64_t a = s < 0 ? -s : s, r = (2 * a + ch) / (2 * ch);     // mean over channels, halves away from zero (as ingest.read_wav_pcm16)
-        pcm_out[i] = (int16_t)(s < 0 ? -r : r);
-    }
     return d.samples;
 }
 
