@@ -9,6 +9,7 @@
 // samples per channel - a 10-second utterance costs the decode of its first 4 seconds.
 #include <cstdint>
 #include <cstring>
+#include <new>
 #include <vector>
 
 #include "../../include/slsb200.h"
@@ -209,10 +210,10 @@ int read_subframe(BitReader& br, int64_t* out, int blocksize, int bps) {
         std::vector<int32_t> res((size_t)blocksize);
         const int rc = read_residual(br, res.data() + order, blocksize, order);
         if (rc != FLAC_OK) return rc;
-        for (int i = order; i < blocksize; ++i) {
-            int64_t acc = 0;
-            for (int j = 0; j < order; ++j) acc += (int64_t)coef[j] * out[i - 1 - j];
-            out[i] = (acc >> shift) + res[i];
+        for (int i = order; i < blocksize; ++i) {        // unsigned accumulation: corrupt streams may wrap, valid ones never get near 2^63
+            uint64_t acc = 0;
+            for (int j = 0; j < order; ++j) acc += (uint64_t)(int64_t)coef[j] * (uint64_t)out[i - 1 - j];
+            out[i] = (int64_t)((uint64_t)((int64_t)acc >> shift) + (uint64_t)(int64_t)res[i]);
         }
     } else {
         return FLAC_E_RESERVED;
@@ -260,7 +261,7 @@ int decode(const uint8_t* data, int64_t n, int64_t max_samples, bool verify_md5,
     const bool whole = d.si.total == 0 || want >= d.si.total;
     const size_t stride = (size_t)(d.si.max_block > 16 ? d.si.max_block : 16);
     std::vector<int64_t> chan((size_t)ch * stride);
-    if (want != INT64_MAX && !d.mono16) d.pcm.reserve((size_t)want * ch);
+    if (want != INT64_MAX && !d.mono16) d.pcm.reserve((size_t)(want < (1 << 24) ? want : (1 << 24)) * ch);   // STREAMINFO is untrusted input
     if (info_only) return FLAC_OK;
     Md5 md5;
     std::vector<uint8_t> md5_buf;
@@ -309,11 +310,11 @@ int decode(const uint8_t* data, int64_t n, int64_t max_samples, bool verify_md5,
         if (crc16(data + pos, body) != (uint16_t)((data[pos + body] << 8) | data[pos + body + 1])) return FLAC_E_CRC16;
         pos += body + 2;
         int64_t* L = chan.data(); int64_t* R = chan.data() + stride;
-        if (ch_code == 8) for (int i = 0; i < blocksize; ++i) R[i] = L[i] - R[i];                       // left / side
-        else if (ch_code == 9) for (int i = 0; i < blocksize; ++i) L[i] = L[i] + R[i];                  // side / right
+        if (ch_code == 8) for (int i = 0; i < blocksize; ++i) R[i] = (int64_t)((uint64_t)L[i] - (uint64_t)R[i]);          // left / side
+        else if (ch_code == 9) for (int i = 0; i < blocksize; ++i) L[i] = (int64_t)((uint64_t)L[i] + (uint64_t)R[i]);     // side / right
         else if (ch_code == 10) for (int i = 0; i < blocksize; ++i) {                                   // mid / side
-            const int64_t s = R[i], m = (L[i] << 1) | (s & 1);
-            L[i] = (m + s) >> 1; R[i] = (m - s) >> 1;
+            const uint64_t s = (uint64_t)R[i], m = ((uint64_t)L[i] << 1) | (s & 1);
+            L[i] = (int64_t)(m + s) >> 1; R[i] = (int64_t)(m - s) >> 1;
         }
         // ---------------- output (+ MD5 over the whole stream when it is decoded completely) ----------------
         const int64_t take = blocksize < want - d.samples ? blocksize : want - d.samples;
@@ -375,7 +376,8 @@ int64_t slsb_flac_decode(const uint8_t* data, int64_t nbytes, int64_t max_sample
                          int32_t* info) {
     if (!data || nbytes <= 0 || !info) return FLAC_E_ARG;
     Decoded d;
-    const int rc = decode(data, nbytes, max_samples, verify_md5 != 0, d, pcm_out == nullptr);
+    int rc;
+    try { rc = decode(data, nbytes, max_samples, verify_md5 != 0, d, pcm_out == nullptr); } catch (const std::bad_alloc&) { rc = FLAC_E_ARG; }
     info[0] = d.si.rate; info[1] = d.si.channels; info[2] = d.si.bps; info[3] = (int32_t)(d.si.total & 0x7fffffff);
     info[4] = d.md5_checked ? 1 : 0; info[5] = (int32_t)(d.si.total >> 31);
     if (rc != FLAC_OK) return rc;
@@ -391,7 +393,8 @@ int64_t slsb_flac_decode_mono16(const uint8_t* data, int64_t nbytes, int64_t max
     if (!data || nbytes <= 0 || !pcm_out || pcm_capacity < 0) return FLAC_E_ARG;
     Decoded d;
     d.mono16 = pcm_out; d.mono16_cap = pcm_capacity;
-    const int rc = decode(data, nbytes, max_samples, verify_md5 != 0, d);
+    int rc;
+    try { rc = decode(data, nbytes, max_samples, verify_md5 != 0, d); } catch (const std::bad_alloc&) { rc = FLAC_E_ARG; }
     if (sample_rate) *sample_rate = d.si.rate;
     if (rc != FLAC_OK) return rc;
     return d.samples;

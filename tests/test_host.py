@@ -471,3 +471,40 @@ def test_score_files_tool_decode_stage(sls, tmp_path):
     r = subprocess.run([sys.executable, tool, "--protocol", str(tmp_path / "trials.txt"), "--audio-dir", str(tmp_path / "nowhere"), "--shard-only",
                         "--out", str(tmp_path / "x.txt")], capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "missing" in r.stderr
+
+
+def test_flac_decoder_survives_corrupted_streams(lib):
+    """Untrusted input: bit flips, byte substitutions, truncations and absurd STREAMINFO fields either decode (when the damage
+    missed everything that is checked) or return an error code - never crash, never write past the output buffer."""
+    import flac_enc
+    rs = np.random.RandomState(7)
+    x = (rs.randn(9000) * 4000).astype(np.int64)
+    streams = [flac_enc.encode(x, kind="lpc8", porder=3, blocksize=1024), flac_enc.encode(np.stack([x, x // 2], 1), kind="fixed3", stereo=10, porder=2),
+               bytes.fromhex(RFC9639_EXAMPLES["d2_fixed_rice_side_right_two_frames"][0].replace(" ", ""))]
+    guard = 64
+    ok = err = 0
+    for data in streams:
+        for trial in range(150):
+            bad = bytearray(data)
+            kind = trial % 3
+            if kind == 0:
+                for _ in range(1 + trial % 4):
+                    bad[rs.randint(4, len(bad))] ^= 1 << rs.randint(8)
+            elif kind == 1:
+                pos = rs.randint(4, len(bad))
+                bad[pos:pos + rs.randint(1, 9)] = bytes(rs.randint(0, 256, size=rs.randint(1, 9)).tolist())
+            else:
+                bad = bad[:rs.randint(5, len(bad))]
+            buf = np.frombuffer(bytes(bad), dtype=np.uint8)
+            out = np.full(len(x) + guard, 12345, dtype=np.int16)
+            n = lib.slsb_flac_decode_mono16(buf.ctypes.data, buf.size, 0, 1, out.ctypes.data, len(x), None)
+            assert n <= len(x) and (out[len(x):] == 12345).all()
+            ok, err = ok + (n >= 0), err + (n < 0)
+    assert err > 300 and ok + err == 450                       # almost every mutation is caught by a CRC, the MD5 or a syntax check
+    huge = bytearray(streams[0])
+    huge[4 + 4 + 13] |= 0x0F                                   # total samples: top bits of the 36-bit field
+    huge[4 + 4 + 14:4 + 4 + 18] = b"\xff\xff\xff\xff"
+    buf = np.frombuffer(bytes(huge), dtype=np.uint8)
+    info = (__import__("ctypes").c_int32 * 6)()
+    out32 = np.empty(1 << 16, dtype=np.int32)
+    assert lib.slsb_flac_decode(buf.ctypes.data, buf.size, 0, 1, out32.ctypes.data, out32.size, info) < 0
