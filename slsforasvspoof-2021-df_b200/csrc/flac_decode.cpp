@@ -230,6 +230,12 @@ struct Decoded {
 
 int decode(const uint8_t* data, int64_t n, int64_t max_samples, bool verify_md5, Decoded& d, bool info_only = false) {
     init_tables();
+    if (n >= 10 && memcmp(data, "ID3", 3) == 0) {           // an ID3v2 tag some taggers put in front of the stream: 10-byte header, sync-safe size
+        const int64_t sz = ((int64_t)(data[6] & 0x7f) << 21) | ((int64_t)(data[7] & 0x7f) << 14) | ((int64_t)(data[8] & 0x7f) << 7) | (data[9] & 0x7f);
+        const int64_t skip = 10 + sz + ((data[5] & 0x10) ? 10 : 0);
+        if (skip >= n) return FLAC_E_TRUNC;
+        data += skip; n -= skip;
+    }
     if (n < 42 || memcmp(data, "fLaC", 4) != 0) return FLAC_E_MAGIC;
     int64_t pos = 4; bool last = false, have_si = false;
     while (!last) {
@@ -270,7 +276,10 @@ int decode(const uint8_t* data, int64_t n, int64_t max_samples, bool verify_md5,
     while (pos < n && d.samples < want) {
         // ---------------- frame header ----------------
         if (pos + 5 > n) return FLAC_E_TRUNC;
-        if (data[pos] != 0xFF || (data[pos + 1] & 0xFE) != 0xF8) return FLAC_E_HEADER;
+        if (data[pos] != 0xFF || (data[pos + 1] & 0xFE) != 0xF8) {
+            if (d.si.total == 0 && d.samples > 0) break;     // stream of unknown length followed by something else (e.g. an ID3v1 tag)
+            return FLAC_E_HEADER;
+        }
         BitReader br(data + pos, n - pos);
         br.bits(15);
         br.bits(1);                                          // blocking strategy: the sample position is not needed for a sequential decode

@@ -403,6 +403,9 @@ def test_flac_decoder_every_syntax_element_against_test_encoder(sls, lib):
         n, info, pcm = _flac_decode(lib, flac_enc.encode(x, **kw))
         assert n == len(x) and info[4] == 1 and np.array_equal(pcm[:, 0], x), kw
     data = flac_enc.encode(mono, kind="lpc8", porder=2)
+    tagged = b"ID3\x04\x00\x00" + bytes([0, 0, 1, 5]) + bytes(133) + data + b"TAG" + bytes(125)       # ID3v2 in front (133 bytes), ID3v1 behind
+    n, info, pcm = _flac_decode(lib, tagged)
+    assert n == len(mono) and info[4] == 1 and np.array_equal(pcm[:, 0], mono)
     n, info, pcm = _flac_decode(lib, data, max_samples=6460)
     assert n == 6460 and info[4] == 0 and np.array_equal(pcm[:, 0], mono[:6460])            # early stop: head only, MD5 not checked
     bad = bytearray(data)
