@@ -511,3 +511,33 @@ def test_flac_decoder_survives_corrupted_streams(lib):
     info = (__import__("ctypes").c_int32 * 6)()
     out32 = np.empty(1 << 16, dtype=np.int32)
     assert lib.slsb_flac_decode(buf.ctypes.data, buf.size, 0, 1, out32.ctypes.data, out32.size, info) < 0
+
+
+def test_eval_datasets_mirror_the_reference(sls, tmp_path):
+    """data_utils_SSL.py surface on the native decoders: genSpoof_list's three branches, Dataset_ASVspoof2021_eval
+    (<base>/flac/<utt>.flac) and Dataset_in_the_wild_eval (<base><file>) return (float32 [64600], utt_id) equal to the
+    reference's int16 / 32768 -> pad(); they collate through a DataLoader like main.py:161-165 uses them."""
+    import flac_enc
+    rs = np.random.RandomState(9)
+    utts = ["DF_E_2000011", "DF_E_2000013", "DF_E_2000024"]
+    clips = [(rs.randn(n) * 3000).astype(np.int16) for n in (80000, 64600, 20001)]
+    os.makedirs(tmp_path / "flac")
+    for u, c in zip(utts, clips):
+        (tmp_path / "flac" / f"{u}.flac").write_bytes(flac_enc.encode(c.astype(np.int64), kind="lpc8", porder=3, rate=16000))
+    (tmp_path / "eval.txt").write_text("".join(u + "\n" for u in utts))
+    (tmp_path / "train.txt").write_text("LA_0079 LA_T_1138215 - - bonafide\nLA_0079 LA_T_1271820 - A01 spoof\n")
+    assert sls.genSpoof_list(str(tmp_path / "eval.txt"), is_train=False, is_eval=True) == utts
+    labels, keys = sls.genSpoof_list(str(tmp_path / "train.txt"), is_train=True, is_eval=False)
+    assert keys == ["LA_T_1138215", "LA_T_1271820"] and labels == {"LA_T_1138215": 1, "LA_T_1271820": 0}
+    assert sls.genSpoof_list(str(tmp_path / "train.txt")) == (labels, keys)
+    ds = sls.Dataset_ASVspoof2021_eval(utts, str(tmp_path))
+    assert len(ds) == 3
+    for i, c in enumerate(clips):
+        x, u = ds[i]
+        assert u == utts[i] and x.dtype == torch.float32 and x.shape == (64600,)
+        assert np.array_equal(x.numpy(), sls.pad(c.astype(np.float32) / np.float32(32768.0)))
+    xb, ub = next(iter(torch.utils.data.DataLoader(ds, batch_size=3, shuffle=False, drop_last=False)))
+    assert xb.shape == (3, 64600) and list(ub) == utts
+    sls.write_wav_pcm16(str(tmp_path / "wild_7.wav"), clips[2])
+    x, u = sls.Dataset_in_the_wild_eval(["wild_7.wav"], str(tmp_path) + "/")[0]
+    assert u == "wild_7.wav" and np.array_equal(x.numpy(), sls.pad(clips[2].astype(np.float32) / np.float32(32768.0)))
