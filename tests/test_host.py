@@ -541,3 +541,34 @@ def test_eval_datasets_mirror_the_reference(sls, tmp_path):
     sls.write_wav_pcm16(str(tmp_path / "wild_7.wav"), clips[2])
     x, u = sls.Dataset_in_the_wild_eval(["wild_7.wav"], str(tmp_path) + "/")[0]
     assert u == "wild_7.wav" and np.array_equal(x.numpy(), sls.pad(clips[2].astype(np.float32) / np.float32(32768.0)))
+
+
+def test_evaluate_2021_DF_tool_matches_oracle_eer(sls, tmp_path):
+    """tools/evaluate_2021_DF.py: the reference's CLI contract (3 arguments, trial-count / column checks, phase filter,
+    "eer: %.2f") with the EER of the pinned oracle restatement of eval_metrics_DF.compute_eer."""
+    from oracle.eer import compute_eer as oracle_eer
+    rs = np.random.RandomState(13)
+    n = 400
+    utts = [f"DF_E_{4000000 + i}" for i in range(n)]
+    bona = rs.rand(n) < 0.2
+    phase = np.where(rs.rand(n) < 0.7, "eval", "progress")
+    scores = np.where(bona, rs.beta(5, 2, n), rs.beta(2, 5, n))
+    scores[::17] = 0.5                                                  # ties
+    os.makedirs(tmp_path / "keys" / "CM")
+    (tmp_path / "keys" / "CM" / "trial_metadata.txt").write_text("".join(
+        f"LA_0009 {u} nocodec asvspoof A14 {'bonafide' if b else 'spoof'} notrim {p} traditional_vocoder - - - -\n" for u, b, p in zip(utts, bona, phase)))
+    sls.write_score_file(str(tmp_path / "score.txt"), utts, scores.tolist())
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "evaluate_2021_DF.py")
+    for ph in ("eval", "progress"):
+        r = subprocess.run([sys.executable, tool, str(tmp_path / "score.txt"), str(tmp_path / "keys"), ph], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-1500:]
+        m = phase == ph
+        want = oracle_eer(scores[m & bona], scores[m & ~bona])[0]
+        assert r.stdout.strip().splitlines()[-1] == "eer: %.2f" % (100 * want)
+    sls.write_score_file(str(tmp_path / "short.txt"), utts[:-1], scores[:-1].tolist())
+    r = subprocess.run([sys.executable, tool, str(tmp_path / "short.txt"), str(tmp_path / "keys"), "eval"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 1 and "CHECK: submission has 399 of 400 expected trials." in r.stdout
+    r = subprocess.run([sys.executable, tool, str(tmp_path / "score.txt"), str(tmp_path / "keys"), "dev"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 1 and "phase must be" in r.stdout
+    r = subprocess.run([sys.executable, tool, str(tmp_path / "score.txt")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 1 and "invalid input arguments" in r.stdout
