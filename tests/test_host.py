@@ -572,3 +572,36 @@ def test_evaluate_2021_DF_tool_matches_oracle_eer(sls, tmp_path):
     assert r.returncode == 1 and "phase must be" in r.stdout
     r = subprocess.run([sys.executable, tool, str(tmp_path / "score.txt")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 1 and "invalid input arguments" in r.stdout
+
+
+def test_c_abi_is_plain_c_and_callable_from_a_c_host(sls, tmp_path):
+    """The boundary is a C ABI: include/slsb200.h compiles as strict C99 (no C++ / torch types) and a C program linked against
+    libslsb200.so calls it - ABI version, the FLAC decoder on RFC 9639's first example, the GEMM schedule replay, and
+    slsb_create failing loudly without a GPU (no CPU fallback)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "host.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "slsb200.h"
+int main(void) {
+    static const unsigned char ex1[] = {0x66,0x4c,0x61,0x43,0x80,0x00,0x00,0x22,0x10,0x00,0x10,0x00,0x00,0x00,0x0f,0x00,0x00,0x0f,0x0a,0xc4,0x42,0xf0,
+        0x00,0x00,0x00,0x01,0x3e,0x84,0xb4,0x18,0x07,0xdc,0x69,0x03,0x07,0x58,0x6a,0x3d,0xad,0x1a,0x2e,0x0f,0xff,0xf8,0x69,0x18,0x00,0x00,0xbf,
+        0x03,0x58,0xfd,0x03,0x12,0x8b,0xaa,0x9a};
+    int32_t pcm[8], info[6], items[5 * 4096], split = 0;
+    int64_t n = slsb_flac_decode(ex1, (int64_t)sizeof ex1, 0, 1, pcm, 8, info);
+    int k = slsb_debug_pair_schedule(12864, 3072, 74, items, 4096, &split);
+    slsb_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    printf("abi=%d flac=%lld L=%d R=%d md5=%d items=%d split=%d\n", slsb_abi_version(), (long long)n, pcm[0], pcm[1], info[4], k, split);
+    return 0;
+}
+''')
+    exe = tmp_path / "host"
+    libdir = os.path.dirname(sls.LIB_PATH)
+    cc = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+                         "-L", libdir, "-l:" + os.path.basename(sls.LIB_PATH), "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.strip() == "abi=1 flac=1 L=25588 R=10416 md5=1 items=632 split=2"       # 8 x 74 whole tiles + 20 tiles x 2 slices
