@@ -181,16 +181,33 @@ class PcmShard:
 
 def score_pcm_shard(model, shard: PcmShard, batch: int = 64, samples: int = 64600, lo: int = 0, hi: Optional[int] = None) -> torch.Tensor:
     """Scores clips lo..hi-1 of a shard (a rank's ``shard_range``) with ``model`` (a ``Model`` / ``ModelSLS`` of this
-    package): ``exp(logp[:, 1])`` per clip, float32 CPU tensor, protocol order (main.py:178-192)."""
+    package): ``exp(logp[:, 1])`` per clip, float32 CPU tensor, protocol order (main.py:178-192).
+
+    Two pinned upload buffers: while the (synchronous, GIL-free) ``slsb_score_pcm16_host`` call of batch i runs, a helper thread
+    gathers batch i + 1 from the memory-mapped shard into the other buffer, so the device never waits for the page cache."""
     hi = len(shard) if hi is None else hi
     eng = model.engine()
     head, prec = model._head(), model._prec()
     out = torch.empty(max(hi - lo, 0), dtype=torch.float32)
-    stage = torch.empty(batch * samples, dtype=torch.int16, pin_memory=torch.cuda.is_available())     # one pinned upload buffer, re-used
-    for a in range(lo, hi, batch):
+    pin = torch.cuda.is_available()
+    stages = [torch.empty(batch * samples, dtype=torch.int16, pin_memory=pin) for _ in range(2)]
+    starts = list(range(lo, hi, batch))
+
+    def stage_batch(j):
+        a = starts[j]
         b = min(a + batch, hi)
         pcm, off, lens = shard.batch(a, b, max_samples=samples)
-        up = stage[:pcm.size]
+        up = stages[j & 1][:pcm.size]
         up.numpy()[:] = pcm                                       # the only host copy: memory-mapped shard -> pinned buffer
-        out[a - lo:b - lo] = eng.score_pcm16_arrays(up, torch.from_numpy(off), torch.from_numpy(lens), head, prec, samples)
+        return a, b, up, torch.from_numpy(off), torch.from_numpy(lens)
+
+    if not starts:
+        return out
+    with cf.ThreadPoolExecutor(max_workers=1) as ex:
+        nxt = ex.submit(stage_batch, 0)
+        for j in range(len(starts)):
+            a, b, up, off, lens = nxt.result()
+            if j + 1 < len(starts):
+                nxt = ex.submit(stage_batch, j + 1)              # fills the other buffer while this batch is on the device
+            out[a - lo:b - lo] = eng.score_pcm16_arrays(up, off, lens, head, prec, samples)
     return out

@@ -605,3 +605,38 @@ int main(void) {
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr
     assert r.stdout.strip() == "abi=1 flac=1 L=25588 R=10416 md5=1 items=632 split=2"       # 8 x 74 whole tiles + 20 tiles x 2 slices
+
+
+def test_score_pcm_shard_prefetch_keeps_order_and_buffers_apart(sls, tmp_path):
+    """Host logic of score_pcm_shard with a stand-in engine (no GPU): every batch reaches the scorer exactly once, in order, with
+    the (pcm, offsets, lens) of its own clips even though the next batch is being staged concurrently into the other buffer."""
+    import time as _time
+    rs = np.random.RandomState(21)
+    lens = rs.randint(50, 400, size=23).tolist()
+    clips = [rs.randint(-32768, 32768, size=n).astype(np.int16) for n in lens]
+    sls.write_pcm_shard(str(tmp_path / "s"), [f"u{i}" for i in range(len(clips))], clips)
+    shard = sls.PcmShard(str(tmp_path / "s"))
+    calls = []
+
+    class FakeEngine:
+        def score_pcm16_arrays(self, pcm, off, ln, head, prec, samples):
+            _time.sleep(0.01)                                   # let the prefetch of the next batch overlap this "forward"
+            got = [pcm[int(o):int(o) + int(n)].numpy().copy() for o, n in zip(off, ln)]
+            calls.append(got)
+            return torch.tensor([float(g.astype(np.int64).sum()) for g in got])
+
+    class FakeModel:
+        def engine(self): return FakeEngine()
+        def _head(self): return 3
+        def _prec(self): return 1
+
+    for batch, lo, hi, cut in ((4, 0, None, 300), (5, 3, 19, 100), (64, 0, None, 64600), (1, 20, 23, 64600)):
+        calls.clear()
+        out = sls.score_pcm_shard(FakeModel(), shard, batch=batch, samples=cut, lo=lo, hi=hi)
+        h = len(clips) if hi is None else hi
+        want = [clips[i][:cut] for i in range(lo, h)]
+        flat = [g for c in calls for g in c]
+        assert len(flat) == len(want) and all(np.array_equal(a, b) for a, b in zip(flat, want))
+        assert out.tolist() == [float(w.astype(np.int64).sum()) for w in want]
+        assert [len(c) for c in calls] == [min(batch, h - a) for a in range(lo, h, batch)]
+    assert sls.score_pcm_shard(FakeModel(), shard, lo=5, hi=5).numel() == 0
