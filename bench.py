@@ -238,9 +238,10 @@ def main():
     for i in range(3):
         eng.score_submit(host[i % n_pool], head, prec, out=outs[i % 4])
     eng.score_wait()
-    # the loop is host-timed, so one host hiccup (scheduler, page fault) lands in it: two passes, both reported, the faster one is `value`
+    # the loop is host-timed, so a host hiccup (scheduler, page fault) lands in it: three passes of K steps, all reported,
+    # `value` is the median pass
     e2e_passes = []
-    for _ in range(2):
+    for _ in range(3):
         barrier()
         t0 = time.perf_counter()
         for i in range(args.steps):
@@ -248,7 +249,7 @@ def main():
         eng.score_wait()
         torch.cuda.synchronize()
         e2e_passes.append(max_over_ranks((time.perf_counter() - t0) * 1e3))
-    e2e_ms = min(e2e_passes)
+    e2e_ms = sorted(e2e_passes)[1]
     assert all(bool(torch.isfinite(o).all()) for o in outs)
     # the un-pipelined loop (one synchronising slsb_score_host call per step) for comparison
     barrier()
