@@ -364,6 +364,92 @@ __global__ void __launch_bounds__(256) sls_fuse_pool_kernel(LayerPtrs L, int n_l
         for (int j = (int)gridDim.x * J + threadIdx.x; j < ldo; j += blockDim.x) out[(long long)b * ldo + j] = from_f32<TO>(0.f);
 }
 
+// ---- experimental (SLSB_POOL_TMA=1, bf16 layers, D = 1024; not validated on hardware yet - see DESIGN.md section 9) ----
+// The kernel above is long-scoreboard bound at 50 % occupancy (ncu: 3.8-4.2 TB/s): its bytes in flight live in registers.
+// Here a producer warp streams the 25 per-layer chunks of the block's 3 frames (3 x 2 KB, contiguous) through an 8-stage shared
+// memory ring with cp.async.bulk + mbarriers; 4 consumer warps accumulate w_l * x_l from shared memory (8 channels x 3 frames per
+// thread).  Same arithmetic order as sls_fuse_pool_kernel<bf16, TO, 8> => identical bits.
+constexpr int kPtStages = 8, kPtD = 1024, kPtChunk = 3 * kPtD * 2;
+constexpr int kPtSmem = kPtStages * kPtChunk + 3 * kPtD * 4 + 32 * 4 + 2 * kPtStages * 8;
+
+__device__ __forceinline__ void pool_bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(160) sls_fuse_pool_tma_kernel(LayerPtrs L, int n_layers, const float* __restrict__ layer_w, int T,
+                                                                const float* __restrict__ bn, float bn_eps, TO* __restrict__ out, int ldo) {
+    constexpr int D = kPtD;
+    extern __shared__ __align__(128) uint8_t pt_smem[];
+    float* fp = reinterpret_cast<float*>(pt_smem + kPtStages * kPtChunk);          // [3][D] pooled-input tile
+    float* lw = fp + 3 * D;                                                         // [32] layer weights of this utterance
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(lw + 32);
+    uint64_t* empty_bar = full_bar + kPtStages;
+    const int i = blockIdx.x, b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kPtStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 4); }
+        mbar_fence_init();
+    }
+    if (threadIdx.x < n_layers) lw[threadIdx.x] = layer_w[b * n_layers + threadIdx.x];
+    __syncthreads();
+    const long long off = ((long long)b * T + 3 * i) * D;
+    if (warp == 4) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int l = 0; l < n_layers; ++l) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_expect_tx(&full_bar[stage], kPtChunk);
+                pool_bulk_load(pt_smem + stage * kPtChunk, static_cast<const bf16*>(L.p[l]) + off, kPtChunk, &full_bar[stage]);
+                if (++stage == kPtStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        const int c = threadIdx.x * 8;
+        float s[3][8];
+#pragma unroll
+        for (int di = 0; di < 3; ++di)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s[di][e] = 0.f;
+        int stage = 0; uint32_t phase = 0;
+        for (int l = 0; l < n_layers; ++l) {
+            const float w = lw[l];
+            mbar_wait(&full_bar[stage], phase);
+            const uint8_t* chunk = pt_smem + stage * kPtChunk;
+#pragma unroll
+            for (int di = 0; di < 3; ++di) {
+                const uint4 q = *reinterpret_cast<const uint4*>(chunk + (di * D + c) * 2);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    s[di][2 * e] = fmaf(__low2float(h[e]), w, s[di][2 * e]);
+                    s[di][2 * e + 1] = fmaf(__high2float(h[e]), w, s[di][2 * e + 1]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            if (++stage == kPtStages) { stage = 0; phase ^= 1; }
+        }
+        const float g = bn[0] / sqrtf(bn[3] + bn_eps), beta = bn[1], rm = bn[2];
+#pragma unroll
+        for (int di = 0; di < 3; ++di)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) fp[di * D + c + e] = selu((s[di][e] - rm) * g + beta);
+    }
+    __syncthreads();
+    const int J = D / 3;
+    for (int j = threadIdx.x; j < J; j += blockDim.x) {
+        float m = -INFINITY;
+#pragma unroll
+        for (int di = 0; di < 3; ++di)
+#pragma unroll
+            for (int dj = 0; dj < 3; ++dj) m = fmaxf(m, fp[di * D + 3 * j + dj]);
+        out[(long long)b * ldo + i * J + j] = from_f32<TO>(m);
+    }
+    if (i == (int)gridDim.x - 1)
+        for (int j = (int)gridDim.x * J + threadIdx.x; j < ldo; j += blockDim.x) out[(long long)b * ldo + j] = from_f32<TO>(0.f);
+}
+
 // partial sums [B][KS][N] -> h = selu(sum + bias) -> fc3 -> selu -> log_softmax ; one block of 1024 threads per utterance
 // (one hidden unit per thread: the KS partials of a unit are read by consecutive threads -> coalesced rows of the partial matrix)
 __global__ void __launch_bounds__(1024) sls_tail_kernel(const float* __restrict__ partial, int KS, int Hd, const float* __restrict__ b1,
@@ -504,7 +590,17 @@ int sls_fuse_pool(const void* const* layers, int layers_bf16, int n_layers, cons
     const size_t sm = 3 * D * sizeof(float);
     // bf16 layers: 4 channels per thread (8-byte loads, D / 4 threads) measured faster in the step than 8 per thread (0.14 vs 0.17 ms)
     static const int vec8 = getenv("SLSB_POOL_VEC") ? atoi(getenv("SLSB_POOL_VEC")) == 8 : 0;
-    if (layers_bf16 && vec8) {
+    static const int pool_tma = getenv("SLSB_POOL_TMA") ? atoi(getenv("SLSB_POOL_TMA")) : 0;
+    if (layers_bf16 && pool_tma && D == kPtD) {
+        static bool configured = false;
+        if (!configured) {
+            SLSB_CUDA_CHECK(cudaFuncSetAttribute(sls_fuse_pool_tma_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPtSmem));
+            SLSB_CUDA_CHECK(cudaFuncSetAttribute(sls_fuse_pool_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPtSmem));
+            configured = true;
+        }
+        if (out_bf16) sls_fuse_pool_tma_kernel<bf16><<<grid, 160, kPtSmem, stream>>>(L, n_layers, layer_w, T, bn, bn_eps, static_cast<bf16*>(out), ldo);
+        else sls_fuse_pool_tma_kernel<float><<<grid, 160, kPtSmem, stream>>>(L, n_layers, layer_w, T, bn, bn_eps, static_cast<float*>(out), ldo);
+    } else if (layers_bf16 && vec8) {
         const int nt = D / 8 > 32 ? D / 8 : 32;
         if (out_bf16) sls_fuse_pool_kernel<bf16, bf16, 8><<<grid, nt, sm, stream>>>(L, n_layers, layer_w, T, D, bn, bn_eps, static_cast<bf16*>(out), ldo);
         else sls_fuse_pool_kernel<bf16, float, 8><<<grid, nt, sm, stream>>>(L, n_layers, layer_w, T, D, bn, bn_eps, static_cast<float*>(out), ldo);
