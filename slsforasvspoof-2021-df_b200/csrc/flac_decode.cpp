@@ -28,6 +28,16 @@ struct BitReader {
     bool fail = false;
     BitReader(const uint8_t* d, int64_t bytes) : p(d), n(bytes) {}
     inline void refill() {
+        if (next + 8 <= n) {                                   // one unaligned 8-byte load, whole bytes that fit are consumed
+            uint64_t v;
+            memcpy(&v, p + next, 8);
+            v = __builtin_bswap64(v);
+            const int take = (64 - cnt) >> 3;                  // bytes that fit above the `cnt` valid bits
+            if (take == 8) { win = v; }
+            else if (take > 0) { win |= (v >> (64 - 8 * take)) << (64 - cnt - 8 * take); }
+            next += take; cnt += 8 * take;
+            return;
+        }
         while (cnt <= 56 && next < n) { win |= (uint64_t)p[next++] << (56 - cnt); cnt += 8; }
     }
     inline uint32_t bits(int k) {                   // k in 0..32
@@ -153,24 +163,69 @@ int read_residual(BitReader& br, int32_t* res, int blocksize, int order) {
             const int raw = (int)br.bits(5);
             for (int j = 0; j < count; ++j) res[i++] = raw ? br.sbits(raw) : 0;
         } else {
+            // bit-reader state in locals for the hot loop (the int32 stores to `res` may alias the reader's members otherwise)
+            uint64_t win = br.win; int cnt = br.cnt; int64_t next = br.next;
+            const uint8_t* const p = br.p; const int64_t n = br.n;
             for (int j = 0; j < count; ++j) {
+                if (cnt <= 56 && next + 8 <= n) {                          // 8-byte refill, whole bytes only (taken on nearly every sample: predictable)
+                    uint64_t v;
+                    memcpy(&v, p + next, 8);
+                    v = __builtin_bswap64(v);
+                    const int take = (64 - cnt) >> 3;
+                    win |= (v >> (64 - 8 * take)) << (64 - cnt - 8 * take);   // cnt in 0..56 here, so take is 1..8 and both shifts are < 64
+                    next += take; cnt += 8 * take;
+                }
                 uint32_t u;
-                if (br.cnt < 48) br.refill();
-                const int lead = br.win ? __builtin_clzll(br.win) : 64;
-                if (lead + 1 + k <= br.cnt && lead + 1 + k < 64) {      // whole code word inside the window: one step
-                    const uint64_t w = br.win << (lead + 1);
+                const int lead = win ? __builtin_clzll(win) : 64;
+                if (lead + 1 + k <= cnt && lead + 1 + k < 64) {            // whole code word inside the window: one step
+                    const uint64_t w = win << (lead + 1);
                     u = ((uint32_t)lead << k) | (k ? (uint32_t)(w >> (64 - k)) : 0u);
-                    br.win = w << k; br.cnt -= lead + 1 + k;
-                } else {
+                    win = w << k; cnt -= lead + 1 + k;
+                } else {                                                    // long code word or end of data: the careful path
+                    br.win = win; br.cnt = cnt; br.next = next;
                     const uint32_t q = br.unary();
                     u = (q << k) | (k ? br.bits(k) : 0u);
+                    win = br.win; cnt = br.cnt; next = br.next;
                 }
-                res[i++] = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);       // zig-zag: even -> u / 2, odd -> -(u + 1) / 2
+                res[i++] = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);           // zig-zag: even -> u / 2, odd -> -(u + 1) / 2
             }
+            br.win = win; br.cnt = cnt; br.next = next;
         }
         if (br.fail) return FLAC_E_TRUNC;
     }
     return FLAC_OK;
+}
+
+// out[i] = res[i] + (sum_j coef[j] * out[i - 1 - j] >> shift); unsigned accumulation: corrupt streams may wrap, valid ones never get
+// near 2^63.  The common orders are compiled with the tap loop unrolled.
+template <int ORDER>
+inline void predict_n(int64_t* out, const int32_t* res, const int32_t* coef, int order, int shift, int blocksize) {
+    const int n = ORDER > 0 ? ORDER : order;
+    int64_t c[ORDER > 0 ? ORDER : 32];
+    for (int j = 0; j < n; ++j) c[j] = coef[j];
+    for (int i = n; i < blocksize; ++i) {
+        uint64_t acc = 0;
+        for (int j = 0; j < n; ++j) acc += (uint64_t)c[j] * (uint64_t)out[i - 1 - j];
+        out[i] = (int64_t)((uint64_t)((int64_t)acc >> shift) + (uint64_t)(int64_t)res[i]);
+    }
+}
+void predict(int64_t* out, const int32_t* res, const int32_t* coef, int order, int shift, int blocksize) {
+    switch (order) {
+        case 0: for (int i = 0; i < blocksize; ++i) out[i] = res[i]; break;
+        case 1: predict_n<1>(out, res, coef, order, shift, blocksize); break;
+        case 2: predict_n<2>(out, res, coef, order, shift, blocksize); break;
+        case 3: predict_n<3>(out, res, coef, order, shift, blocksize); break;
+        case 4: predict_n<4>(out, res, coef, order, shift, blocksize); break;
+        case 5: predict_n<5>(out, res, coef, order, shift, blocksize); break;
+        case 6: predict_n<6>(out, res, coef, order, shift, blocksize); break;
+        case 7: predict_n<7>(out, res, coef, order, shift, blocksize); break;
+        case 8: predict_n<8>(out, res, coef, order, shift, blocksize); break;
+        case 9: predict_n<9>(out, res, coef, order, shift, blocksize); break;
+        case 10: predict_n<10>(out, res, coef, order, shift, blocksize); break;
+        case 11: predict_n<11>(out, res, coef, order, shift, blocksize); break;
+        case 12: predict_n<12>(out, res, coef, order, shift, blocksize); break;
+        default: predict_n<0>(out, res, coef, order, shift, blocksize); break;
+    }
 }
 
 int read_subframe(BitReader& br, int64_t* out, int blocksize, int bps) {
@@ -210,11 +265,7 @@ int read_subframe(BitReader& br, int64_t* out, int blocksize, int bps) {
         std::vector<int32_t> res((size_t)blocksize);
         const int rc = read_residual(br, res.data() + order, blocksize, order);
         if (rc != FLAC_OK) return rc;
-        for (int i = order; i < blocksize; ++i) {        // unsigned accumulation: corrupt streams may wrap, valid ones never get near 2^63
-            uint64_t acc = 0;
-            for (int j = 0; j < order; ++j) acc += (uint64_t)(int64_t)coef[j] * (uint64_t)out[i - 1 - j];
-            out[i] = (int64_t)((uint64_t)((int64_t)acc >> shift) + (uint64_t)(int64_t)res[i]);
-        }
+        predict(out, res.data(), coef, order, shift, blocksize);
     } else {
         return FLAC_E_RESERVED;
     }
