@@ -640,3 +640,21 @@ def test_score_pcm_shard_prefetch_keeps_order_and_buffers_apart(sls, tmp_path):
         assert out.tolist() == [float(w.astype(np.int64).sum()) for w in want]
         assert [len(c) for c in calls] == [min(batch, h - a) for a in range(lo, h, batch)]
     assert sls.score_pcm_shard(FakeModel(), shard, lo=5, hi=5).numel() == 0
+
+
+def test_library_sass_is_blackwell_native(sls):
+    """Build guard (cuobjdump, no GPU): the hot kernels carry tcgen05 / TMEM / TMA SASS (UTC*MMA, LDTM, UTMALDG, UTMASTG,
+    UTMAREDG, UBLKCP) and no kernel falls back to the legacy mma.sync path (HMMA)."""
+    import shutil
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "sass_evidence.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-1500:]
+    rows = {ln.split('",')[0].strip('"'): dict(zip(r.stdout.splitlines()[0].split(",")[1:], map(int, ln.split('",')[1].split(","))))
+            for ln in r.stdout.splitlines()[1:]}
+    pair, attn, ln2, lns = rows["tc_gemm_pair_kernel"], rows["attn_tc_kernel"], rows["tc_gemm_ln2_kernel<1>"], rows["ln_stream_kernel<true>"]
+    assert pair["UTCHMMA"] > 0 and pair["LDTM"] > 0 and pair["UTMALDG"] > 0 and pair["UTMASTG"] > 0 and pair["UTMAREDG"] > 0
+    assert attn["UTCHMMA"] > 0 and attn["STTM"] > 0 and attn["UTMALDG"] > 0           # P written back into tensor memory
+    assert ln2["UTCHMMA"] > 0 and ln2["UTMASTG"] > 0 and lns["UBLKCP"] > 0
+    assert all(v["HMMA"] == 0 for v in rows.values())
