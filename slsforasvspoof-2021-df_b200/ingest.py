@@ -61,26 +61,27 @@ FLAC_ERRORS = {-2: "not a FLAC stream", -3: "truncated stream", -4: "bad frame h
 
 def decode_flac_bytes(data: bytes, max_samples: Optional[int] = None, verify_md5: bool = True, sample_rate: Optional[int] = SAMPLE_RATE) -> np.ndarray:
     """A whole .flac file in memory -> mono int16 [n] (channels averaged like ``read_wav_pcm16``).  ``max_samples`` stops the
-    decode early (the MD5 is then not checked - it covers the whole stream; frame CRCs always are)."""
+    decode early (the MD5 is then not checked unless the clip ends before - it covers the whole stream; frame CRCs always are)."""
     import ctypes as C
     from ._lib import load
     lib = load()
     buf = np.frombuffer(data, dtype=np.uint8)
-    probe = (C.c_int32 * 6)()
-    rc = lib.slsb_flac_decode(buf.ctypes.data, buf.size, 1, 0, None, 0, probe)      # STREAMINFO + first frame only
-    if rc < 0:
-        raise AudioFormatError(f"FLAC: {FLAC_ERRORS.get(int(rc), rc)}")
-    total = int(probe[3]) | (int(probe[5]) << 31)
-    if sample_rate is not None and probe[0] != sample_rate:
-        raise AudioFormatError(f"FLAC: need {sample_rate} Hz, got {probe[0]} Hz")
-    if probe[2] != 16:
-        raise AudioFormatError(f"FLAC: need 16-bit samples, got {probe[2]}")
-    cap = total if total > 0 else 1 << 26
     if max_samples:
-        cap = min(cap, int(max_samples))
+        cap = int(max_samples)                                      # the common path (pad() keeps the head): one call, no probe
+    else:
+        probe = (C.c_int32 * 6)()
+        rc = lib.slsb_flac_decode(buf.ctypes.data, buf.size, 0, 0, None, 0, probe)      # STREAMINFO only
+        if rc < 0:
+            raise AudioFormatError(f"FLAC: {FLAC_ERRORS.get(int(rc), rc)}")
+        total = int(probe[3]) | (int(probe[5]) << 31)
+        cap = total if total > 0 else 1 << 26
     out = np.empty(cap, dtype=np.int16)
     rate = C.c_int32(0)
     n = lib.slsb_flac_decode_mono16(buf.ctypes.data, buf.size, int(max_samples or 0), 1 if verify_md5 else 0, out.ctypes.data, cap, C.byref(rate))
+    if sample_rate is not None and rate.value not in (0, sample_rate):
+        raise AudioFormatError(f"FLAC: need {sample_rate} Hz, got {rate.value} Hz")
+    if n == -9:
+        raise AudioFormatError("FLAC: need 16-bit samples at a constant format (unsupported stream)")
     if n < 0:
         raise AudioFormatError(f"FLAC: {FLAC_ERRORS.get(int(n), n)}")
     return out[:n]
