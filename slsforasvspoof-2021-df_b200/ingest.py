@@ -180,26 +180,21 @@ class PcmShard:
         return np.ascontiguousarray(pcm), rel, lens.astype(np.int32)
 
 
-def score_pcm_shard(model, shard: PcmShard, batch: int = 64, samples: int = 64600, lo: int = 0, hi: Optional[int] = None) -> torch.Tensor:
-    """Scores clips lo..hi-1 of a shard (a rank's ``shard_range``) with ``model`` (a ``Model`` / ``ModelSLS`` of this
-    package): ``exp(logp[:, 1])`` per clip, float32 CPU tensor, protocol order (main.py:178-192).
-
-    Two pinned upload buffers: while the (synchronous, GIL-free) ``slsb_score_pcm16_host`` call of batch i runs, a helper thread
-    gathers batch i + 1 from the memory-mapped shard into the other buffer, so the device never waits for the page cache."""
-    hi = len(shard) if hi is None else hi
-    eng = model.engine()
-    head, prec = model._head(), model._prec()
-    out = torch.empty(max(hi - lo, 0), dtype=torch.float32)
+def _score_batches(eng, head: int, prec: int, samples: int, batch: int, n_items: int, fetch) -> torch.Tensor:
+    """Common loop of the file / shard scorers.  ``fetch(a, b)`` returns ``(pcm int16 [total], offsets int64 [b - a], lens int32
+    [b - a])`` for items a..b-1.  Two pinned upload buffers: while the (synchronous, GIL-free) ``slsb_score_pcm16_host`` call of
+    batch j runs, a helper thread fetches and stages batch j + 1 into the other buffer, so the device never waits for the host."""
+    out = torch.empty(max(n_items, 0), dtype=torch.float32)
     pin = torch.cuda.is_available()
     stages = [torch.empty(batch * samples, dtype=torch.int16, pin_memory=pin) for _ in range(2)]
-    starts = list(range(lo, hi, batch))
+    starts = list(range(0, n_items, batch))
 
     def stage_batch(j):
         a = starts[j]
-        b = min(a + batch, hi)
-        pcm, off, lens = shard.batch(a, b, max_samples=samples)
+        b = min(a + batch, n_items)
+        pcm, off, lens = fetch(a, b)
         up = stages[j & 1][:pcm.size]
-        up.numpy()[:] = pcm                                       # the only host copy: memory-mapped shard -> pinned buffer
+        up.numpy()[:] = pcm                                       # the only host copy: decoder output / memory-mapped shard -> pinned buffer
         return a, b, up, torch.from_numpy(off), torch.from_numpy(lens)
 
     if not starts:
@@ -210,5 +205,44 @@ def score_pcm_shard(model, shard: PcmShard, batch: int = 64, samples: int = 6460
             a, b, up, off, lens = nxt.result()
             if j + 1 < len(starts):
                 nxt = ex.submit(stage_batch, j + 1)              # fills the other buffer while this batch is on the device
-            out[a - lo:b - lo] = eng.score_pcm16_arrays(up, off, lens, head, prec, samples)
+            out[a:b] = eng.score_pcm16_arrays(up, off, lens, head, prec, samples)
     return out
+
+
+def score_pcm_shard(model, shard: PcmShard, batch: int = 64, samples: int = 64600, lo: int = 0, hi: Optional[int] = None) -> torch.Tensor:
+    """Scores clips lo..hi-1 of a shard (a rank's ``shard_range``) with ``model`` (a ``Model`` / ``ModelSLS`` of this
+    package): ``exp(logp[:, 1])`` per clip, float32 CPU tensor, protocol order (main.py:178-192)."""
+    hi = len(shard) if hi is None else hi
+    return _score_batches(model.engine(), model._head(), model._prec(), samples, batch, hi - lo,
+                          lambda a, b: shard.batch(lo + a, lo + b, max_samples=samples))
+
+
+def score_audio_files(model, paths: Sequence[str], batch: int = 64, samples: int = 64600, workers: int = 6, ahead: int = 4) -> torch.Tensor:
+    """FLAC / WAV files -> scores without a shard on disk: what ``produce_evaluation_file`` does with its 6-worker DataLoader
+    (main.py:161-193), as a pipeline - a decode pool runs ``ahead`` batches in front of the device, each batch is staged into a
+    pinned buffer while the previous one is being scored, 2 bytes per sample of the un-padded heads are uploaded."""
+    n = len(paths)
+    pool = cf.ThreadPoolExecutor(max_workers=max(1, workers))
+    futures = {}
+
+    def submit_upto(j_last):
+        for i in range(len(futures), min(n, (j_last + 1) * batch)):
+            futures[i] = pool.submit(read_audio_pcm16, paths[i], samples)
+
+    def fetch(a, b):
+        submit_upto(b // batch + ahead)
+        clips = [futures[i].result() for i in range(a, b)]
+        for i in range(a, b):
+            futures[i] = None                                     # drop the decoded clip, keep the index count
+        if any(c.size == 0 for c in clips):
+            raise AudioFormatError(f"empty clip in {paths[a:b]}")
+        lens = np.array([c.size for c in clips], dtype=np.int32)
+        off = np.zeros(len(clips), dtype=np.int64)
+        np.cumsum(lens[:-1], out=off[1:])
+        return np.concatenate(clips), off, lens
+
+    try:
+        submit_upto(ahead)
+        return _score_batches(model.engine(), model._head(), model._prec(), samples, batch, n, fetch)
+    finally:
+        pool.shutdown(wait=False, cancel_futures=True)

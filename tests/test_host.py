@@ -658,3 +658,41 @@ def test_library_sass_is_blackwell_native(sls):
     assert attn["UTCHMMA"] > 0 and attn["STTM"] > 0 and attn["UTMALDG"] > 0           # P written back into tensor memory
     assert ln2["UTCHMMA"] > 0 and ln2["UTMASTG"] > 0 and lns["UBLKCP"] > 0
     assert all(v["HMMA"] == 0 for v in rows.values())
+
+
+def test_score_audio_files_pipeline_with_stand_in_engine(sls, tmp_path):
+    """score_audio_files (decode pool running ahead of the scorer, no shard on disk) hands every file to the scorer once, in
+    order, as the head of its decoded clip; a stand-in engine replaces the GPU."""
+    import flac_enc
+    rs = np.random.RandomState(23)
+    clips = [(rs.randn(n) * 2000).astype(np.int16) for n in rs.randint(200, 3000, size=19)]
+    paths = []
+    for i, c in enumerate(clips):
+        if i % 3 == 0:
+            paths.append(str(tmp_path / f"f{i}.wav"))
+            sls.write_wav_pcm16(paths[-1], c)
+        else:
+            paths.append(str(tmp_path / f"f{i}.flac"))
+            (tmp_path / f"f{i}.flac").write_bytes(flac_enc.encode(c.astype(np.int64), kind="fixed2", blocksize=512, rate=16000))
+    seen = []
+
+    class FakeEngine:
+        def score_pcm16_arrays(self, pcm, off, ln, head, prec, samples):
+            got = [pcm[int(o):int(o) + int(n)].numpy().copy() for o, n in zip(off, ln)]
+            seen.extend(got)
+            return torch.tensor([float(g.astype(np.int64).sum()) for g in got])
+
+    class FakeModel:
+        def engine(self): return FakeEngine()
+        def _head(self): return 1
+        def _prec(self): return 1
+
+    for batch, cut, workers, ahead in ((4, 1000, 3, 2), (64, 64600, 1, 1), (1, 500, 6, 8)):
+        seen.clear()
+        out = sls.score_audio_files(FakeModel(), paths, batch=batch, samples=cut, workers=workers, ahead=ahead)
+        want = [c[:cut] for c in clips]
+        assert len(seen) == len(want) and all(np.array_equal(a, b) for a, b in zip(seen, want))
+        assert out.tolist() == [float(w.astype(np.int64).sum()) for w in want]
+    assert sls.score_audio_files(FakeModel(), [], batch=4).numel() == 0
+    with pytest.raises(FileNotFoundError):
+        sls.score_audio_files(FakeModel(), paths[:3] + [str(tmp_path / "missing.flac")], batch=2)
