@@ -146,8 +146,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "utterances_per_second", "value": v, "unit": "utt/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"XLS-R-300M + {HEAD_NAMES[args.head]}, 64600-sample clips (BASELINE config 2), random-init weights",
-                   "sample": f"{bs} clips per step on CPU"},
+        "config": {"workload": f"XLS-R-300M + {HEAD_NAMES[args.head]}, batch={args.batch} x 64600-sample clips per GPU (BASELINE config 2), random-init weights",
+                   "head": args.head, "sample": f"each step scores {bs} clips of that workload on the host cores (bounded sample)"},
         "cpu_baseline": {"value": v, "unit": "utt/s", "cores": cores, "kind": "port", "sample": f"{args.steps} steps x {bs} clips, fp32, torch CPU oracle port (reference head code on the restated fairseq trunk)"},
         "e2e": {"value": v, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
