@@ -696,3 +696,23 @@ def test_score_audio_files_pipeline_with_stand_in_engine(sls, tmp_path):
     assert sls.score_audio_files(FakeModel(), [], batch=4).numel() == 0
     with pytest.raises(FileNotFoundError):
         sls.score_audio_files(FakeModel(), paths[:3] + [str(tmp_path / "missing.flac")], batch=2)
+
+
+def test_bench_reference_arm_contract(tmp_path):
+    """`bench.py --impl reference` (CPU oracle port timed on the host cores): one JSON line with the GPU arm's metric / unit /
+    workload, `impl`, `cpu_baseline`, and an `e2e` equal to the line's own value; under a multi-rank launch only rank 0 works and
+    prints, the other ranks exit 0 silently."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--head", "sae"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stderr[-1500:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "utterances_per_second" and d["unit"] == "utt/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["e2e"] == {"value": d["value"], "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert "batch=64 x 64600-sample clips per GPU (BASELINE config 2)" in d["config"]["workload"] and d["config"]["head"] == "sae"
+    r1 = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, timeout=300, cwd=root,
+                        env=dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"))
+    assert r1.returncode == 0 and not [ln for ln in r1.stdout.splitlines() if ln.startswith("{")]
