@@ -716,3 +716,25 @@ def test_bench_reference_arm_contract(tmp_path):
     r1 = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, timeout=300, cwd=root,
                         env=dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"))
     assert r1.returncode == 0 and not [ln for ln in r1.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_compute_eer_matches_oracle_on_random_cases_with_ties(sls):
+    """Property test of scoring.compute_eer (torch, any device) against the pinned oracle restatement of
+    eval_metrics_DF.compute_eer: heavy ties (quantised scores), tiny and lopsided class counts - EER and threshold equal exactly."""
+    from hypothesis import given, settings, strategies as st
+    from oracle.eer import compute_eer as oracle_eer
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 40), st.integers(1, 40), st.integers(2, 12), st.integers(0, 2 ** 31 - 1))
+    def check(n_bona, n_spoof, levels, seed):
+        rs = np.random.RandomState(seed)
+        bona = np.round(rs.beta(4, 2, n_bona) * levels) / levels
+        spoof = np.round(rs.beta(2, 4, n_spoof) * levels) / levels
+        scores = np.concatenate([bona, spoof])
+        lab = np.concatenate([np.ones(n_bona, bool), np.zeros(n_spoof, bool)])
+        perm = rs.permutation(scores.size)                         # protocol order mixes the classes
+        got = sls.compute_eer(torch.from_numpy(scores[perm]), torch.from_numpy(lab[perm]))
+        want = oracle_eer(scores[perm][lab[perm]], scores[perm][~lab[perm]])
+        assert got[0] == float(want[0]) and got[1] == float(want[1])
+
+    check()
