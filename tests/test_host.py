@@ -738,3 +738,43 @@ def test_compute_eer_matches_oracle_on_random_cases_with_ties(sls):
         assert got[0] == float(want[0]) and got[1] == float(want[1])
 
     check()
+
+
+def test_flac_decoder_roundtrip_property(lib):
+    """decode(encode(x)) == x with the MD5 verified, over random signals, block sizes, predictors, Rice settings, stereo modes and
+    bit depths (test encoder: tests/flac_enc.py)."""
+    import flac_enc
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(0, 2 ** 31 - 1), st.sampled_from([8, 12, 16, 20, 24]), st.integers(1, 1500),
+           st.sampled_from([16, 64, 192, 255, 256, 576, 1000, 1152, 4096]),
+           st.sampled_from(["verbatim", "constant", "fixed0", "fixed1", "fixed2", "fixed3", "fixed4", "lpc1", "lpc2", "lpc5", "lpc8", "lpc12", "lpc20", "lpc32"]),
+           st.integers(0, 4), st.integers(0, 1), st.sampled_from([None, None, 8, 9, 10]), st.sampled_from(["noise", "sine", "silence", "dc", "full", "sparse"]))
+    def check(seed, bps, n, blocksize, kind, porder, method, stereo, signal):
+        rs = np.random.RandomState(seed)
+        hi = (1 << (bps - 1)) - 1
+        t = np.arange(n)
+
+        def make():
+            if signal == "noise":
+                return rs.randint(-hi // 4, hi // 4 + 1, size=n)
+            if signal == "sine":
+                return (0.6 * hi * np.sin(t * rs.uniform(0.01, 0.5)) + rs.randn(n) * max(1, hi / 500)).astype(np.int64)
+            if signal == "silence":
+                return np.zeros(n, np.int64)
+            if signal == "dc":
+                return np.full(n, rs.randint(-hi, hi + 1), np.int64)
+            if signal == "full":
+                return np.where(rs.rand(n) < 0.5, hi, -hi - 1).astype(np.int64)
+            return (rs.randint(-hi, hi + 1, size=n) * (rs.rand(n) < 0.05)).astype(np.int64) << rs.randint(0, 3)
+        x = make() if stereo is None else np.stack([make(), make()], 1)
+        x = np.clip(x, -hi - 1, hi)
+        esc = tuple(i for i in range(1 << porder) if rs.rand() < 0.2)
+        data = flac_enc.encode(x, bps=bps, rate=16000, blocksize=blocksize, kind=kind, stereo=stereo, porder=porder, method=method,
+                               escape_partitions=esc)
+        n_dec, info, pcm = _flac_decode(lib, data)
+        assert n_dec == n and info[:3] == [16000, 1 if stereo is None else 2, bps] and info[4] == 1
+        assert np.array_equal(pcm if stereo is not None else pcm[:, 0], x)
+
+    check()
