@@ -357,7 +357,8 @@ int decode(const uint8_t* data, int64_t n, int64_t max_samples, bool verify_md5,
         static const int ss_table[8] = {0, 8, 12, 0, 16, 20, 24, 32};
         const int bps = ss_code == 0 ? d.si.bps : ss_table[ss_code];
         const int nch = ch_code < 8 ? ch_code + 1 : 2;
-        if (nch != ch || bps != d.si.bps || (size_t)blocksize > stride) return FLAC_E_UNSUPPORTED;     // mid-stream format changes: not in scope
+        if (nch != ch || bps != d.si.bps || (size_t)blocksize > stride) return FLAC_E_UNSUPPORTED;
+        if (bps == 32 && ch_code >= 8) return FLAC_E_UNSUPPORTED;   // 33-bit side channel: not needed for speech corpora, rejected rather than guessed     // mid-stream format changes: not in scope
         // ---------------- subframes ----------------
         for (int c = 0; c < nch; ++c) {
             const bool side = (ch_code == 8 && c == 1) || (ch_code == 9 && c == 0) || (ch_code == 10 && c == 1);

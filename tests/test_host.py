@@ -402,6 +402,10 @@ def test_flac_decoder_every_syntax_element_against_test_encoder(sls, lib):
                   ((mono >> 3) << 3, dict(kind="fixed2")), (mono * 200, dict(kind="lpc8", bps=24)), (mono >> 8, dict(kind="fixed2", bps=8))):
         n, info, pcm = _flac_decode(lib, flac_enc.encode(x, **kw))
         assert n == len(x) and info[4] == 1 and np.array_equal(pcm[:, 0], x), kw
+    wide = rs.randint(-2 ** 28, 2 ** 28, size=3000).astype(np.int64) << 3                      # 32-bit samples: independent channels decode,
+    n, info, pcm = _flac_decode(lib, flac_enc.encode(wide, bps=32, kind="lpc4", blocksize=1024))   # a 33-bit side channel is refused
+    assert n == len(wide) and info[2] == 32 and info[4] == 1 and np.array_equal(pcm[:, 0], wide)
+    assert _flac_decode(lib, flac_enc.encode(np.stack([wide, wide + 5], 1), bps=32, kind="verbatim", stereo=10, blocksize=512))[0] == -9
     data = flac_enc.encode(mono, kind="lpc8", porder=2)
     tagged = b"ID3\x04\x00\x00" + bytes([0, 0, 1, 5]) + bytes(133) + data + b"TAG" + bytes(125)       # ID3v2 in front (133 bytes), ID3v1 behind
     n, info, pcm = _flac_decode(lib, tagged)
