@@ -6,9 +6,10 @@
 //                    write P (bf16) into a SWIZZLE_128B K-major smem tile that aliases the dead Q/K tiles, and a second
 //                    tcgen05.mma (V as MN-major B operand, exactly the [key][d] layout TMA delivers) produces O in the
 //                    TMEM columns S vacated.  256 TMEM columns + 96 KB smem per CTA -> two CTAs per SM overlap
-//                    softmax with the other CTA's TMA/MMA.  T <= 256.
+//                    softmax with the other CTA's TMA/MMA.  T <= 256.  (attn_tc_v1_kernel, kept for A/B.)
+//   attention_tc   : the production kernel further down (persistent, warp-specialised, P in TMEM), T <= 512.
 //   attention_simt : fp32 math, fp32 or bf16 I/O, any T (key tiles of 64, online softmax).  fp32 verification mode and
-//                    the T > 256 path.
+//                    the T > 512 path.
 #include "common.cuh"
 #include "kernels.h"
 #include <cstdlib>
@@ -304,57 +305,77 @@ attn_tc_v1_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 //   of the same half, is pulled into registers, the half is handed back to the MMA warp at once, and the normalised rows
 //   leave through a SWIZZLE_128B smem tile + 3-D TMA store (rows >= T are clipped by the tensor map).
 // =================================================================================================
-constexpr int P_STAGES = 2;
-constexpr int P_SQ = 2 * AQ * 128;            // up to two 128-row query tiles, 32 KB
-constexpr int P_SK = 256 * 128;               // 32 KB (Tp <= 256 keys)
-constexpr int P_SV = 256 * 128;               // 32 KB
-constexpr int P_STAGE = P_SQ + P_SK + P_SV;   // 96 KB
-constexpr int P_OUT_OFFSET = P_STAGES * P_STAGE;          // 2 x [128 rows x 64 bf16] output staging tiles (one per warpgroup)
-constexpr int P_BAR_OFFSET = P_OUT_OFFSET + 2 * 16384;
-constexpr int P_SMEM = P_BAR_OFFSET + 256;
+// narrow (T <= 256): 2 stages of {2 Q tiles, 256 keys of K, 256 of V}; wide (T <= 512): 1 stage of {4 Q tiles, 512 keys, 512 keys}
+template <bool kWide> struct AttnGeo {
+    static constexpr int STAGES = kWide ? 1 : 2;
+    static constexpr int QCAP = kWide ? 4 : 2;            // 128-row query tiles per item
+    static constexpr int KVCAP = kWide ? 512 : 256;       // keys per item
+    static constexpr int SQ = QCAP * AQ * 128;
+    static constexpr int SK = KVCAP * 128;
+    static constexpr int SV = KVCAP * 128;
+    static constexpr int STAGE = SQ + SK + SV;            // 96 KB / 192 KB
+    static constexpr int OUT_OFFSET = STAGES * STAGE;     // 2 x [128 rows x 64 bf16] output staging tiles (one per warpgroup)
+    static constexpr int BAR_OFFSET = OUT_OFFSET + 2 * 16384;
+    static constexpr int SMEM = BAR_OFFSET + 256;
+};
 constexpr int P_THREADS = 352;                // 8 softmax warps + TMA producer + 2 MMA issuers
 constexpr int P_OCOL = 192;                   // O accumulator columns inside a TMEM half
+constexpr int P_KB_MAX = 192;                 // widest key block when an item needs several (S must stay clear of the live O columns)
 
-// 32 score columns in registers -> four independent running maxima (cols >= len are padding / other utterances)
-__device__ __forceinline__ void max32(const uint32_t (&a)[32], int col0, int len, float (&mx)[4]) {
-    if (col0 + 32 <= len) {
+// 32 score columns in registers -> four independent running maxima; columns >= lim are padding / other utterances / stale
+__device__ __forceinline__ void max32(const uint32_t (&a)[32], int col0, int lim, float (&mx)[4]) {
+    if (col0 + 32 <= lim) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) mx[j & 3] = fmaxf(mx[j & 3], __uint_as_float(a[j]));
     } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) if (col0 + j < len) mx[j & 3] = fmaxf(mx[j & 3], __uint_as_float(a[j]));
+        for (int j = 0; j < 32; ++j) if (col0 + j < lim) mx[j & 3] = fmaxf(mx[j & 3], __uint_as_float(a[j]));
     }
 }
 
+// Key blocks: an item whose padded key count Tp fits a TMEM half (Tp <= 256) is ONE block: S -> row max -> P -> O, as described
+// above.  A longer item (wide mode, Tp <= 512) is cut into nkb blocks of kbw <= 192 keys and scheduled in two rounds over the
+// same TMEM columns: round 1 recomputes S block by block only for the row maxima, round 2 recomputes it again, exponentiates
+// against the GLOBAL row max and accumulates O += P_kb V_kb.  QK^T is 4 MMAs per block (the tensor pipe idles ~85 % of this
+// kernel), so recomputing it is cheaper than rescaling O, and the result is what a single block would give: no online re-base,
+// no dependence on the blocking.
+template <bool kWide>
 __global__ void __launch_bounds__(P_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_out,
-               int Tn, int Tp, int H, int n_items, int n_qt, const int* __restrict__ lens, int stagger, long long* __restrict__ trace) {
+               int Tn, int Tp, int H, int n_items, int n_qt, int kvbox, int nkb_arg, int kbw_arg, const int* __restrict__ lens, int stagger,
+               long long* __restrict__ trace) {
+    using G = AttnGeo<kWide>;
+    const int nkb = kWide ? nkb_arg : 1;          // narrow items are one block: compile-time, so that path keeps its codegen
+    const int kbw = kWide ? kbw_arg : Tp;
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0) { if (threadIdx.x == 0) printf("slsb: dynamic smem base not 1024-aligned\n"); __trap(); }
     // optional timeline of CTA 0 (slsb_op_attention_trace): trace[unit * 16 + event] = clock64()
 #define ATT_TRACE(unit, ev) do { if (trace != nullptr && blockIdx.x == 0 && (unit) < 64) trace[(unit) * 16 + (ev)] = clock64(); } while (0)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_BAR_OFFSET);
-    uint64_t* full = bars;                    // [P_STAGES] loads landed
-    uint64_t* stage_free = bars + 2;          // [P_STAGES] every MMA that reads the stage has completed
-    uint64_t* s_ready = bars + 4;             // [2] S = Q K^T complete in TMEM half w
-    uint64_t* p_ready = bars + 6;             // [2] P written back to TMEM half w (4 warp arrivals)
-    uint64_t* o_ready = bars + 8;             // [2] O = P V complete
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G::BAR_OFFSET);
+    uint64_t* full = bars;                    // [STAGES] loads landed
+    uint64_t* stage_free = bars + 2;          // [STAGES] every MMA that reads the stage has completed
+    uint64_t* s_ready = bars + 4;             // [2] S block complete in TMEM half w (one completion per phase)
+    uint64_t* p_ready = bars + 6;             // [2] S block consumed / P written back to TMEM half w (4 warp arrivals per phase)
+    uint64_t* o_ready = bars + 8;             // [2] O = P V complete (once per unit)
     uint64_t* tmem_free = bars + 10;          // [2] O has been read out of half w (4 warp arrivals)
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* pv_done = bars + 12;            // [2] P_kb V_kb complete: its P columns may be overwritten by the next S block
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int D = H * HD;
     const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // items blockIdx.x, +grid, ...
     const int my_units = my_items * n_qt;
-    const int nchunk = Tp / 16;               // 16-key chunks (MMA k-steps of the second product)
+    const int nph = nkb == 1 ? 1 : 2 * nkb;   // phases per unit (see above)
 
     griddep_launch();
     if (warp == 8 && lane == 0) {
         tma_prefetch_desc(&tm_q);
         tma_prefetch_desc(&tm_kv);
         tma_prefetch_desc(&tm_out);
-        for (int i = 0; i < P_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&stage_free[i], n_qt); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&s_ready[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_ready[i], 1); mbar_init(&tmem_free[i], 4); }
+        for (int i = 0; i < G::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&stage_free[i], n_qt); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s_ready[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_ready[i], 1); mbar_init(&tmem_free[i], 4); mbar_init(&pv_done[i], 1);
+        }
         mbar_fence_init();
     }
     if (warp == 9) tmem_alloc<512>(tmem_ptr);
@@ -367,18 +388,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     if (warp == 8) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            const uint32_t tx = (uint32_t)(n_qt * AQ * 128 + 2 * Tp * 128);
+            const int n_kvbox = (Tp + kvbox - 1) / kvbox;
+            const uint32_t tx = (uint32_t)(n_qt * AQ * 128 + 2 * n_kvbox * kvbox * 128);
             for (int n = 0; n < my_items; ++n) {
                 const int item = blockIdx.x + n * gridDim.x;
                 const int b = item / H, h = item - b * H;
-                const int st = n % P_STAGES;
-                mbar_wait(&stage_free[st], ((n / P_STAGES) & 1) ^ 1);
+                const int st = n % G::STAGES;
+                mbar_wait(&stage_free[st], ((n / G::STAGES) & 1) ^ 1);
                 ATT_TRACE(n * n_qt, 9);
-                uint8_t* base = smem + st * P_STAGE;
+                uint8_t* base = smem + st * G::STAGE;
                 mbar_expect_tx(&full[st], tx);
                 for (int qt = 0; qt < n_qt; ++qt) tma_load_2d(base + qt * (AQ * 128), &tm_q, &full[st], h * HD, b * Tn + qt * AQ);
-                tma_load_2d(base + P_SQ, &tm_kv, &full[st], D + h * HD, b * Tn);
-                tma_load_2d(base + P_SQ + P_SK, &tm_kv, &full[st], 2 * D + h * HD, b * Tn);
+                for (int i = 0; i < n_kvbox; ++i) {
+                    tma_load_2d(base + G::SQ + i * kvbox * 128, &tm_kv, &full[st], D + h * HD, b * Tn + i * kvbox);
+                    tma_load_2d(base + G::SQ + G::SK + i * kvbox * 128, &tm_kv, &full[st], 2 * D + h * HD, b * Tn + i * kvbox);
+                }
             }
         }
     } else if (warp >= 9) {
@@ -389,35 +413,47 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         // MUFU-bound: profiles/r01_attention_notes.md).
         if (lane == 0) {
             const int w = warp - 9;
-            const uint32_t idesc_s = make_idesc_bf16(AQ, Tp);
             const uint32_t idesc_o = make_idesc_bf16(AQ, HD, 0, 1);
             const uint32_t th = tmem + w * 256;
+            uint32_t ph = 0, pvn = 0;
             for (int u = w, k = 0; u < my_units; u += 2, ++k) {
-                const int n = u / n_qt, qt = u - n * n_qt, st = n % P_STAGES;
-                // S(u) = Q_qt K^T -> TMEM half w, columns [0, Tp)
-                mbar_wait(&full[st], (n / P_STAGES) & 1);
+                const int n = u / n_qt, qt = u - n * n_qt, st = n % G::STAGES;
+                mbar_wait(&full[st], (n / G::STAGES) & 1);
                 ATT_TRACE(u, 10);
                 if (k == 0 && w == 1 && stagger > 0) { const long long t0 = clock64(); while (clock64() - t0 < stagger) { } }
                 mbar_wait(&tmem_free[w], (k & 1) ^ 1);
                 tc_fence_after();
                 ATT_TRACE(u, 0);
-                const uint32_t sq = smem_u32(smem + st * P_STAGE + qt * (AQ * 128));
-                const uint32_t sk = smem_u32(smem + st * P_STAGE + P_SQ);
+                const uint32_t sq = smem_u32(smem + st * G::STAGE + qt * (AQ * 128));
+                const uint32_t sk = smem_u32(smem + st * G::STAGE + G::SQ);
+                const uint32_t sv = smem_u32(smem + st * G::STAGE + G::SQ + G::SK);
                 const uint64_t da = make_smem_desc_sw128(sq, 0, 1024);
-                const uint64_t dk = make_smem_desc_sw128(sk, 0, 1024);
+                for (int p = 0; p < nph; ++p) {
+                    const int kb = p < nkb ? p : p - nkb;
+                    const bool do_pv = nkb == 1 || p >= nkb;
+                    const int kb0 = kb * kbw, wk = min(kbw, Tp - kb0);
+                    // S block = Q_qt K[kb0 : kb0 + wk]^T -> TMEM half w, columns [0, wk)
+                    const uint32_t idesc_s = make_idesc_bf16(AQ, wk);
+                    const uint64_t dk = make_smem_desc_sw128(sk + kb0 * 128, 0, 1024);
 #pragma unroll
-                for (int kk = 0; kk < HD / 16; ++kk) tc_mma_f16(th, da + uint64_t(2 * kk), dk + uint64_t(2 * kk), idesc_s, kk != 0);
-                tc_commit(&s_ready[w]);
-                ATT_TRACE(u, 1);
-                // O(u) = P V ; A = packed bf16 P in TMEM, B = V [key][d] (MN-major)
-                mbar_wait(&p_ready[w], k & 1);
-                tc_fence_after();
-                ATT_TRACE(u, 2);
-                const uint32_t sv = smem_u32(smem + st * P_STAGE + P_SQ + P_SK);
-                uint64_t db = make_smem_desc_sw128(sv, 32768, 1024);
-                for (int kk = 0; kk < nchunk; ++kk) {
-                    tc_mma_f16_ts(th + P_OCOL, th + kk * 8, db, idesc_o, kk != 0);
-                    db += 2048 >> 4;                 // next 16 keys of V
+                    for (int kk = 0; kk < HD / 16; ++kk) tc_mma_f16(th, da + uint64_t(2 * kk), dk + uint64_t(2 * kk), idesc_s, kk != 0);
+                    tc_commit(&s_ready[w]);
+                    if (p == 0) ATT_TRACE(u, 1);
+                    mbar_wait(&p_ready[w], ph & 1); ++ph;
+                    tc_fence_after();
+                    if (!do_pv) continue;
+                    if (p + 1 == nph) ATT_TRACE(u, 2);
+                    // O (+)= P_kb V_kb ; A = packed bf16 P in TMEM, B = V [key][d] (MN-major)
+                    uint64_t db = make_smem_desc_sw128(sv + kb0 * 128, 32768, 1024);
+                    for (int kk = 0; kk < wk / 16; ++kk) {
+                        tc_mma_f16_ts(th + P_OCOL, th + kk * 8, db, idesc_o, (kb | kk) != 0);
+                        db += 2048 >> 4;                 // next 16 keys of V
+                    }
+                    if (p + 1 < nph) {                   // the next S block overwrites the P columns this product reads
+                        tc_commit(&pv_done[w]);
+                        mbar_wait(&pv_done[w], pvn & 1); ++pvn;
+                        tc_fence_after();
+                    }
                 }
                 tc_commit(&o_ready[w]);
                 tc_commit(&stage_free[st]);          // one arrival per unit of the item (barrier count n_qt): all its MMAs are done
@@ -429,11 +465,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         const int w = warp >> 2, q = warp & 3;
         const int r = q * 32 + lane;
         const uint32_t trow = tmem + (uint32_t(q * 32) << 16) + w * 256;
-        uint8_t* stage_tile = smem + P_OUT_OFFSET + w * 16384;
+        uint8_t* stage_tile = smem + G::OUT_OFFSET + w * 16384;
         const int bar_id = 1 + w;
         const bool issuer = r == 0;
-        const int npiece = (Tp + 31) / 32;
         constexpr float kLog2e = 1.4426950408889634f;
+        uint32_t ph = 0;
         for (int u = w, k = 0; u < my_units; u += 2, ++k) {
             const int n = u / n_qt, qt = u - n * n_qt;
             const int item = blockIdx.x + n * gridDim.x;
@@ -441,71 +477,78 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             const int len = lens ? min(lens[b], Tn) : Tn;
             const int rows_valid = min(AQ, Tn - qt * AQ);
             const bool active = q * 32 < rows_valid;           // warp-uniform: quadrants with no valid query row skip the math
-            mbar_wait(&s_ready[w], k & 1);
-            tc_fence_after();
-            if (issuer) ATT_TRACE(u, 4);
-            float sum = 0.f;
-            if (active) {
-                // ---- pass 1: row max, 32-column TMEM loads double-buffered in registers (a piece may run past Tp into the stale
-                // O columns of the half: masked by len)
-                float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-                {
-                    uint32_t a0[32], a1[32];
-                    tmem_ld_32x32b_x32(trow, a0);
-                    tmem_ld_wait();
+            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            float mxl = 0.f;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            for (int p = 0; p < nph; ++p) {
+                const int kb = p < nkb ? p : p - nkb;
+                const bool do_max = nkb == 1 || p < nkb, do_exp = nkb == 1 || p >= nkb;
+                const int kb0 = kb * kbw, wk = min(kbw, Tp - kb0);
+                const int lim = min(len - kb0, wk);            // valid columns of this block (may be <= 0: all padding)
+                const int npiece = (wk + 31) / 32, nchunk = wk / 16;
+                mbar_wait(&s_ready[w], ph & 1); ++ph;
+                tc_fence_after();
+                if (issuer && p == 0) ATT_TRACE(u, 4);
+                if (active) {
+                    if (do_max) {
+                        // ---- row max, 32-column TMEM loads double-buffered in registers (a piece may run past the block into stale
+                        // columns of the half: masked by lim)
+                        uint32_t a0[32], a1[32];
+                        tmem_ld_32x32b_x32(trow, a0);
+                        tmem_ld_wait();
 #pragma unroll 1
-                    for (int c = 0; c < npiece; c += 2) {
-                        if (c + 1 < npiece) tmem_ld_32x32b_x32(trow + (c + 1) * 32, a1);
-                        max32(a0, c * 32, len, mx4);
+                        for (int c = 0; c < npiece; c += 2) {
+                            if (c + 1 < npiece) tmem_ld_32x32b_x32(trow + (c + 1) * 32, a1);
+                            max32(a0, c * 32, lim, mx4);
+                            tmem_ld_wait();
+                            if (c + 1 >= npiece) break;
+                            if (c + 2 < npiece) tmem_ld_32x32b_x32(trow + (c + 2) * 32, a0);
+                            max32(a1, (c + 1) * 32, lim, mx4);
+                            tmem_ld_wait();
+                        }
+                        if (issuer && p == 0) ATT_TRACE(u, 5);
+                    }
+                    if (do_exp) {
+                        // ---- p = exp(s - max) -> packed bf16 written back over the columns of S this thread has already consumed
+                        // (P chunk c covers 32-bit columns [8c, 8c+8); the S columns still to be read start at 16(c+1))
+                        if (p == 0 || p == nkb) mxl = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * kLog2e;   // key 0 is valid: finite
+                        auto exp_chunk = [&](const uint32_t (&cur)[16], int c) {
+                            float pe[16];
+                            if (c * 16 + 16 <= lim) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) pe[j] = ex2_approx(fmaf(__uint_as_float(cur[j]), kLog2e, -mxl));
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) pe[j] = c * 16 + j < lim ? ex2_approx(fmaf(__uint_as_float(cur[j]), kLog2e, -mxl)) : 0.f;
+                            }
+                            s0 += (pe[0] + pe[4]) + (pe[8] + pe[12]); s1 += (pe[1] + pe[5]) + (pe[9] + pe[13]);
+                            s2 += (pe[2] + pe[6]) + (pe[10] + pe[14]); s3 += (pe[3] + pe[7]) + (pe[11] + pe[15]);
+                            uint32_t pk[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(pe[2 * j], pe[2 * j + 1]);
+                            tmem_st_32x32b_x8(trow + c * 8, pk);
+                        };
+                        uint32_t a0[16], a1[16];
+                        tmem_ld_32x32b_x16(trow, a0);
                         tmem_ld_wait();
-                        if (c + 1 >= npiece) break;
-                        if (c + 2 < npiece) tmem_ld_32x32b_x32(trow + (c + 2) * 32, a0);
-                        max32(a1, (c + 1) * 32, len, mx4);
-                        tmem_ld_wait();
+#pragma unroll 1
+                        for (int c = 0; c < nchunk; c += 2) {
+                            if (c + 1 < nchunk) tmem_ld_32x32b_x16(trow + (c + 1) * 16, a1);
+                            exp_chunk(a0, c);
+                            tmem_ld_wait();
+                            if (c + 1 >= nchunk) break;
+                            if (c + 2 < nchunk) tmem_ld_32x32b_x16(trow + (c + 2) * 16, a0);
+                            exp_chunk(a1, c + 1);
+                            tmem_ld_wait();
+                        }
+                        tmem_st_wait();
                     }
                 }
-                if (issuer) ATT_TRACE(u, 5);
-                // ---- pass 2: p = exp(s - max) -> packed bf16 written back over the columns of S this thread has already consumed
-                // (P chunk c covers 32-bit columns [8c, 8c+8); the S columns still to be read start at 16(c+1))
-                const float mxl = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * kLog2e;   // key 0 is valid: finite
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                auto exp_chunk = [&](const uint32_t (&cur)[16], int c) {
-                    float p[16];
-                    if (c * 16 + 16 <= len) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) p[j] = ex2_approx(fmaf(__uint_as_float(cur[j]), kLog2e, -mxl));
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) p[j] = c * 16 + j < len ? ex2_approx(fmaf(__uint_as_float(cur[j]), kLog2e, -mxl)) : 0.f;
-                    }
-                    s0 += (p[0] + p[4]) + (p[8] + p[12]); s1 += (p[1] + p[5]) + (p[9] + p[13]);
-                    s2 += (p[2] + p[6]) + (p[10] + p[14]); s3 += (p[3] + p[7]) + (p[11] + p[15]);
-                    uint32_t pk[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(p[2 * j], p[2 * j + 1]);
-                    tmem_st_32x32b_x8(trow + c * 8, pk);
-                };
-                {
-                    uint32_t a0[16], a1[16];
-                    tmem_ld_32x32b_x16(trow, a0);
-                    tmem_ld_wait();
-#pragma unroll 1
-                    for (int c = 0; c < nchunk; c += 2) {
-                        if (c + 1 < nchunk) tmem_ld_32x32b_x16(trow + (c + 1) * 16, a1);
-                        exp_chunk(a0, c);
-                        tmem_ld_wait();
-                        if (c + 1 >= nchunk) break;
-                        if (c + 2 < nchunk) tmem_ld_32x32b_x16(trow + (c + 2) * 16, a0);
-                        exp_chunk(a1, c + 1);
-                        tmem_ld_wait();
-                    }
-                }
-                sum = (s0 + s1) + (s2 + s3);
-                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_ready[w]);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p_ready[w]);
+            const float sum = (s0 + s1) + (s2 + s3);
             if (issuer) ATT_TRACE(u, 6);
             // ---- epilogue: O / sum -> bf16 -> swizzled smem tile -> TMA store
             mbar_wait(&o_ready[w], k & 1);
@@ -596,13 +639,19 @@ int attention_tc_v1(const void* qkv, void* out, int B, int T, int H, const int* 
 
 namespace slsb {
 int attention_tc(const void* qkv, void* out, int B, int T, int H, const int* lens, int num_sms, cudaStream_t stream, long long* trace) {
-    const int Tp = (T + 15) / 16 * 16;
-    if (Tp > 256) { set_error("attention_tc: T=%d > 256 (use attention_simt)", T); return -1; }
+    if (T > 512) { set_error("attention_tc: T=%d > 512 (use attention_simt)", T); return -1; }
+    const bool wide = T > 256;
+    // padded key count: a multiple of 16 (MMA k-steps of P V); wide items load K / V as two boxes of Tp / 2 keys (TMA boxes hold
+    // at most 256 rows), so there Tp is a multiple of 32
+    const int Tp = wide ? (T + 31) / 32 * 32 : (T + 15) / 16 * 16;
+    const int kvbox = wide ? Tp / 2 : Tp;
+    const int nkb = wide ? (Tp + P_KB_MAX - 1) / P_KB_MAX : 1;
+    const int kbw = wide ? ((Tp + nkb - 1) / nkb + 15) / 16 * 16 : Tp;
     const int D = H * HD;
     CUtensorMap tq, tkv, to;
     uint64_t dims[2] = {(uint64_t)(3 * D), (uint64_t)B * T};
     uint64_t strides[1] = {(uint64_t)(3 * D) * 2};
-    uint32_t boxq[2] = {HD, AQ}, boxkv[2] = {HD, (uint32_t)Tp};
+    uint32_t boxq[2] = {HD, AQ}, boxkv[2] = {HD, (uint32_t)kvbox};
     if (encode_tmap_bf16(&tq, qkv, 2, dims, strides, boxq)) return -1;
     if (encode_tmap_bf16(&tkv, qkv, 2, dims, strides, boxkv)) return -1;
     // output viewed as (d, t, b) so that a 128-row store box is clipped at the end of ITS utterance
@@ -612,14 +661,20 @@ int attention_tc(const void* qkv, void* out, int B, int T, int H, const int* len
     if (encode_tmap_bf16(&to, out, 3, odims, ostrides, obox)) return -1;
     static bool configured = false;
     if (!configured) {
-        SLSB_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
+        SLSB_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnGeo<false>::SMEM));
+        SLSB_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnGeo<true>::SMEM));
         configured = true;
     }
     const int n_items = B * H, n_qt = (T + AQ - 1) / AQ;
     const int grid = n_items < num_sms ? n_items : num_sms;
     static int stagger = -1;
     if (stagger < 0) { const char* sv = getenv("SLSB_ATTN_STAGGER"); stagger = sv ? atoi(sv) : 0; }
-    SLSB_CUDA_CHECK(launch_pdl(attn_tc_kernel, dim3(grid), dim3(P_THREADS), P_SMEM, stream, tq, tkv, to, T, Tp, H, n_items, n_qt, lens, stagger, trace));
+    if (wide)
+        SLSB_CUDA_CHECK(launch_pdl(attn_tc_kernel<true>, dim3(grid), dim3(P_THREADS), AttnGeo<true>::SMEM, stream, tq, tkv, to, T, Tp, H, n_items, n_qt,
+                                   kvbox, nkb, kbw, lens, stagger, trace));
+    else
+        SLSB_CUDA_CHECK(launch_pdl(attn_tc_kernel<false>, dim3(grid), dim3(P_THREADS), AttnGeo<false>::SMEM, stream, tq, tkv, to, T, Tp, H, n_items, n_qt,
+                                   kvbox, nkb, kbw, lens, stagger, trace));
     return 0;
 }
 }  // namespace slsb

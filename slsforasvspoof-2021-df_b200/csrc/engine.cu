@@ -309,8 +309,8 @@ static int pos_conv(slsb_engine* e, bool bf, const float* x, const void* Wp, con
 static int attention(slsb_engine* e, bool bf, const void* qkv, void* out, int B, int T, int H, const int* flens, cudaStream_t st) {
     ProfScope ps(e, st, PK_ATTN, 4.0 * (double)B * H * T * T * 64);
     int impl = e->cfg.attn_impl;
-    if (impl == SLSB_ATTN_AUTO) impl = (bf && T <= 256) ? SLSB_ATTN_TC : SLSB_ATTN_SIMT;
-    if ((impl == SLSB_ATTN_TC || impl == SLSB_ATTN_TC_V1) && T > 256) impl = SLSB_ATTN_SIMT;
+    if (impl == SLSB_ATTN_AUTO) impl = (bf && T <= 512) ? SLSB_ATTN_TC : SLSB_ATTN_SIMT;      // 512 frames = 10.2 s: bf16 never leaves tcgen05 (config 4)
+    if ((impl == SLSB_ATTN_TC && T > 512) || (impl == SLSB_ATTN_TC_V1 && T > 256)) impl = SLSB_ATTN_SIMT;
     if (impl == SLSB_ATTN_TC && bf) LAUNCH(attention_tc(qkv, out, B, T, H, flens, e->num_sms, st));
     else if (impl == SLSB_ATTN_TC_V1 && bf) LAUNCH(attention_tc_v1(qkv, out, B, T, H, flens, e->num_sms, st));
     else LAUNCH(attention_simt(qkv, out, bf ? 1 : 0, B, T, H, flens, st));

@@ -19,7 +19,8 @@
 //   A_POS4  : the same convolution as a Toeplitz GEMM with full-width tiles: four consecutive output frames t = 4i + j share
 //             one accumulator row, column (j, n) = 64 j + n, so N = 256; k-block u (0 .. K+2) multiplies input frame 4i + u
 //             with weight tap u - j (zero outside [0, K): the 3-D weight map's out-of-range fill).  A rows = 2 utterances x 64
-//             slots of i through a 4-D map (c, t % 4, t / 4, b); B = four 64-row boxes of the un-expanded weights.
+//             slots of i through a 4-D map (c, t % 4, t / 4, b) (T > 256: several 64-slot blocks per utterance pair); B = four
+//             64-row boxes of the un-expanded weights.
 #include "common.cuh"
 #include "kernels.h"
 #include <cstdlib>
@@ -55,6 +56,7 @@ struct DevParams {
     int batches, m_tiles, n_tiles;
     int conv_cin, conv_stride;
     int pos_T, pos_B;  // A_POS4: frames per utterance / utterances
+    int pos_sb;        // A_POS4: 256-frame slot blocks per utterance (m_blk = pair * pos_sb + slot block)
     void* out;
     long long ldc, out_batch_stride;
     const float* bias;
@@ -222,9 +224,10 @@ __device__ __forceinline__ void epilogue_tile_tma(const DevParams& p, const CUte
 
 // A_POS4 epilogue: accumulator row r = (utterance bb, slot i), column (j, n): out[b, 4i + j, 64 g + n] = x + gelu(acc + bias)
 // (wav2vec2.py:915-917).  128 columns per warp = shifts j = 2 half, 2 half + 1.
-__device__ __forceinline__ void epilogue_tile_pos4(const DevParams& p, uint32_t taddr, int half, int r, int g, int pair,
+__device__ __forceinline__ void epilogue_tile_pos4(const DevParams& p, uint32_t taddr, int half, int r, int g, int m_blk,
                                                    uint64_t* full_bar, uint32_t full_parity) {
-    const int bb = r >> 6, i = r & 63;
+    const int pair = m_blk / p.pos_sb, sb = m_blk - pair * p.pos_sb;
+    const int bb = r >> 6, i = sb * 64 + (r & 63);
     const int b = 2 * pair + bb;
     mbar_wait(full_bar, full_parity);
     tc_fence_after();
@@ -435,7 +438,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     } else if constexpr (A_MODE == A_POS) {
                         tma_load_3d(sa, &tmap_a, &full_bar[stage], n_blk * BLOCK_K, m_blk * BLOCK_M + kb, b);
                     } else {       // A_POS4: input frame 4i + kb of utterances 2 m_blk, 2 m_blk + 1, channels of group n_blk
-                        tma_load_4d(sa, &tmap_a, &full_bar[stage], n_blk * 64, kb & 3, kb >> 2, 2 * m_blk);
+                        const int pair = m_blk / p.pos_sb, sb = m_blk - pair * p.pos_sb;     // 64 slots (256 output frames) per tile
+                        tma_load_4d(sa, &tmap_a, &full_bar[stage], n_blk * 64, kb & 3, sb * 64 + (kb >> 2), 2 * pair);
                     }
                     if constexpr (A_MODE == A_POS4) {
 #pragma unroll
@@ -895,7 +899,8 @@ int tc_gemm(const TcGemmArgs& g, int num_sms, cudaStream_t stream) {
     dp.act = g.act; dp.out_bf16 = g.out_bf16;
     if (g.a_mode == A_POS4) {       // tiles: (utterance pair, group); k-blocks: taps + 3 input frames
         dp.pos_T = g.M; dp.pos_B = g.batches;
-        dp.batches = 1; dp.m_tiles = (g.batches + 1) / 2; dp.n_tiles = g.N / 64;
+        dp.pos_sb = (g.M + 255) / 256;                       // utterances longer than 256 frames take several slot blocks
+        dp.batches = 1; dp.m_tiles = ((g.batches + 1) / 2) * dp.pos_sb; dp.n_tiles = g.N / 64;
         dp.K = g.K + 3 * BLOCK_K;
     }
     if (g.k_splits > 1) {

@@ -143,7 +143,8 @@ def test_conv_implicit_gemm(lib, cuda, prec, B, Lin, k, s):
 
 # ------------------------------------------------------------------------------------------ positional conv
 @pytest.mark.parametrize("prec", [FP32, BF16])
-@pytest.mark.parametrize("B,T,lens", [(2, 201, None), (3, 97, [97, 50, 80])])
+@pytest.mark.parametrize("B,T,lens", [(2, 201, None), (3, 97, [97, 50, 80]), (1, 256, None), (2, 257, None), (3, 374, [374, 300, 120]), (3, 499, None),
+                                      (2, 512, None), (1, 700, None)])
 def test_posconv(lib, cuda, prec, B, T, lens):
     D, K, G = 1024, 128, 16
     x = _rand((B, T, D), 30)
@@ -305,6 +306,45 @@ def test_attention_tc_rebase_path(lib, cuda, T, first_big):
     out = torch.zeros(B, T, H * 64, device=cuda, dtype=torch.bfloat16)
     ok(lib, lib.slsb_op_attention(2, 1, P(qkv), P(out), B, T, H, None, stream()), "attention")
     report(f"attention re-base T={T}", out, _attn_ref(qkv, B, T, H, None), atol=2e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("B,T,lens", [(2, 257, None), (3, 288, [288, 257, 31]), (2, 300, [300, 193]), (2, 374, None), (3, 374, [374, 200, 150]),
+                                      (1, 416, None), (2, 499, None), (5, 499, [499, 480, 353, 340, 1]), (1, 512, None), (37, 499, None)])
+def test_attention_tc_key_blocks(lib, cuda, B, T, lens):
+    """257 <= T <= 512 (5-10 s clips): the persistent tcgen05 kernel in its wide geometry (one 192 KB stage, up to four query
+    tiles, key blocks of <= 192 columns: max round then exp round against the global row max); with and without padding masks,
+    incl. blocks that are entirely padding, vs the fp32 torch reference and vs the CUDA-core kernel."""
+    H = 16
+    qkv = _rand((B, T, 3 * H * 64), 63, 0.5)
+    qkv[..., :H * 64] *= 0.5
+    qkv[0, T // 2:, H * 64:2 * H * 64] *= 6.0              # utterance 0: the row maxima live in the later key blocks
+    qkv = qkv.bfloat16()
+    lens_t = torch.tensor(lens, dtype=torch.int32, device=cuda) if lens else None
+    outs = []
+    for _ in range(2):
+        out = torch.full((B, T, H * 64), float("nan"), device=cuda, dtype=torch.bfloat16)
+        ok(lib, lib.slsb_op_attention(2, 1, P(qkv), P(out), B, T, H, P(lens_t), stream()), "attention wide")
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])                     # bit-stable
+    out = outs[0].clone()
+    simt = torch.zeros_like(out)
+    ok(lib, lib.slsb_op_attention(1, 1, P(qkv), P(simt), B, T, H, P(lens_t), stream()), "attention simt")
+    ref = _attn_ref(qkv, B, T, H, lens)
+    if lens:
+        for i, n in enumerate(lens):
+            out[i, n:] = 0
+            ref[i, n:] = 0
+            simt[i, n:] = 0
+    report(f"attention tc wide T={T}", out, ref, atol=1.5e-2, rtol=1e-2)
+    report(f"attention tc wide vs simt T={T}", out, simt, atol=1.5e-2, rtol=1e-2)
+
+
+def test_attention_tc_rejects_T_above_512(lib, cuda):
+    B, T, H = 1, 513, 16
+    qkv = _rand((B, T, 3 * H * 64), 64, 0.5).bfloat16()
+    out = torch.zeros(B, T, H * 64, device=cuda, dtype=torch.bfloat16)
+    assert lib.slsb_op_attention(2, 1, P(qkv), P(out), B, T, H, None, stream()) != 0
+    assert b"512" in lib.slsb_last_error()
 
 
 def test_attention_long_simt(lib, cuda):

@@ -153,6 +153,43 @@ def test_variable_length_padding_mask(sls, cuda, precision):
     assert torch.equal(out.argmax(-1)[decided], ref.argmax(-1)[decided]) and int(decided.sum()) >= 2
 
 
+LONG_LENS = [80000, 120000, 160000, 96000, 140000, 110000, 155000, 88000, 159999, 81234, 131072, 100000]   # 5 ... 10 s
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_long_clips_5_to_10_s_parity(sls, cuda, precision):
+    """BASELINE config 4 at its stated upper range: 24-layer model, clips of 5, 7.5 and 10 s (T = 249 ... 499 frames) and
+    lengths in between, bucketed by frame count, right-padded inside a bucket with a key-padding mask (wav2vec2.py:567-586).
+    bf16: attention runs on the tcgen05 kernel in its wide geometry (T > 256); fp32: CUDA-core verification path.
+    Gate: |log-prob - oracle(clip alone, un-padded)| <= 1e-4 fp32 / 2e-2 bf16, identical argmax on every margin-decided clip
+    (>= 8 of the 12 must be decided: margin > 2 x the observed error)."""
+    from oracle.trunk import synth_clips
+    om = _oracle("sae")
+    m = _product(sls, "sae", om, precision)
+    eng = m.engine()
+    clips = [synth_clips(300 + i, 1, n)[0] for i, n in enumerate(LONG_LENS)]
+    assert eng.frames(80000) == 249 and eng.frames(120000) == 374 and eng.frames(160000) == 499
+    with torch.no_grad():
+        ref = torch.cat([om(c[None]) for c in clips])
+    got = torch.empty_like(ref)
+    batches = sls.bucket_by_frames(LONG_LENS, eng.frames, bucket_frames=64, max_batch=4)
+    assert sorted(i for b in batches for i in b) == list(range(len(clips)))
+    for batch in batches:
+        S = LONG_LENS[batch[0]]
+        wav = torch.zeros(len(batch), S)
+        for j, i in enumerate(batch):
+            wav[j, :LONG_LENS[i]] = clips[i]
+        with torch.no_grad():
+            out = m(wav.to(cuda), return_sae_loss=False, sample_lengths=torch.tensor([LONG_LENS[i] for i in batch]))
+        got[torch.tensor(batch)] = out.cpu()
+    err = float((got - ref).abs().max())
+    margin = (ref[:, 0] - ref[:, 1]).abs()
+    decided = margin > 2 * err
+    print(f"[long clips/{precision}] max|logprob err|={err:.3e} decided={int(decided.sum())}/{len(clips)} margins={margin.tolist()}")
+    assert torch.isfinite(got).all() and err <= TOL[precision]
+    assert int(decided.sum()) >= 8 and torch.equal(got.argmax(-1)[decided], ref.argmax(-1)[decided])
+
+
 def test_score_file_roundtrip(sls, cuda, tmp_path):
     om = _oracle("sae")
     m = _product(sls, "sae", om, "bf16")
