@@ -19,7 +19,7 @@ from .scoring import (produce_evaluation_file, score_synthetic_shard, gather_sco
                       synth_clip_host)
 from .data_utils import genSpoof_list, pad, Dataset_ASVspoof2021_eval, Dataset_in_the_wild_eval
 from .ingest import (read_wav_pcm16, write_wav_pcm16, decode_wav_files, write_pcm_shard, wav_files_to_shard, PcmShard,
-                     score_pcm_shard, AudioFormatError, decode_flac_bytes, read_flac_pcm16, read_audio_pcm16, decode_audio_files,
+                     score_pcm_shard, AudioFormatError, decode_flac_bytes, read_flac_pcm16, read_audio_pcm16, read_audio_float32, decode_audio_files,
                      audio_files_to_shard, score_audio_files)
 
 __all__ = ["Model", "ModelWindowTopK", "ModelSLS", "SSLModel", "AutoEncoderTopK", "getAttenF", "Engine", "make_config",
@@ -29,5 +29,5 @@ __all__ = ["Model", "ModelWindowTopK", "ModelSLS", "SSLModel", "AutoEncoderTopK"
            "load_library", "LIB_PATH", "EXPORTED_SYMBOLS", "PRECISIONS", "HEAD_NONE", "HEAD_SAE", "HEAD_WINDOW",
            "HEAD_SLS", "PREC_FP32", "PREC_BF16", "read_wav_pcm16", "write_wav_pcm16", "decode_wav_files", "write_pcm_shard",
            "wav_files_to_shard", "PcmShard", "score_pcm_shard", "AudioFormatError", "decode_flac_bytes", "read_flac_pcm16",
-           "read_audio_pcm16", "decode_audio_files", "audio_files_to_shard", "score_audio_files", "genSpoof_list", "pad", "Dataset_ASVspoof2021_eval",
+           "read_audio_pcm16", "read_audio_float32", "decode_audio_files", "audio_files_to_shard", "score_audio_files", "genSpoof_list", "pad", "Dataset_ASVspoof2021_eval",
            "Dataset_in_the_wild_eval"]

@@ -166,6 +166,17 @@ struct ProfScope {
     ~ProfScope() { if (idx >= 0) cudaEventRecord(e->prof[idx].b, st); }
 };
 
+// Every C-ABI entry that takes an engine runs on the engine's device and leaves the caller's current device as it found it
+// (a process may touch several GPUs: torch's current device need not be the engine's).
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 static int conv_len(const slsb_config& c, int n, int upto = -1) {
     const int last = upto < 0 ? c.n_conv : upto;
     for (int i = 0; i < last; ++i) n = n < c.conv_kernel[i] ? 0 : (n - c.conv_kernel[i]) / c.conv_stride[i] + 1;   // C division truncates: no frames below the kernel width
@@ -678,7 +689,7 @@ int slsb_create(const slsb_config* cfg, int device, slsb_engine** out) {
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { set_error("slsb_create: no CUDA device (this library has no CPU fallback)"); return -2; }
     if (device < 0 || device >= n) { set_error("slsb_create: device %d out of range (%d devices)", device, n); return -1; }
     cudaDeviceProp prop;
-    SLSB_CUDA_CHECK(cudaSetDevice(device));
+    DeviceGuard guard(device);            // allocate the arena on `device`, hand the caller's current device back
     SLSB_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) { set_error("slsb_create: device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor); return -2; }
     if (cfg->n_conv < 1 || cfg->n_conv > 8 || cfg->embed_dim % 128 || cfg->embed_dim / cfg->n_heads != 64 || cfg->conv_dim != 512 ||
@@ -697,6 +708,7 @@ int slsb_create(const slsb_config* cfg, int device, slsb_engine** out) {
 
 int slsb_destroy(slsb_engine* e) {
     if (!e) return 0;
+    DeviceGuard guard(e->device);
     cudaDeviceSynchronize();
     for (auto& kv : e->w) { if (kv.second.f32) cudaFree(kv.second.f32); if (kv.second.b16) cudaFree(kv.second.b16); }
     Buf* bufs[] = {&e->fe[0], &e->fe[1], &e->lnbuf, &e->qkv, &e->attn, &e->ffn, &e->xmid, &e->xfinal, &e->xc, &e->xpad, &e->acts, &e->encoded,
@@ -723,6 +735,7 @@ int64_t slsb_weight_numel(slsb_engine* e, const char* name) {
 
 int slsb_set_weight(slsb_engine* e, const char* name, const float* src, int64_t numel, void* stream) {
     if (!e || !name || !src) { set_error("slsb_set_weight: null argument"); return -1; }
+    DeviceGuard guard(e->device);
     auto it = e->w.find(name);
     if (it == e->w.end()) { set_error("slsb_set_weight: unknown tensor '%s'", name); return -1; }
     if (it->second.numel != numel) { set_error("slsb_set_weight: '%s' expects %lld elements, got %lld", name, (long long)it->second.numel, (long long)numel); return -1; }
@@ -734,6 +747,7 @@ int slsb_set_weight(slsb_engine* e, const char* name, const float* src, int64_t 
 
 int slsb_finalize_weights(slsb_engine* e, void* stream) {
     if (!e) { set_error("null engine"); return -1; }
+    DeviceGuard guard(e->device);
     for (auto& kv : e->w) {
         if (!kv.second.set) { set_error("slsb_finalize_weights: tensor '%s' was never set", kv.first.c_str()); return -1; }
         if (kv.second.gemm) LAUNCH(convert_f32_to_bf16(kv.second.f32, kv.second.b16, kv.second.numel, static_cast<cudaStream_t>(stream)));
@@ -750,6 +764,7 @@ int64_t slsb_launch_count(const slsb_engine* e) { return e ? e->launches : -1; }
 int slsb_forward(slsb_engine* e, const float* wav_dev, const int32_t* sample_lens_dev, int B, int S, int head, int precision,
                  float* logprob_dev, void* stream) {
     if (check_ready(e)) return -1;
+    DeviceGuard guard(e->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (run_trunk(e, wav_dev, sample_lens_dev, B, S, precision, head, st)) return -1;
     e->head = head;
@@ -760,6 +775,7 @@ int slsb_forward(slsb_engine* e, const float* wav_dev, const int32_t* sample_len
 
 int slsb_extract_feat(slsb_engine* e, const float* wav_dev, const int32_t* sample_lens_dev, int B, int S, int precision, float* x_dev, void* stream) {
     if (check_ready(e)) return -1;
+    DeviceGuard guard(e->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (run_trunk(e, wav_dev, sample_lens_dev, B, S, precision, SLSB_HEAD_NONE, st)) return -1;
     e->head = SLSB_HEAD_NONE;
@@ -769,6 +785,7 @@ int slsb_extract_feat(slsb_engine* e, const float* wav_dev, const int32_t* sampl
 
 int slsb_get_tensor(slsb_engine* e, const char* name, float* dst, int64_t numel, void* stream) {
     if (!e || !name || !dst) { set_error("slsb_get_tensor: null argument"); return -1; }
+    DeviceGuard guard(e->device);
     if (e->B == 0) { set_error("slsb_get_tensor: no forward has run yet"); return -1; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const slsb_config& c = e->cfg;
@@ -816,6 +833,7 @@ int slsb_get_tensor(slsb_engine* e, const char* name, float* dst, int64_t numel,
 
 int slsb_get_sparse(slsb_engine* e, int32_t* idx_dev, float* val_dev, int32_t* count_dev, void* stream) {
     if (!e || !idx_dev || !val_dev) { set_error("slsb_get_sparse: null argument"); return -1; }
+    DeviceGuard guard(e->device);
     if (!e->have_sel) { set_error("slsb_get_sparse: last forward ran no SAE head"); return -1; }
     const slsb_config& c = e->cfg;
     const long long M = (long long)e->B * e->T;
@@ -827,6 +845,7 @@ int slsb_get_sparse(slsb_engine* e, int32_t* idx_dev, float* val_dev, int32_t* c
 
 int slsb_sae_encode(slsb_engine* e, const float* x_dev, int64_t rows, int T, int window, int precision, float* encoded_dev, void* stream) {
     if (check_ready(e)) return -1;
+    DeviceGuard guard(e->device);
     const slsb_config& c = e->cfg;
     if (c.sae_dict <= 0) { set_error("engine has no SAE weights"); return -1; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -846,6 +865,7 @@ int slsb_sae_encode(slsb_engine* e, const float* x_dev, int64_t rows, int T, int
 
 int slsb_sae_decode(slsb_engine* e, const float* encoded_dev, int64_t rows, int precision, float* recon_dev, void* stream) {
     if (check_ready(e)) return -1;
+    DeviceGuard guard(e->device);
     const slsb_config& c = e->cfg;
     if (c.sae_dict <= 0) { set_error("engine has no SAE weights"); return -1; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -862,6 +882,7 @@ int slsb_sae_decode(slsb_engine* e, const float* encoded_dev, int64_t rows, int 
 
 int slsb_sae_loss(slsb_engine* e, int precision, float* loss_dev, void* stream) {
     if (check_ready(e)) return -1;
+    DeviceGuard guard(e->device);
     const slsb_config& c = e->cfg;
     if (!e->have_sel) { set_error("slsb_sae_loss: last forward ran no SAE head"); return -1; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -878,6 +899,7 @@ int slsb_sae_loss(slsb_engine* e, int precision, float* loss_dev, void* stream) 
 int64_t slsb_score_submit(slsb_engine* e, const float* wav_host, const int32_t* lens_host, int B, int S, int head, int precision,
                           float* scores_host, void* stream) {
     if (check_ready(e)) return -1;
+    DeviceGuard guard(e->device);
     if (!wav_host || !scores_host) { set_error("slsb_score_submit: null buffer"); return -1; }
     if (head == SLSB_HEAD_NONE) { set_error("slsb_score_submit: a classifier head is required"); return -1; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -915,6 +937,7 @@ int64_t slsb_score_submit(slsb_engine* e, const float* wav_host, const int32_t* 
 
 int slsb_score_wait(slsb_engine* e, int64_t ticket) {
     if (!e) { set_error("null engine"); return -1; }
+    DeviceGuard guard(e->device);
     if (ticket >= e->submit_seq) { set_error("slsb_score_wait: ticket %lld was never submitted", (long long)ticket); return -1; }
     const int64_t lo = ticket < 0 ? (e->submit_seq > 4 ? e->submit_seq - 4 : 0) : ticket;
     const int64_t hi = ticket < 0 ? e->submit_seq : ticket + 1;
@@ -939,6 +962,7 @@ int slsb_ingest_pcm16(const int16_t* pcm_dev, const int64_t* offsets_dev, const 
 int slsb_score_pcm16_host(slsb_engine* e, const int16_t* pcm_host, int64_t total_samples, const int64_t* offsets_host, const int32_t* lens_host,
                           int B, int S, int head, int precision, float* scores_host, void* stream) {
     if (check_ready(e)) return -1;
+    DeviceGuard guard(e->device);
     if (!pcm_host || !offsets_host || !lens_host || !scores_host) { set_error("slsb_score_pcm16_host: null buffer"); return -1; }
     if (head == SLSB_HEAD_NONE) { set_error("slsb_score_pcm16_host: a classifier head is required"); return -1; }
     for (int b = 0; b < B; ++b) {
@@ -965,6 +989,7 @@ int slsb_score_pcm16_host(slsb_engine* e, const int16_t* pcm_host, int64_t total
 
 int slsb_profile_enable(slsb_engine* e, int on) {
     if (!e) { set_error("null engine"); return -1; }
+    DeviceGuard guard(e->device);
     for (auto& r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     e->prof.clear();
     e->profiling = on != 0;
@@ -973,6 +998,7 @@ int slsb_profile_enable(slsb_engine* e, int on) {
 
 int slsb_profile_read(slsb_engine* e, int kind, double* ms_out, double* flops_out, int64_t* launches_out) {
     if (!e) { set_error("null engine"); return -1; }
+    DeviceGuard guard(e->device);
     SLSB_CUDA_CHECK(cudaDeviceSynchronize());
     double ms = 0.0, fl = 0.0; int64_t n = 0;
     for (auto& r : e->prof) {

@@ -69,9 +69,10 @@ struct BitReader {
     inline void align() { const int r = cnt & 7; win <<= r; cnt -= r; }   // `next * 8` is byte aligned, so cnt mod 8 = bits left in the current byte
 };
 
-uint8_t crc8_table[256]; uint16_t crc16_table[256]; uint16_t crc16_slice[8][256]; bool tables_ready = false;
-void init_tables() {
-    if (tables_ready) return;
+uint8_t crc8_table[256]; uint16_t crc16_table[256]; uint16_t crc16_slice[8][256];
+// Built exactly once, race-free: the decoder runs on many threads at once (ingest.py's thread pool calls it with the GIL
+// released), and a function-local static is initialised under the C++11 guarantee (one thread builds, the others wait).
+void build_tables() {
     for (int i = 0; i < 256; ++i) {
         uint8_t c = (uint8_t)i; uint16_t d = (uint16_t)(i << 8);
         for (int b = 0; b < 8; ++b) { c = (uint8_t)((c & 0x80) ? ((c << 1) ^ 0x07) : (c << 1)); d = (uint16_t)((d & 0x8000) ? ((d << 1) ^ 0x8005) : (d << 1)); }
@@ -83,7 +84,10 @@ void init_tables() {
         crc16_slice[0][i] = c;
         for (int k = 1; k < 8; ++k) { c = (uint16_t)((c << 8) ^ crc16_table[c >> 8]); crc16_slice[k][i] = c; }
     }
-    tables_ready = true;
+}
+void init_tables() {
+    static const bool once = (build_tables(), true);
+    (void)once;
 }
 uint8_t crc8(const uint8_t* p, int64_t n) { uint8_t c = 0; for (int64_t i = 0; i < n; ++i) c = crc8_table[c ^ p[i]]; return c; }
 uint16_t crc16(const uint8_t* p, int64_t n) {
@@ -322,6 +326,7 @@ int decode(const uint8_t* data, int64_t n, int64_t max_samples, bool verify_md5,
     if (info_only) return FLAC_OK;
     Md5 md5;
     std::vector<uint8_t> md5_buf;
+    bool cut_short = false;      // a stream of unknown length (total == 0) stopped by max_samples: the MD5 covers only a head
     d.pcm.clear();
     d.samples = 0;
     while (pos < n && d.samples < want) {
@@ -379,6 +384,7 @@ int decode(const uint8_t* data, int64_t n, int64_t max_samples, bool verify_md5,
         }
         // ---------------- output (+ MD5 over the whole stream when it is decoded completely) ----------------
         const int64_t take = blocksize < want - d.samples ? blocksize : want - d.samples;
+        if (take < blocksize && d.si.total == 0) cut_short = true;
         if (d.mono16) {
             if (bps != 16) return FLAC_E_UNSUPPORTED;
             if (d.samples + take > d.mono16_cap) return FLAC_E_ARG;
@@ -416,7 +422,10 @@ int decode(const uint8_t* data, int64_t n, int64_t max_samples, bool verify_md5,
     }
     if (d.si.total > 0 && whole && d.samples != d.si.total) return FLAC_E_TRUNC;
     if (d.si.total == 0 && d.samples == 0) return FLAC_E_TRUNC;
-    if (whole && verify_md5) {
+    // total == 0 with max_samples: `whole` could not know the length; if the loop stopped at `want` with audio frames still
+    // ahead (or inside a block), the digest is of a truncated head and must not be compared with STREAMINFO's
+    if (d.si.total == 0 && max_samples > 0 && d.samples >= want && pos + 1 < n && data[pos] == 0xFF && (data[pos + 1] & 0xFE) == 0xF8) cut_short = true;
+    if (whole && verify_md5 && !cut_short) {
         bool zero = true;
         for (int i = 0; i < 16; ++i) zero = zero && d.si.md5[i] == 0;
         if (!zero) {                                         // an all-zero signature means "not computed by the encoder"

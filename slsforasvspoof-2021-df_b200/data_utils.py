@@ -1,7 +1,7 @@
 """Eval-side mirror of the reference's ``data_utils_SSL.py`` (same names, same return values) on the native decoders, so that
 ``main.py``'s evaluation branch (:640-650: ``genSpoof_list`` -> ``Dataset_ASVspoof2021_eval`` -> ``produce_evaluation_file``)
 runs unchanged against this package.  ``__getitem__`` returns what the reference returns - ``(float32 Tensor [64600], utt_id)``
-- but decodes with ``ingest.read_audio_pcm16`` (FLAC: csrc/flac_decode.cpp, head of the clip only) instead of librosa.
+- but decodes with ``ingest.read_audio_float32`` (FLAC: csrc/flac_decode.cpp, head of the clip only) instead of librosa.
 
 For throughput use ``ingest.audio_files_to_shard`` + ``score_pcm_shard`` (2 bytes per sample uploaded, ``pad`` on the device);
 this module is the compatibility surface.  Training-side pieces (RawBoost, ``Dataset_ASVspoof2019_train``) are out of scope.
@@ -12,7 +12,7 @@ import numpy as np
 import torch
 from torch.utils.data import Dataset
 
-from .ingest import read_audio_pcm16
+from .ingest import read_audio_float32
 from .scoring import pad_clip
 
 
@@ -51,8 +51,10 @@ class _EvalClips(Dataset):
 
     def __getitem__(self, index):
         utt_id = self.list_IDs[index]
-        pcm = read_audio_pcm16(self._path(utt_id), max_samples=self.cut)      # pad() only ever looks at the first `cut` samples
-        x = pcm.astype(np.float32) / np.float32(32768.0)                      # what libsndfile hands librosa for 16-bit audio
+        # pad() only ever looks at the first `cut` samples; float32 mono exactly as libsndfile + librosa deliver it for 16-bit
+        # audio at 16 kHz (multi-channel: float mean of the channels, not an integer one).  Other rates / bit depths raise
+        # AudioFormatError: the reference would resample (librosa), this path never guesses - resample off-line.
+        x = read_audio_float32(self._path(utt_id), max_samples=self.cut)
         return torch.from_numpy(pad_clip(x, self.cut)), utt_id
 
 

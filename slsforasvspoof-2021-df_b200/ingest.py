@@ -33,17 +33,27 @@ def read_wav_pcm16(path: str, sample_rate: int = SAMPLE_RATE) -> np.ndarray:
     """RIFF/WAVE, 16-bit PCM -> int16 [n].  Multi-channel files are averaged to mono (what ``librosa.load(mono=True)`` does,
     here in integer arithmetic rounded half away from zero); other sample widths or rates are rejected - resampling is an
     off-line step, the scorer never guesses."""
-    with wave.open(path, "rb") as w:
-        if w.getsampwidth() != 2 or w.getcomptype() != "NONE":
-            raise AudioFormatError(f"{path}: need 16-bit PCM, got sample width {w.getsampwidth()} / {w.getcomptype()}")
-        if w.getframerate() != sample_rate:
-            raise AudioFormatError(f"{path}: need {sample_rate} Hz, got {w.getframerate()} Hz")
-        ch = w.getnchannels()
-        pcm = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2")
+    pcm, ch = _read_wav_frames(path, sample_rate)
     if ch > 1:
         s = pcm.reshape(-1, ch).astype(np.int32).sum(axis=1)
         pcm = (np.sign(s) * ((np.abs(s) * 2 + ch) // (2 * ch))).astype(np.int16)
     return np.ascontiguousarray(pcm, dtype=np.int16)
+
+
+def _read_wav_frames(path: str, sample_rate: int = SAMPLE_RATE, max_frames: Optional[int] = None) -> Tuple[np.ndarray, int]:
+    """Interleaved int16 samples + channel count of a 16-bit PCM RIFF/WAVE file; every other flavour (24-bit, float,
+    WAVE_FORMAT_EXTENSIBLE, other rates) raises ``AudioFormatError`` - including the ones the ``wave`` module itself refuses."""
+    try:
+        with wave.open(path, "rb") as w:
+            if w.getsampwidth() != 2 or w.getcomptype() != "NONE":
+                raise AudioFormatError(f"{path}: need 16-bit PCM, got sample width {w.getsampwidth()} / {w.getcomptype()}")
+            if w.getframerate() != sample_rate:
+                raise AudioFormatError(f"{path}: need {sample_rate} Hz, got {w.getframerate()} Hz")
+            ch = w.getnchannels()
+            n = w.getnframes() if max_frames is None else min(w.getnframes(), int(max_frames))
+            return np.frombuffer(w.readframes(n), dtype="<i2"), ch
+    except (wave.Error, EOFError) as e:
+        raise AudioFormatError(f"{path}: not a 16-bit PCM RIFF/WAVE file ({e})") from None
 
 
 def write_wav_pcm16(path: str, pcm: np.ndarray, sample_rate: int = SAMPLE_RATE) -> None:
@@ -98,6 +108,41 @@ def read_audio_pcm16(path: str, max_samples: Optional[int] = None) -> np.ndarray
         return read_flac_pcm16(path, max_samples)
     pcm = read_wav_pcm16(path)
     return pcm[:max_samples] if max_samples else pcm
+
+
+def read_audio_float32(path: str, max_samples: Optional[int] = None) -> np.ndarray:
+    """What ``librosa.load(path, sr=16000)`` hands the reference's ``__getitem__`` (data_utils_SSL.py:111) for 16-bit audio at
+    16 kHz: float32 mono in [-1, 1).  Mono files: ``int16 / 32768`` (exact).  Multi-channel files: every channel converted to
+    float32 first, THEN averaged in float32 - librosa's ``to_mono`` - so an odd channel sum keeps its half LSB (the int16 scorer
+    path ``read_audio_pcm16`` rounds it; ASVspoof 2021 and In-the-Wild are mono, where the two agree bit for bit)."""
+    if path.lower().endswith(".flac"):
+        import ctypes as C
+        from ._lib import load
+        lib = load()
+        with open(path, "rb") as f:
+            buf = np.frombuffer(f.read(), dtype=np.uint8)
+        info = (C.c_int32 * 6)()
+        rc = lib.slsb_flac_decode(buf.ctypes.data, buf.size, 0, 0, None, 0, info)          # STREAMINFO
+        if rc < 0:
+            raise AudioFormatError(f"{path}: FLAC: {FLAC_ERRORS.get(int(rc), rc)}")
+        rate, ch, bps = int(info[0]), int(info[1]), int(info[2])
+        if rate != SAMPLE_RATE or bps != 16:
+            raise AudioFormatError(f"{path}: need 16-bit samples at {SAMPLE_RATE} Hz, got {bps}-bit at {rate} Hz")
+        if ch == 1:
+            return read_flac_pcm16(path, max_samples).astype(np.float32) / np.float32(32768.0)
+        total = int(info[3]) | (int(info[5]) << 31)
+        cap = int(max_samples) if (max_samples and (total == 0 or max_samples < total)) else (total if total > 0 else 1 << 24)
+        out = np.empty(cap * ch, dtype=np.int32)
+        n = lib.slsb_flac_decode(buf.ctypes.data, buf.size, int(max_samples or 0), 1, out.ctypes.data, out.size, info)
+        if n < 0:
+            raise AudioFormatError(f"{path}: FLAC: {FLAC_ERRORS.get(int(n), n)}")
+        frames = out[:n * ch].reshape(n, ch)
+    else:
+        pcm, ch = _read_wav_frames(path, SAMPLE_RATE, max_samples)
+        if ch == 1:
+            return pcm.astype(np.float32) / np.float32(32768.0)
+        frames = pcm.reshape(-1, ch)
+    return np.mean(frames.astype(np.float32) / np.float32(32768.0), axis=1, dtype=np.float32)
 
 
 def decode_audio_files(paths: Sequence[str], workers: int = 6, max_samples: Optional[int] = None) -> List[np.ndarray]:

@@ -28,7 +28,7 @@ def _load_fairseq_checkpoint(trunk: TrunkParams, cp_path: str) -> None:
             f"Could not load SSL checkpoint '{cp_path}' (file not found). Pass cp_path=None for a random-init trunk "
             "(synthetic benchmarks / parity tests).")
     from .weights import load_checkpoint_tensors
-    sd = load_checkpoint_tensors(cp_path)          # restricted unpickler: omegaconf / fairseq classes become inert stubs
+    sd = load_checkpoint_tensors(cp_path)          # allowlist unpickler (weights.py): only tensors + plain containers resolve, every other global becomes an inert stub
     missing, unexpected = trunk.load_state_dict(sd, strict=False)
     hard = [k for k in missing if not k.startswith(("quantizer", "project_q", "final_proj"))]
     if hard:

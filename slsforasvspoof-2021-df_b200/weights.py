@@ -183,12 +183,45 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], geo: TrunkGeometry, prefix: str
 # ---------------------------------------------------------------------------------------------------------------------
 # checkpoints without fairseq (main.py:531-592, model.py:113-115)
 # ---------------------------------------------------------------------------------------------------------------------
-_SAFE_PICKLE_ROOTS = ("torch", "collections", "numpy", "builtins", "_codecs", "argparse", "copyreg", "typing", "enum", "functools")
+# Exact (module, name) pairs a checkpoint may resolve.  Whole modules are NOT trusted: ``builtins.eval``, ``builtins.getattr``,
+# ``torch.utils.cpp_extension.load``, ``torch.storage._load_from_bytes``, ``functools.partial`` ... are all reachable through
+# "safe-looking" roots, so anything that is not listed here (or is not a torch dtype / legacy storage class / numpy scalar
+# type, checked by type below) is replaced by an inert stub and is never called.
+_SAFE_GLOBALS = frozenset({
+    ("collections", "OrderedDict"), ("collections", "defaultdict"),
+    ("torch._utils", "_rebuild_tensor_v2"), ("torch._utils", "_rebuild_tensor"), ("torch._utils", "_rebuild_parameter"),
+    ("torch._utils", "_rebuild_parameter_with_state"), ("torch._tensor", "_rebuild_from_type_v2"),
+    ("torch", "Size"), ("torch", "device"), ("torch", "Tensor"), ("torch.nn.parameter", "Parameter"),
+    ("torch.storage", "UntypedStorage"), ("torch.storage", "TypedStorage"),
+    ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+    ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"), ("numpy", "ndarray"), ("numpy", "dtype"),
+    ("argparse", "Namespace"), ("_codecs", "encode"), ("copyreg", "_reconstructor"),
+    ("builtins", "set"), ("builtins", "frozenset"), ("builtins", "dict"), ("builtins", "list"), ("builtins", "tuple"),
+    ("builtins", "int"), ("builtins", "float"), ("builtins", "complex"), ("builtins", "bool"), ("builtins", "str"),
+    ("builtins", "bytes"), ("builtins", "bytearray"), ("builtins", "slice"), ("builtins", "range"), ("builtins", "object"),
+})
+
+
+def _is_safe_global(module: str, name: str) -> bool:
+    if (module, name) in _SAFE_GLOBALS:
+        return True
+    if module == "torch" and "." not in name:
+        obj = getattr(torch, name, None)
+        if isinstance(obj, torch.dtype):                                   # torch.float32, torch.bfloat16, ...
+            return True
+        if name.endswith("Storage") and isinstance(obj, type):           # legacy typed storages named in persistent ids
+            return True
+    if module == "numpy" and "." not in name:
+        import numpy as np
+        obj = getattr(np, name, None)
+        return isinstance(obj, type) and issubclass(obj, np.generic)       # numpy scalar types (np.float64, ...)
+    return False
 
 
 def _stub_class(module: str, name: str):
-    """Stand-in for a class that only matters to fairseq (omegaconf configs, task / criterion objects): constructible
-    with anything, absorbs any pickled state, never executes foreign code."""
+    """Stand-in for everything outside the allowlist (omegaconf configs, fairseq task / criterion objects, and equally any
+    function a hostile file names): constructible / callable with anything, absorbs any pickled state, runs no code of the
+    named object - the named module is never even imported."""
     def _init(self, *a, **k):
         self.__dict__["_args"] = (a, k)
 
@@ -196,19 +229,23 @@ def _stub_class(module: str, name: str):
         self.__dict__["_state"] = state
 
     return type(name, (), {"__module__": module, "__init__": _init, "__setstate__": _setstate, "__call__": lambda self, *a, **k: self,
-                           "__getattr__": lambda self, k: None, "__reduce__": lambda self: (dict, ())})
+                           "__getattr__": lambda self, k: None, "__reduce__": lambda self: (dict, ()),
+                           "__setitem__": lambda self, k, v: None, "append": lambda self, v: None, "extend": lambda self, v: None,
+                           "add": lambda self, v: None, "update": lambda self, *a, **k: None})
 
 
 class _TensorOnlyUnpickler:
-    """``pickle_module`` for ``torch.load``: tensors / containers load normally, every class outside torch, numpy and the
-    standard containers becomes an inert stub, so a fairseq ``xlsr2_300m.pt`` (``cfg`` = omegaconf objects) or a training
-    checkpoint written by ``main.py`` loads on a box that has neither fairseq nor omegaconf."""
+    """``pickle_module`` for ``torch.load``: tensors and plain containers load normally; a global is resolved only when its exact
+    (module, name) is on ``_SAFE_GLOBALS`` (or it is a torch dtype / storage class / numpy scalar type); every other global
+    becomes an inert stub.  So a fairseq ``xlsr2_300m.pt`` (``cfg`` = omegaconf objects) or a training checkpoint written by
+    ``main.py`` loads on a box that has neither fairseq nor omegaconf, and a crafted file cannot reach ``eval`` / ``exec`` /
+    ``os.system`` / ``torch.utils.cpp_extension.load`` through it (tests/test_host.py::test_checkpoint_unpickler_*)."""
     import pickle as _pickle
     __name__ = "pickle"
 
     class Unpickler(_pickle.Unpickler):
         def find_class(self, module, name):
-            if module.split(".")[0] in _SAFE_PICKLE_ROOTS:
+            if _is_safe_global(module, name):
                 return super().find_class(module, name)
             return _stub_class(module, name)
 

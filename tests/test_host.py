@@ -204,6 +204,86 @@ def test_checkpoint_loads_without_fairseq_or_omegaconf(sls, tmp_path):
         torch.save({"note": "no tensors"}, p2); sls.load_checkpoint_tensors(p2)
 
 
+class _Boom:
+    """Pickles as a call of an arbitrary global: ``__reduce__`` -> (callable, args)."""
+    def __init__(self, fn, args): self.fn, self.args = fn, args
+    def __reduce__(self): return self.fn, self.args
+
+
+def test_checkpoint_unpickler_resolves_only_the_allowlist(sls, tmp_path, monkeypatch):
+    """the loader must not execute what a crafted checkpoint names.  Each payload would run code under a plain
+    ``torch.load(weights_only=False)`` (and under a root-module allowlist: all of them live below builtins / os / torch /
+    functools); here every one becomes an inert stub, the marker file is never written, and the tensors still load."""
+    import functools, os as _os, subprocess
+    from importlib import import_module
+    weights = import_module("slsforasvspoof-2021-df_b200.weights")
+    marker = tmp_path / "pwned"
+    cmd = f"touch {marker}"
+    payloads = {
+        "os.system": _Boom(_os.system, (cmd,)),
+        "builtins.eval": _Boom(eval, (f"__import__('os').system({cmd!r})",)),
+        "builtins.exec": _Boom(exec, (f"import os; os.system({cmd!r})",)),
+        "builtins.getattr": _Boom(getattr, ("abc", "upper")),
+        "builtins.__import__": _Boom(__import__, ("os",)),
+        "subprocess.check_output": _Boom(subprocess.check_output, (["touch", str(marker)],)),
+        "functools.partial": _Boom(functools.partial, (_os.system, cmd)),
+        "torch.load": _Boom(torch.load, (str(marker),)),
+        "torch.storage._load_from_bytes": _Boom(torch.storage._load_from_bytes, (b"x",)),
+        "torch.hub.load": _Boom(torch.hub.load, ("a/b", "c")),
+    }
+    good = {"w": torch.arange(6.0).reshape(2, 3), "n": torch.tensor([1, 2], dtype=torch.int64), "h": torch.ones(2, dtype=torch.bfloat16)}
+    for name, boom in payloads.items():
+        path = str(tmp_path / "evil.pt")
+        torch.save({"model": good, "cfg": boom, "extra": [boom, {"k": boom}]}, path)
+        got = sls.load_checkpoint_tensors(path)
+        assert not marker.exists(), name
+        assert set(got) == set(good) and all(torch.equal(got[k], good[k]) for k in good), name
+    # the allowlist is exact pairs, not module roots
+    assert weights._is_safe_global("collections", "OrderedDict") and weights._is_safe_global("torch", "float32")
+    assert weights._is_safe_global("torch", "FloatStorage") and weights._is_safe_global("numpy", "float64")
+    for mod, nm in [("builtins", "eval"), ("builtins", "exec"), ("builtins", "getattr"), ("builtins", "__import__"), ("os", "system"),
+                    ("torch.utils.cpp_extension", "load"), ("torch", "load"), ("torch.storage", "_load_from_bytes"), ("functools", "partial"),
+                    ("copyreg", "__newobj__x"), ("numpy", "load"), ("torch", "hub"), ("torch", "ops"), ("numpy", "ndarray.tofile")]:
+        assert not weights._is_safe_global(mod, nm), (mod, nm)
+    # numpy payloads that fairseq checkpoints really carry (optimizer history, extra_state) still load
+    path = str(tmp_path / "np.pt")
+    torch.save({"model": good, "extra_state": {"best": np.float64(0.25), "hist": np.arange(4), "ns": __import__("argparse").Namespace(lr=[1e-3])}}, path)
+    assert set(sls.load_checkpoint_tensors(path)) == set(good)
+
+
+def test_checkpoint_unpickler_survives_corrupted_files(sls, tmp_path):
+    """Mutation fuzz (like the FLAC decoder's): a byte-flipped or truncated checkpoint either still yields tensors or raises
+    an ordinary exception - no crash, no hang, nothing executed."""
+    import zipfile
+    geo = sls.TrunkGeometry(layers=1)
+    sd = {k: v for k, v in list(sls.TrunkParams(geo).state_dict().items())[:6]}
+    src = tmp_path / "ok.pt"
+    torch.save({"model": sd, "cfg": {"a": [1, 2, 3]}}, str(src))
+    blob = src.read_bytes()
+    with zipfile.ZipFile(str(src)) as z:
+        pkl = [n for n in z.namelist() if n.endswith("data.pkl")][0]
+        info = z.getinfo(pkl)
+    lo = blob.find(b"data.pkl") + 8                                          # mutate inside / around the pickle stream
+    rs = np.random.RandomState(3)
+    outcomes = {"ok": 0, "raised": 0}
+    for trial in range(120):
+        b = bytearray(blob)
+        if trial % 4 == 3:
+            b = b[:rs.randint(16, len(b))]
+        else:
+            for _ in range(rs.randint(1, 4)):
+                b[lo + rs.randint(0, max(1, info.file_size + 64))] ^= 1 << rs.randint(0, 8)
+        pth = tmp_path / "mut.pt"
+        pth.write_bytes(bytes(b))
+        try:
+            got = sls.load_checkpoint_tensors(str(pth))
+            assert all(torch.is_tensor(v) for v in got.values())
+            outcomes["ok"] += 1
+        except Exception:
+            outcomes["raised"] += 1
+    assert outcomes["ok"] + outcomes["raised"] == 120 and outcomes["raised"] > 0
+
+
 def test_shard_ranges_cover_exactly(sls):
     for n, w in [(611829, 8), (10, 4), (3, 8), (0, 2)]:
         r = [sls.shard_range(n, k, w) for k in range(w)]
@@ -420,6 +500,34 @@ def test_flac_decoder_every_syntax_element_against_test_encoder(sls, lib):
     assert _flac_decode(lib, bytes(md5_bad))[0] == -8 and _flac_decode(lib, bytes(md5_bad), verify=0)[0] == len(mono)
 
 
+def test_flac_unknown_length_stream_with_early_stop_and_threads(sls, lib):
+    """(1) STREAMINFO total == 0 ("unknown") + max_samples: the digest covers only the decoded head, so a non-zero
+    stored MD5 must NOT raise a spurious MD5 error - neither at a block boundary nor inside a block; the complete decode of the
+    same stream still verifies it.  (2) first use of the decoder from many threads at once (CRC tables built race-free)."""
+    import concurrent.futures as cf
+    import flac_enc
+    rs = np.random.RandomState(1)
+    x = (6000 * np.sin(np.arange(20000) * 0.03) + rs.randn(20000) * 200).astype(np.int64)
+    data = bytearray(flac_enc.encode(x, kind="lpc8", porder=2, blocksize=4096))
+    si = 8                                                                # "fLaC" + 4-byte block header, then STREAMINFO
+    data[si + 13] &= 0xF0
+    data[si + 14:si + 18] = bytes(4)                                      # 36-bit total-samples field -> 0
+    data = bytes(data)
+    for cut in (4096, 8192, 5000, 1, 19999):
+        n, info, pcm = _flac_decode(lib, data, max_samples=cut)
+        assert n == cut and info[3] == 0 and info[4] == 0 and np.array_equal(pcm[:, 0], x[:cut]), cut
+    n, info, pcm = _flac_decode(lib, data)                                 # decoded to the end: MD5 verified
+    assert n == len(x) and info[4] == 1 and np.array_equal(pcm[:, 0], x)
+    n, info, pcm = _flac_decode(lib, data, max_samples=30000)              # limit beyond the end: still the whole stream
+    assert n == len(x) and info[4] == 1
+    bad = bytearray(data)
+    bad[si + 18 + 3] ^= 0x55                                               # wrong stored MD5: caught on a complete decode only
+    assert _flac_decode(lib, bytes(bad))[0] == -8 and _flac_decode(lib, bytes(bad), max_samples=5000)[0] == 5000
+    with cf.ThreadPoolExecutor(max_workers=16) as ex:
+        outs = list(ex.map(lambda i: sls.decode_flac_bytes(data, 6000 + i, sample_rate=None), range(64)))
+    assert all(np.array_equal(o, x[:6000 + i].astype(np.int16)) for i, o in enumerate(outs))
+
+
 def test_flac_files_to_shard_through_the_ingest_api(sls, tmp_path):
     """read_flac_pcm16 / decode_audio_files / audio_files_to_shard: mono and stereo 16 kHz FLAC + a WAV, heads of 64 600 samples."""
     import flac_enc
@@ -545,6 +653,31 @@ def test_eval_datasets_mirror_the_reference(sls, tmp_path):
     sls.write_wav_pcm16(str(tmp_path / "wild_7.wav"), clips[2])
     x, u = sls.Dataset_in_the_wild_eval(["wild_7.wav"], str(tmp_path) + "/")[0]
     assert u == "wild_7.wav" and np.array_equal(x.numpy(), sls.pad(clips[2].astype(np.float32) / np.float32(32768.0)))
+    # multi-channel input is down-mixed like librosa.load(mono=True): per-channel float32, THEN the float mean - an odd
+    # channel sum keeps its half LSB (the int16 scorer path rounds it); stereo WAV and stereo FLAC, early stop included
+    import wave
+    st = np.stack([clips[2].astype(np.int64), (clips[2].astype(np.int64) // 3) | 1], 1)               # plenty of odd sums
+    want = np.mean(st.astype(np.float32) / np.float32(32768.0), axis=1, dtype=np.float32)              # librosa.to_mono
+    with wave.open(str(tmp_path / "wild_st.wav"), "wb") as w:
+        w.setnchannels(2); w.setsampwidth(2); w.setframerate(16000)
+        w.writeframes(st.astype("<i2").tobytes())
+    (tmp_path / "wild_st.flac").write_bytes(flac_enc.encode(st, kind="fixed2", stereo=10, rate=16000))
+    for name in ("wild_st.wav", "wild_st.flac"):
+        x, _ = sls.Dataset_in_the_wild_eval([name], str(tmp_path) + "/")[0]
+        assert np.array_equal(x.numpy(), sls.pad(want)), name
+        assert np.array_equal(sls.read_audio_float32(str(tmp_path / name), max_samples=777), want[:777])
+        assert np.abs(sls.read_audio_pcm16(str(tmp_path / name)).astype(np.float32) / 32768 - want).max() == pytest.approx(0.5 / 32768)
+    # formats the reference would resample / convert are refused with ONE exception type (never guessed): 8 kHz, 24-bit, junk
+    with wave.open(str(tmp_path / "w8k.wav"), "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(8000); w.writeframes(bytes(200))
+    with wave.open(str(tmp_path / "w24.wav"), "wb") as w:
+        w.setnchannels(1); w.setsampwidth(3); w.setframerate(16000); w.writeframes(bytes(300))
+    (tmp_path / "junk.wav").write_bytes(b"RIFF\x10\x00\x00\x00WAVEfmt \x28\x00\x00\x00\xfe\xff" + bytes(60))       # WAVE_FORMAT_EXTENSIBLE stub
+    for name in ("w8k.wav", "w24.wav", "junk.wav"):
+        with pytest.raises(sls.AudioFormatError):
+            sls.Dataset_in_the_wild_eval([name], str(tmp_path) + "/")[0]
+        with pytest.raises(sls.AudioFormatError):
+            sls.read_wav_pcm16(str(tmp_path / name))
 
 
 def test_evaluate_2021_DF_tool_matches_oracle_eer(sls, tmp_path):
