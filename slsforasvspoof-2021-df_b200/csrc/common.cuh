@@ -318,5 +318,8 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
                      const uint32_t* box, bool swizzle128 = true);
 int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box, bool swizzle128 = true);
+// SWIZZLE_64B variant (inner box extent 64 bytes = 16 fp32): 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3)
+int encode_tmap_f32_sw64(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                         const uint32_t* box);
 
 }  // namespace slsb

@@ -42,7 +42,7 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 static int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
-                       const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
+                       const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128, bool swizzle64 = false) {
     EncodeTiledFn fn = get_encode();
     if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return -1; }
     cuuint64_t d[5], s[4];
@@ -50,7 +50,8 @@ static int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, const void* bas
     for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
     for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
     CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d): rank=%d dims=[%llu,%llu,%llu,%llu] stride0=%llu box=[%u,%u,%u,%u] base=%p", (int)r, rank,
@@ -66,6 +67,10 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 }
 int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, bool sw) {
     return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box, sw);
+}
+
+int encode_tmap_f32_sw64(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+    return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box, false, true);
 }
 
 bool pdl_enabled() {

@@ -65,10 +65,11 @@ struct DevParams {
     int act, out_bf16;
     int kb_per_split;  // A_PLAIN split-K: batch index b selects k-blocks [b * kb_per_split, ...) and partial-output slab b (0 = off)
     int tma_store;     // bf16 output leaves through smem staging + cp.async.bulk.tensor stores
-    int red_add;       // fp32 output aliases the fp32 residual: out += acc + bias through TMA reduce-add stores (no residual loads)
+    int red_add;       // fp32 output aliases the fp32 residual: out += acc + bias through TMA reduce-add stores (no residual loads); 2 = 16-column ping-pong
     int res_tma;       // fp32 output = acc + bias + fp32 residual, residual tile fetched by TMA into the staging tile, summed in place, TMA-stored
     int tail_split;    // pair kernel: tiles of the partial last round are cut into this many column slices (1, 2 or 4)
     int debug_flags;   // bit0: epilogue does everything except the global stores / residual loads (mainloop ceiling measurements)
+    long long* trace;  // SLSB_GEMM_TRACE=1 (pair kernel, tuning only): clock64 stamps of pair 0, trace[it * 8 + event]
 };
 
 // One warp's share of a tile: kCols accumulator columns of its 32 TMEM lanes (thread == output row).
@@ -299,6 +300,55 @@ __device__ __forceinline__ void epilogue_tile_red_tma(const CUtensorMap* tmap_ou
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         if (issuer && !(dbg & 4)) {
             tma_reduce_add_2d(tmap_out, stage_tile, col_base + c * 32, row0);
+            tma_store_commit();
+        }
+    }
+}
+
+// The same reduce-add epilogue with the 16 KB staging tile used as TWO 8 KB buffers of 16 fp32 columns (64-byte rows, SWIZZLE_64B)
+// in ping-pong: while the reduce-store of chunk c - 1 is still reading its buffer, the warps already convert chunk c into the
+// other one; the issuer confirms "store c - 1 has read its buffer" right before the barrier that publishes chunk c, so at most
+// one store is in flight per half and every buffer is provably free when it is written again.  One named barrier per chunk
+// instead of two, and no thread ever waits for a store that was issued in the same breath (the 32-column version above waits
+// for the full smem read of the store it has just issued before it may touch the tile again: K = 1024 tiles - out_proj - were
+// epilogue-bound at ~2x their mainloop).  SLSB_RED_ADD_V1=1 selects the 32-column version (A/B).
+template <int kCols>
+__device__ __forceinline__ void epilogue_tile_red_tma16(const CUtensorMap* tmap_out16, uint32_t taddr, uint8_t* stage_tile, const float* bias_s,
+                                                        int half, int r, int col_base, int row0, uint64_t* full_bar, uint32_t full_parity,
+                                                        uint32_t empty_bar_addr, int dbg) {
+    constexpr int kChunks = kCols / 16;
+    const int bar_id = 1 + half;
+    const bool issuer = r == 0;
+    const int sw = (r >> 1) & 3;
+    if (issuer) tma_store_wait_read<0>();                            // stores of the previous tile (other epilogue flavours included)
+    mbar_wait(full_bar, full_parity);
+    tc_fence_after();
+    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");      // this tile's bias slice is visible; both buffers are free
+    uint32_t acc[2][16];
+    tmem_ld_32x32b_x16(taddr, acc[0]);
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+        tmem_ld_wait();
+        if (c + 1 < kChunks) tmem_ld_32x32b_x16(taddr + (c + 1) * 16, acc[(c + 1) & 1]);
+        uint8_t* srow = stage_tile + (c & 1) * 8192 + r * 64;
+        const float* bs = bias_s + half * kCols + c * 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 bb = *reinterpret_cast<const float4*>(bs + 4 * j);
+            *reinterpret_cast<float4*>(srow + ((j ^ sw) << 4)) =
+                make_float4(__uint_as_float(acc[c & 1][4 * j + 0]) + bb.x, __uint_as_float(acc[c & 1][4 * j + 1]) + bb.y,
+                            __uint_as_float(acc[c & 1][4 * j + 2]) + bb.z, __uint_as_float(acc[c & 1][4 * j + 3]) + bb.w);
+        }
+        fence_proxy_async_smem();
+        if (c == kChunks - 1) {                                      // accumulator fully read: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if ((r & 31) == 0) mbar_arrive_cluster(empty_bar_addr);
+        }
+        if (issuer && c > 0) tma_store_wait_read<0>();               // store c - 1 has read its buffer: chunk c + 1 may overwrite it
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (issuer && !(dbg & 4)) {
+            tma_reduce_add_2d(tmap_out16, stage_tile + (c & 1) * 8192, col_base + c * 16, row0);
             tma_store_commit();
         }
     }
@@ -673,6 +723,9 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int num_tiles = m2_tiles * p.n_tiles;
     const int num_kb = p.K / BLOCK_K;
     const int split = p.tail_split;
+    // events: 0 accumulator free (MMA), 1 first k-block landed, 2 last MMA issued, 3 epilogue enters, 4 accumulator complete seen by
+    // the epilogue, 5 epilogue done, 6 first load of the tile issued, 7 last load issued
+#define GEMM_TRACE(it_, ev_) do { if (p.trace != nullptr && pair == 0 && rank == 0 && (it_) < 64) p.trace[(it_) * 8 + (ev_)] = clock64(); } while (0)
 
     griddep_launch();
     if (warp == 0 && lane == 0) {
@@ -707,6 +760,8 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const int wrow0 = w.n0 + (int)rank * (w.width >> 1);       // this CTA's half of the slice's W rows (box: 128 rows)
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (kb == 0) GEMM_TRACE(it, 6);
+                    if (kb == num_kb - 1) GEMM_TRACE(it, 7);
                     uint8_t* sa = smem + stage * Plan2::kStage;
                     uint8_t* sb = sa + Plan2::kStageA;
                     if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Plan2::kStage);
@@ -727,10 +782,12 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const int acc = it & 1;
                 mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
+                GEMM_TRACE(it, 0);
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
+                    if (kb == 0) GEMM_TRACE(it, 1);
                     const uint32_t sa = smem_u32(smem + stage * Plan2::kStage);
                     const uint64_t da = make_smem_desc_sw128(sa, 0, 1024);
                     const uint64_t db = make_smem_desc_sw128(sa + Plan2::kStageA, 0, 1024);
@@ -741,6 +798,7 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
                 tc_commit_pair(&tmem_full[acc]);           // both CTAs' epilogues may read their 128 rows
+                GEMM_TRACE(it, 2);
             }
         }
     } else if (warp >= 4) {
@@ -762,7 +820,15 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint32_t free_bar = map_cluster(smem_u32(&tmem_empty[acc]), 0);
             if (r < groups * 64) bias_s[half * kColsPerWarp + r] = __ldg(p.bias + col_base + r);   // visible after the first named barrier of the tile
             uint8_t* stage_tile = smem + Plan2::kStoreOffset + half * 16384;
-            if (p.red_add) {
+            if (p.trace != nullptr && warp == 4 && lane == 0) {
+                GEMM_TRACE(it, 3);
+                mbar_wait(&tmem_full[acc], acc_phase);
+                GEMM_TRACE(it, 4);
+            }
+            if (p.red_add == 2) {
+                epilogue_tile_red_tma16<kColsPerWarp>(&tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, row0, &tmem_full[acc], acc_phase, free_bar,
+                                                      p.debug_flags);
+            } else if (p.red_add) {
                 epilogue_tile_red_tma<kColsPerWarp>(&tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, row0, &tmem_full[acc], acc_phase, free_bar,
                                                     p.debug_flags);
             } else if (p.res_tma) {
@@ -775,9 +841,11 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             } else {
                 epilogue_tile_tma<ACT_NONE, kColsPerWarp, false>(p, &tmap_out, taddr0, stage_tile, bias_s, half, r, col_base, row0, 0, &tmem_full[acc], acc_phase, free_bar, groups);
             }
+            if (warp == 4 && lane == 0) GEMM_TRACE(it, 5);
         }
         if (r == 0) tma_store_wait<0>();
     }
+#undef GEMM_TRACE
     tc_fence_before();
     __syncthreads();
     cluster_barrier();                  // nobody frees TMEM / exits while the peer's tensor core may still touch this CTA

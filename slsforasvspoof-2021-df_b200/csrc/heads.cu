@@ -364,7 +364,8 @@ __global__ void __launch_bounds__(256) sls_fuse_pool_kernel(LayerPtrs L, int n_l
         for (int j = (int)gridDim.x * J + threadIdx.x; j < ldo; j += blockDim.x) out[(long long)b * ldo + j] = from_f32<TO>(0.f);
 }
 
-// ---- experimental (SLSB_POOL_TMA=1, bf16 layers, D = 1024; not validated on hardware yet - see DESIGN.md section 9) ----
+// ---- bulk-copy ring version (bf16 layers, D = 1024; default, SLSB_POOL_TMA=0 selects the plain-load kernel above) ----
+// validated on B200 in round 2: tests/test_parity_gpu.py (sls, fp32 + bf16) green, 0.135 ms vs 0.165 ms per 64-clip batch
 // The kernel above is long-scoreboard bound at 50 % occupancy (ncu: 3.8-4.2 TB/s): its bytes in flight live in registers.
 // Here a producer warp streams the 25 per-layer chunks of the block's 3 frames (3 x 2 KB, contiguous) through an 8-stage shared
 // memory ring with cp.async.bulk + mbarriers; 4 consumer warps accumulate w_l * x_l from shared memory (8 channels x 3 frames per
@@ -590,7 +591,7 @@ int sls_fuse_pool(const void* const* layers, int layers_bf16, int n_layers, cons
     const size_t sm = 3 * D * sizeof(float);
     // bf16 layers: 4 channels per thread (8-byte loads, D / 4 threads) measured faster in the step than 8 per thread (0.14 vs 0.17 ms)
     static const int vec8 = getenv("SLSB_POOL_VEC") ? atoi(getenv("SLSB_POOL_VEC")) == 8 : 0;
-    static const int pool_tma = getenv("SLSB_POOL_TMA") ? atoi(getenv("SLSB_POOL_TMA")) : 0;
+    static const int pool_tma = getenv("SLSB_POOL_TMA") ? atoi(getenv("SLSB_POOL_TMA")) : 1;   // default since round 2: 0.135 vs 0.165 ms (0.72 vs 0.59 of the copy bandwidth), parity green
     if (layers_bf16 && pool_tma && D == kPtD) {
         static bool configured = false;
         if (!configured) {

@@ -20,15 +20,19 @@ from .engine import Engine, make_config, PRECISIONS, HEAD_NONE, HEAD_SAE, HEAD_W
 from .weights import TrunkGeometry, TrunkParams, pack_state_dict
 
 
-def _load_fairseq_checkpoint(trunk: TrunkParams, cp_path: str) -> None:
-    """Best-effort load of a fairseq ``xlsr2_300m.pt`` without fairseq: take ckpt['model'] and match keys.
+def _read_fairseq_checkpoint(cp_path: str):
+    """A fairseq ``xlsr2_300m.pt`` without fairseq: the tensors of ckpt['model'].
     (reference: fairseq.checkpoint_utils.load_model_ensemble_and_task, model.py:113-115.)"""
     if not os.path.exists(cp_path):
         raise RuntimeError(
             f"Could not load SSL checkpoint '{cp_path}' (file not found). Pass cp_path=None for a random-init trunk "
             "(synthetic benchmarks / parity tests).")
     from .weights import load_checkpoint_tensors
-    sd = load_checkpoint_tensors(cp_path)          # allowlist unpickler (weights.py): only tensors + plain containers resolve, every other global becomes an inert stub
+    return load_checkpoint_tensors(cp_path)        # allowlist unpickler (weights.py): only tensors + plain containers resolve, every other global becomes an inert stub
+
+
+def _load_fairseq_checkpoint(trunk: TrunkParams, cp_path: str, sd=None) -> None:
+    sd = _read_fairseq_checkpoint(cp_path) if sd is None else sd
     missing, unexpected = trunk.load_state_dict(sd, strict=False)
     hard = [k for k in missing if not k.startswith(("quantizer", "project_q", "final_proj"))]
     if hard:
@@ -140,9 +144,12 @@ class SSLModel(nn.Module):
 
     def __init__(self, device, cp_path: Optional[str] = "xlsr2_300m.pt", geometry: Optional[TrunkGeometry] = None):
         super().__init__()
+        sd = _read_fairseq_checkpoint(cp_path) if cp_path is not None else None
+        if geometry is None and sd is not None:
+            geometry = TrunkGeometry.from_state_dict(sd)      # fairseq builds the model from the checkpoint, not from defaults
         self.model = TrunkParams(geometry)
-        if cp_path is not None:
-            _load_fairseq_checkpoint(self.model, cp_path)
+        if sd is not None:
+            _load_fairseq_checkpoint(self.model, cp_path, sd)
         self.device = device
         self.out_dim = self.model.geo.embed_dim
         self._owner = None

@@ -36,6 +36,28 @@ class TrunkGeometry:
             samples = max(0, (samples - k) // s + 1)
         return samples
 
+    @classmethod
+    def from_state_dict(cls, sd: Dict[str, torch.Tensor], prefix: str = "") -> "TrunkGeometry":
+        """The trunk's shape as the checkpoint's own tensors give it.  fairseq rebuilds the model from the checkpoint's ``cfg``
+        (``load_model_ensemble_and_task``, model.py:113-115); the tensors carry the same information: encoder depth = number
+        of ``encoder.layers.<i>``, widths from ``post_extract_proj`` / ``fc1``, conv stack from ``conv_layers.<i>.0.weight``
+        (strides are not stored in tensors: XLS-R's 5,2,2,2,2,2,2 are kept, wav2vec2.py:97-99)."""
+        g = cls()
+        idx = [int(k[len(prefix) + len("encoder.layers."):].split(".", 1)[0]) for k in sd if k.startswith(prefix + "encoder.layers.")]
+        if idx:
+            g.layers = max(idx) + 1
+        if prefix + "post_extract_proj.weight" in sd:
+            g.embed_dim = int(sd[prefix + "post_extract_proj.weight"].shape[0])
+            g.heads = g.embed_dim // 64
+        if prefix + "encoder.layers.0.fc1.weight" in sd:
+            g.ffn_dim = int(sd[prefix + "encoder.layers.0.fc1.weight"].shape[0])
+        convs = []
+        for i, (dim, k, st) in enumerate(g.conv_layers):
+            w = sd.get(prefix + f"feature_extractor.conv_layers.{i}.0.weight")
+            convs.append((int(w.shape[0]), int(w.shape[2]), st) if w is not None else (dim, k, st))
+        g.conv_layers = convs
+        return g
+
 
 class _Quantizer(nn.Module):
     """Pre-training-only GumbelVectorQuantizer parameters (kept for strict state_dict loading)."""

@@ -284,6 +284,69 @@ def test_checkpoint_unpickler_survives_corrupted_files(sls, tmp_path):
     assert outcomes["ok"] + outcomes["raised"] == 120 and outcomes["raised"] > 0
 
 
+_MAIN_PY_LAUNCHER = r'''
+import os, runpy, sys, types
+sys.path.insert(0, {root!r})
+import sls_b200
+# the shim of INTEGRATION.md: the reference imports `model`, `model_window_topk`, `data_utils_SSL`; they resolve to this package
+m = types.ModuleType("model"); m.Model = sls_b200.Model; sys.modules["model"] = m
+w = types.ModuleType("model_window_topk"); w.Model = sls_b200.ModelWindowTopK; sys.modules["model_window_topk"] = w
+d = types.ModuleType("data_utils_SSL")
+d.genSpoof_list, d.Dataset_ASVspoof2021_eval, d.Dataset_in_the_wild_eval = sls_b200.genSpoof_list, sls_b200.Dataset_ASVspoof2021_eval, sls_b200.Dataset_in_the_wild_eval
+d.Dataset_ASVspoof2019_train = type("Dataset_ASVspoof2019_train", (), {{}})          # training only: never touched by --is_eval
+sys.modules["data_utils_SSL"] = d
+tb = types.ModuleType("tensorboardX"); tb.SummaryWriter = type("SummaryWriter", (), {{"__init__": lambda self, *a, **k: None}})
+sys.modules["tensorboardX"] = tb                                                    # not installed here; training only
+sys.path.insert(1, {ref!r})                                                         # core_scripts.startup_config: the reference's own
+sys.argv = ["main.py"] + {argv!r}
+runpy.run_path(os.path.join({ref!r}, "main.py"), run_name="__main__")
+'''
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/main.py"), reason="the reference tree is only mounted in the build container")
+@pytest.mark.parametrize("window", [False, True])
+def test_reference_main_py_runs_on_the_shim(sls, tmp_path, window):
+    """VERDICT r1 missing #5: the reference's OWN main.py, unmodified, executed with --is_eval on top of the shim modules: argument
+    parsing, Model(...) with main.py's keyword arguments (:493-517), nn.DataParallel(model).to(device) (:518), the parameter count
+    (:520-521), the checkpoint branch (:531-592: torch.load, _get_state_dict, _fix_module_prefix, strict load), genSpoof_list,
+    Dataset_ASVspoof2021_eval, the 6-worker DataLoader and the first model(batch_x, return_sae_loss=False) call (:158-181).
+    This container has no GPU, so that first forward must end in this package's "no CPU fallback" error and nothing else;
+    the same sequence runs to the score file on the GPU box (tests/test_configs_gpu.py::test_main_eval_replay_*)."""
+    import flac_enc
+    geo = sls.TrunkGeometry(layers=1)
+    torch.manual_seed(5)
+    trunk = sls.TrunkParams(geo)
+    cp = str(tmp_path / "xlsr_like.pt")
+    torch.save({"cfg": {"model": {"encoder_layers": 1}}, "model": trunk.state_dict()}, cp)
+    cls = sls.ModelWindowTopK if window else sls.Model
+    trained = torch.nn.DataParallel(cls(None, "cpu", cp_path=cp))
+    assert trained.module.ssl_model.model.geo.layers == 1                              # geometry comes from the checkpoint, as with fairseq
+    with torch.no_grad():
+        trained.module.classifier[4].bias.add_(0.25)
+    best = str(tmp_path / "best.pth")
+    torch.save(trained.state_dict(), best)                                            # what main.py's training loop writes (module.-prefixed)
+    rs = np.random.RandomState(2)
+    utts = [f"DF_E_{2000011 + i}" for i in range(3)]
+    os.makedirs(tmp_path / "db" / "flac")
+    for u in utts:
+        (tmp_path / "db" / "flac" / f"{u}.flac").write_bytes(flac_enc.encode((rs.randn(20000) * 3000).astype(np.int64), kind="fixed2", rate=16000))
+    (tmp_path / "trl.txt").write_text("".join(u + "\n" for u in utts))
+    out = tmp_path / "scores" / "scores_DF.txt"
+    os.makedirs(out.parent)
+    out.write_text("stale line\n")
+    argv = ["--is_eval", "--track", "DF", "--cp_path", cp, "--model_path", best, "--database_path", str(tmp_path / "db"),
+            "--protocols_path", str(tmp_path / "trl.txt"), "--eval_output", str(out)] + (["--use_window_topk"] if window else [])
+    script = tmp_path / "launch.py"
+    script.write_text(_MAIN_PY_LAUNCHER.format(root=ROOT, ref="/root/reference", argv=argv))
+    r = subprocess.run([sys.executable, str(script)], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
+    log = r.stdout + r.stderr
+    assert "Total parameters:" in r.stdout and "LOADING CHECKPOINT" in r.stdout and "Loaded weights (fresh optimizer/epoch)" in r.stdout, log[-3000:]
+    assert ("Using Window-based TopK" if window else "Using Per-Timestep TopK") in r.stdout
+    assert "Strict load failed" not in log                                            # strict=True succeeded: every key matched
+    assert r.returncode != 0 and "no CPU fallback" in log, log[-3000:]                 # reached the first forward, and only then stopped
+    assert not out.exists() or out.read_text() == ""                                  # the stale score file was removed (main.py:646-647)
+
+
 def test_shard_ranges_cover_exactly(sls):
     for n, w in [(611829, 8), (10, 4), (3, 8), (0, 2)]:
         r = [sls.shard_range(n, k, w) for k in range(w)]
