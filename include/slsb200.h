@@ -33,6 +33,12 @@ extern "C" {
 #define SLSB_ABI_VERSION 1
 
 enum { SLSB_HEAD_NONE = 0, SLSB_HEAD_SAE = 1, SLSB_HEAD_WINDOW = 2, SLSB_HEAD_SLS = 3 };
+/* OR-ed into `head`: keep this forward's intermediates readable afterwards through slsb_get_tensor("layer_results.<i>" / "acts" /
+ * "encoded"), slsb_get_sparse and slsb_sae_loss.  Without it a forward keeps only what the score needs ("x", "pooled",
+ * "sls_weights"): the bf16 layer-result snapshots are written only for the SLS head (which consumes them), and the SAE heads run
+ * their fused select + pool path, which never materialises per-row thresholds or dense codes (model.py:236-240 and :224-225 are the
+ * reference paths that need them: return_interpretability / return_sae_loss). */
+#define SLSB_HEAD_RETAIN 0x100
 enum { SLSB_PREC_FP32 = 0, SLSB_PREC_BF16 = 1 };
 enum { SLSB_ATTN_AUTO = 0, SLSB_ATTN_SIMT = 1, SLSB_ATTN_TC = 2 /* persistent, P in TMEM */, SLSB_ATTN_TC_V1 = 3 /* one CTA per query tile, P in smem */ };
 

@@ -11,7 +11,7 @@ Everything numerical happens in ``libslsb200.so`` (``csrc/``, C ABI in ``include
 imports ``oracle/``.
 """
 from ._lib import SlsbError, LIB_PATH, EXPORTED_SYMBOLS, load as load_library
-from .engine import Engine, make_config, PRECISIONS, HEAD_NONE, HEAD_SAE, HEAD_WINDOW, HEAD_SLS, PREC_FP32, PREC_BF16
+from .engine import Engine, make_config, PRECISIONS, HEAD_NONE, HEAD_SAE, HEAD_WINDOW, HEAD_SLS, HEAD_RETAIN, PREC_FP32, PREC_BF16
 from .weights import TrunkGeometry, TrunkParams, pack_state_dict, load_checkpoint_tensors, load_model_checkpoint, fix_module_prefix
 from .model import Model, ModelWindowTopK, ModelSLS, SSLModel, AutoEncoderTopK, getAttenF
 from .scoring import (produce_evaluation_file, score_synthetic_shard, gather_scores, write_score_file, pad_clip,
@@ -27,7 +27,7 @@ __all__ = ["Model", "ModelWindowTopK", "ModelSLS", "SSLModel", "AutoEncoderTopK"
            "gather_scores", "write_score_file", "pad_clip", "SyntheticEvalSet", "shard_range", "bucket_by_frames",
            "score_variable_length", "compute_eer", "read_score_file", "synth_clip_host", "SlsbError",
            "load_library", "LIB_PATH", "EXPORTED_SYMBOLS", "PRECISIONS", "HEAD_NONE", "HEAD_SAE", "HEAD_WINDOW",
-           "HEAD_SLS", "PREC_FP32", "PREC_BF16", "read_wav_pcm16", "write_wav_pcm16", "decode_wav_files", "write_pcm_shard",
+           "HEAD_SLS", "HEAD_RETAIN", "PREC_FP32", "PREC_BF16", "read_wav_pcm16", "write_wav_pcm16", "decode_wav_files", "write_pcm_shard",
            "wav_files_to_shard", "PcmShard", "score_pcm_shard", "AudioFormatError", "decode_flac_bytes", "read_flac_pcm16",
            "read_audio_pcm16", "read_audio_float32", "decode_audio_files", "audio_files_to_shard", "score_audio_files", "genSpoof_list", "pad", "Dataset_ASVspoof2021_eval",
            "Dataset_in_the_wild_eval"]

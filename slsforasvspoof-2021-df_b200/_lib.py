@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libslsb200.so")
 
 HEAD_NONE, HEAD_SAE, HEAD_WINDOW, HEAD_SLS = 0, 1, 2, 3
+HEAD_RETAIN = 0x100     # OR-ed into the head: keep layer results / SAE intermediates readable after the forward
 PREC_FP32, PREC_BF16 = 0, 1
 ATTN_AUTO, ATTN_SIMT, ATTN_TC, ATTN_TC_V1 = 0, 1, 2, 3
 

@@ -145,7 +145,7 @@ struct slsb_engine {
     bool inplace = false;
     // last call
     int B = 0, S = 0, T = 0, prec = 0, head = 0;
-    bool have_lens = false, have_acts = false, have_sel = false, have_dots = false;
+    bool have_lens = false, have_acts = false, have_sel = false, have_dots = false, have_snap = false;
     int sls_ks = 17, sls_kp = 0;      // fp32 path: 17-way split-K over Kp (a multiple of 16 * 17 * 4 = 1088, so also of the 64-wide k-blocks)
     // optional per-launch CUDA-event timing of the tensor-core kernels (bench.py roofline)
     bool profiling = false;
@@ -155,7 +155,7 @@ struct slsb_engine {
 
 // kinds 0-7 count FLOPs, kinds 8+ count algorithmic HBM bytes (HBM-bound kernels)
 enum ProfKind { PK_ENC_QKV = 0, PK_ENC_OUT = 1, PK_ENC_FC1 = 2, PK_ENC_FC2 = 3, PK_CONV_GEMM = 4, PK_POS_GEMM = 5, PK_OTHER_GEMM = 6, PK_ATTN = 7,
-                PK_LN = 8, PK_SLS_POOL = 9, PK_SLS_FC1 = 10, PK_COUNT = 11 };
+                PK_LN = 8, PK_SLS_POOL = 9, PK_SLS_FC1 = 10, PK_SAE_GEMM = 11, PK_SAE_SELECT = 12, PK_CLS = 13, PK_COUNT = 14 };
 
 struct ProfScope {
     slsb_engine* e; cudaStream_t st; int idx = -1;
@@ -361,8 +361,10 @@ static int check_ready(slsb_engine* e) {
 }
 
 // ---- the trunk: wav -> X[0..n_layers], xfinal (+ xc = xfinal - b_dec) ---------------------------
-static int run_trunk(slsb_engine* e, const float* wav, const int* slens, int B, int S, int prec, int head, cudaStream_t st) {
+static int run_trunk(slsb_engine* e, const float* wav, const int* slens, int B, int S, int prec, int head_flags, cudaStream_t st) {
     const slsb_config& c = e->cfg;
+    const int head = head_flags & 0xFF;
+    const bool retain = (head_flags & SLSB_HEAD_RETAIN) != 0;
     const bool bf = prec == SLSB_PREC_BF16;
     const size_t es = bf ? 2 : 4;
     const int C = c.conv_dim, D = c.embed_dim, F = c.ffn_dim, H = c.n_heads;
@@ -387,6 +389,9 @@ static int run_trunk(slsb_engine* e, const float* wav, const int* slens, int B, 
     if (inplace_env < 0) { const char* v = getenv("SLSB_INPLACE"); inplace_env = v ? atoi(v) : 1; }
     const bool inplace = bf && inplace_env != 0;
     e->inplace = inplace;
+    // bf16 layer-result snapshots (wav2vec2.py:958 layer_results): consumed by the SLS head, otherwise only on request
+    const bool want_snap = head == SLSB_HEAD_SLS || retain;
+    e->have_snap = !inplace || want_snap;
     if ((int)e->X.size() < c.n_layers + 1) e->X.resize(c.n_layers + 1);
     if ((int)e->snap.size() < c.n_layers) e->snap.resize(c.n_layers);
     if (inplace) {
@@ -478,7 +483,7 @@ static int run_trunk(slsb_engine* e, const float* wav, const int* slens, int B, 
                 float* xs = e->X[0].as<float>();
                 LnArgs a;      // LN1 reads the stream = layer result l - 1: snapshot it (bf16) and emit the SLS fc0 dots on the way
                 a.in = xs; a.out = e->lnbuf.p; a.out_bf16 = 1; a.w = W32(p + ".ln1.w"); a.b = W32(p + ".ln1.b"); a.rows = M; a.C = D;
-                if (l > 0) {
+                if (l > 0 && want_snap) {
                     a.copy_out = e->snap[l - 1].p;
                     if (want_dots) { a.dot_w = W32("sls.fc0.w"); a.dot_out = dots + (long long)(l - 1) * M; }
                 }
@@ -523,7 +528,7 @@ static int run_trunk(slsb_engine* e, const float* wav, const int* slens, int B, 
         }
         // 5. X_n = xmid + fc2_{n-1}; final LayerNorm on x only (wav2vec2.py:905-906); xc = x - b_dec feeds the SAE (model.py:70)
         LnArgs a;
-        if (inplace) { a.in = e->X[0].p; a.copy_out = e->snap[c.n_layers - 1].p; }
+        if (inplace) { a.in = e->X[0].p; if (want_snap) a.copy_out = e->snap[c.n_layers - 1].p; }
         else if (res_in_gemm) a.in = e->X[c.n_layers].p;
         else { a.in = e->xmid.p; a.add = e->ybuf.p; a.sum_out = e->X[c.n_layers].as<float>(); }
         a.out = e->xfinal.p; a.w = W32("enc_ln.w"); a.b = W32("enc_ln.b"); a.rows = M; a.C = D;
@@ -562,7 +567,7 @@ static int run_trunk(slsb_engine* e, const float* wav, const int* slens, int B, 
 static int sae_acts(slsb_engine* e, bool bf, const void* xc, long long rows, cudaStream_t st) {
     const slsb_config& c = e->cfg;
     if (e->acts.reserve((size_t)rows * c.sae_dict * 4)) return -1;
-    return linear(e, bf, xc, c.embed_dim, "sae.enc.w", c.sae_dict, c.embed_dim, rows, W32("sae.enc.b"), nullptr, 0, e->acts.p, c.sae_dict, 0, ACT_RELU, st);
+    return linear(e, bf, xc, c.embed_dim, "sae.enc.w", c.sae_dict, c.embed_dim, rows, W32("sae.enc.b"), nullptr, 0, e->acts.p, c.sae_dict, 0, ACT_RELU, st, PK_SAE_GEMM);
 }
 
 // selection pass: fills thr/cut (and votes for the window variant); `sel` is what the keep-rule looks at
@@ -591,8 +596,11 @@ static int sae_select(slsb_engine* e, long long rows, int T, int window, const f
     return 0;
 }
 
-static int run_head(slsb_engine* e, int head, int prec, float* logprob, cudaStream_t st) {
+static int run_head(slsb_engine* e, int head_flags, int prec, float* logprob, cudaStream_t st) {
     const slsb_config& c = e->cfg;
+    const int head = head_flags & 0xFF;
+    const bool retain = (head_flags & SLSB_HEAD_RETAIN) != 0;
+    (void)retain;
     const bool bf = prec == SLSB_PREC_BF16;
     const int B = e->B, T = e->T, D = c.embed_dim;
     const long long M = (long long)B * T;
@@ -605,10 +613,14 @@ static int run_head(slsb_engine* e, int head, int prec, float* logprob, cudaStre
             if (window > 1 && flens) { set_error("window top-k with per-utterance lengths is not defined by the reference"); return -1; }
             if (sae_acts(e, bf, e->xc.p, M, st)) return -1;
             const float* sel = nullptr;
-            if (sae_select(e, M, T, window, &sel, st)) return -1;
-            e->have_acts = true; e->have_sel = true;
+            {   // algorithmic bytes of selection + pooling: the fp32 activations read once
+                ProfScope ps(e, st, PK_SAE_SELECT, (double)M * c.sae_dict * 4);
+                if (sae_select(e, M, T, window, &sel, st)) return -1;
+                e->have_acts = true; e->have_sel = true;
+                if (c.cls_in == c.sae_dict)
+                    LAUNCH(votes_mean_pool(e->acts.as<float>(), sel, e->thr.as<float>(), e->cut.as<int>(), e->pooled.as<float>(), B, T, c.sae_dict, flens, st));
+            }
             if (c.cls_in == c.sae_dict) {
-                LAUNCH(votes_mean_pool(e->acts.as<float>(), sel, e->thr.as<float>(), e->cut.as<int>(), e->pooled.as<float>(), B, T, c.sae_dict, flens, st));
             } else {
                 // use_sparse_features=False: classifier sees the reconstruction (model.py:231-233)
                 if (e->encoded.reserve((size_t)M * c.sae_dict * 4) || e->recon.reserve((size_t)M * D * 4)) return -1;
@@ -627,6 +639,7 @@ static int run_head(slsb_engine* e, int head, int prec, float* logprob, cudaStre
         }
         if (e->scratch.reserve((size_t)(B * c.cls_hidden + 1024) * 4)) return -1;
         ++e->launches;
+        ProfScope ps(e, st, PK_CLS, (double)c.cls_hidden * c.cls_in * 4);
         LAUNCH(classifier_head(e->pooled.as<float>(), B, c.cls_in, c.cls_hidden, W32("cls.ln.w"), W32("cls.ln.b"), W32("cls.fc1.w"), W32("cls.fc1.b"),
                                W32("cls.fc2.w"), W32("cls.fc2.b"), e->scratch.as<float>(), logprob, st));
         return 0;
@@ -766,16 +779,18 @@ int slsb_finalize_weights(slsb_engine* e, void* stream) {
 int slsb_frames_for_samples(const slsb_engine* e, int samples) { return e ? conv_len(e->cfg, samples) : -1; }
 int64_t slsb_launch_count(const slsb_engine* e) { return e ? e->launches : -1; }
 
-int slsb_forward(slsb_engine* e, const float* wav_dev, const int32_t* sample_lens_dev, int B, int S, int head, int precision,
+int slsb_forward(slsb_engine* e, const float* wav_dev, const int32_t* sample_lens_dev, int B, int S, int head_flags, int precision,
                  float* logprob_dev, void* stream) {
     if (check_ready(e)) return -1;
     DeviceGuard guard(e->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (run_trunk(e, wav_dev, sample_lens_dev, B, S, precision, head, st)) return -1;
+    const int head = head_flags & 0xFF;
+    if (head_flags & ~(0xFF | SLSB_HEAD_RETAIN)) { set_error("slsb_forward: unknown head flags 0x%x", head_flags); return -1; }
+    if (run_trunk(e, wav_dev, sample_lens_dev, B, S, precision, head_flags, st)) return -1;
     e->head = head;
     if (head == SLSB_HEAD_NONE) return 0;
     if (!logprob_dev) { set_error("slsb_forward: logprob_dev is null"); return -1; }
-    return run_head(e, head, precision, logprob_dev, st);
+    return run_head(e, head_flags, precision, logprob_dev, st);
 }
 
 int slsb_extract_feat(slsb_engine* e, const float* wav_dev, const int32_t* sample_lens_dev, int B, int S, int precision, float* x_dev, void* stream) {
@@ -803,6 +818,7 @@ int slsb_get_tensor(slsb_engine* e, const char* name, float* dst, int64_t numel,
         const int i = atoi(n.c_str() + 14);
         if (i < 0 || i >= c.n_layers) { set_error("slsb_get_tensor: layer %d out of range", i); return -1; }
         want = M * c.embed_dim;
+        if (!e->have_snap) { set_error("slsb_get_tensor: layer results were not retained by the last forward (pass head | SLSB_HEAD_RETAIN)"); return -1; }
         if (e->inplace) {      // bf16 snapshot of the layer result -> fp32
             if (numel != want) { set_error("slsb_get_tensor: '%s' has %lld elements, caller gave %lld", name, (long long)want, (long long)numel); return -1; }
             ++e->launches;
@@ -906,7 +922,7 @@ int64_t slsb_score_submit(slsb_engine* e, const float* wav_host, const int32_t* 
     if (check_ready(e)) return -1;
     DeviceGuard guard(e->device);
     if (!wav_host || !scores_host) { set_error("slsb_score_submit: null buffer"); return -1; }
-    if (head == SLSB_HEAD_NONE) { set_error("slsb_score_submit: a classifier head is required"); return -1; }
+    if ((head & 0xFF) == SLSB_HEAD_NONE) { set_error("slsb_score_submit: a classifier head is required"); return -1; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!e->copy_stream) {
         SLSB_CUDA_CHECK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
@@ -969,7 +985,7 @@ int slsb_score_pcm16_host(slsb_engine* e, const int16_t* pcm_host, int64_t total
     if (check_ready(e)) return -1;
     DeviceGuard guard(e->device);
     if (!pcm_host || !offsets_host || !lens_host || !scores_host) { set_error("slsb_score_pcm16_host: null buffer"); return -1; }
-    if (head == SLSB_HEAD_NONE) { set_error("slsb_score_pcm16_host: a classifier head is required"); return -1; }
+    if ((head & 0xFF) == SLSB_HEAD_NONE) { set_error("slsb_score_pcm16_host: a classifier head is required"); return -1; }
     for (int b = 0; b < B; ++b) {
         if (lens_host[b] < 1 || offsets_host[b] < 0 || offsets_host[b] + lens_host[b] > total_samples) {
             set_error("slsb_score_pcm16_host: clip %d (offset %lld, %d samples) is empty or outside the %lld-sample buffer", b,

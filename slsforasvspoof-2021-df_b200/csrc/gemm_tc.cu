@@ -886,6 +886,29 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     q.tail_split = 1;
     static const bool tail_on = !(getenv("SLSB_NO_TAIL_SPLIT") && atoi(getenv("SLSB_NO_TAIL_SPLIT")) != 0);
     if (tail_on && dp.tma_store && !dp.red_add && !dp.res_tma) q.tail_split = pair_tail_split(tiles, pairs);   // bf16 TMA-store epilogue handles column slices
+    static const bool trace_on = getenv("SLSB_GEMM_TRACE") && atoi(getenv("SLSB_GEMM_TRACE")) != 0;
+    if (trace_on) {   // tuning aid: timeline of pair 0, printed after a stream sync (never on in production)
+        long long* tr_dev = nullptr;                     // plain device memory: a managed buffer would page-fault inside the kernel
+        static long long tr_buf[64 * 8];
+        SLSB_CUDA_CHECK(cudaMalloc(&tr_dev, sizeof(tr_buf)));
+        SLSB_CUDA_CHECK(cudaMemsetAsync(tr_dev, 0, sizeof(tr_buf), stream));
+        q.trace = tr_dev;
+        SLSB_CUDA_CHECK(launch_pdl(tc_gemm_pair_kernel, dim3(2 * pairs), dim3(kNumThreads), Plan2::kBytes, stream, ta, tb, to, tr, q));
+        SLSB_CUDA_CHECK(cudaMemcpyAsync(tr_buf, tr_dev, sizeof(tr_buf), cudaMemcpyDeviceToHost, stream));
+        SLSB_CUDA_CHECK(cudaStreamSynchronize(stream));
+        long long t0 = 0;
+        for (int i = 0; i < 64 * 8; ++i) if (tr_buf[i] && (!t0 || tr_buf[i] < t0)) t0 = tr_buf[i];
+        fprintf(stderr, "gemm_trace M=%d N=%d K=%d pairs=%d tiles=%d split=%d red_add=%d tma_store=%d act=%d\n", dp.M, dp.N, dp.K, pairs, tiles, q.tail_split,
+                dp.red_add, dp.tma_store, dp.act);
+        for (int it = 0; it < 64; ++it) {
+            if (!tr_buf[it * 8 + 0]) break;
+            fprintf(stderr, "  it %2d: acc_free %7lld first_kb %7lld mma_done_issue %7lld | epi_enter %7lld acc_ready %7lld epi_done %7lld | load_first %7lld load_last %7lld\n", it,
+                    tr_buf[it * 8 + 0] - t0, tr_buf[it * 8 + 1] - t0, tr_buf[it * 8 + 2] - t0, tr_buf[it * 8 + 3] - t0, tr_buf[it * 8 + 4] - t0,
+                    tr_buf[it * 8 + 5] - t0, tr_buf[it * 8 + 6] - t0, tr_buf[it * 8 + 7] - t0);
+        }
+        cudaFree(tr_dev);
+        return 0;
+    }
     SLSB_CUDA_CHECK(launch_pdl(tc_gemm_pair_kernel, dim3(2 * pairs), dim3(kNumThreads), Plan2::kBytes, stream, ta, tb, to, tr, q));
     return 0;
 }
@@ -1065,6 +1088,14 @@ int tc_gemm(const TcGemmArgs& g, int num_sms, cudaStream_t stream) {
             uint64_t strides[1] = {(uint64_t)g.ldw * 2};
             uint32_t box[2] = {BLOCK_K, 128};
             if (encode_tmap_bf16(&tb, g.W, 2, dims, strides, box)) return -1;
+            static const bool red_v1 = getenv("SLSB_RED_ADD_V1") && atoi(getenv("SLSB_RED_ADD_V1")) != 0;
+            if (dp.red_add && !red_v1) {      // 16-column ping-pong reduce-add epilogue: 64-byte rows, SWIZZLE_64B
+                uint64_t odims[2] = {(uint64_t)g.N, (uint64_t)g.M};
+                uint32_t obox[2] = {16, BLOCK_M};
+                uint64_t so[1] = {(uint64_t)g.ldc * 4};
+                if (encode_tmap_f32_sw64(&to, g.out, 2, odims, so, obox)) return -1;
+                dp.red_add = 2;
+            }
             return launch_pair(ta, tb, to, tr, dp, num_sms, stream);
         }
         if (block_n == 256) return launch<256, A_PLAIN>(ta, tb, to, tr, dp, num_sms, stream);

@@ -8,7 +8,7 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib
-from ._lib import (ATTN_AUTO, HEAD_NONE, HEAD_SAE, HEAD_SLS, HEAD_WINDOW, PREC_BF16, PREC_FP32, Config, check, ptr,
+from ._lib import (ATTN_AUTO, HEAD_NONE, HEAD_RETAIN, HEAD_SAE, HEAD_SLS, HEAD_WINDOW, PREC_BF16, PREC_FP32, Config, check, ptr,
                    stream_ptr)
 from .weights import TrunkGeometry
 
@@ -69,10 +69,13 @@ class Engine:
     def frames(self, samples: int) -> int:
         return self.lib.slsb_frames_for_samples(self._h, samples)
 
-    def forward(self, wav: torch.Tensor, head: int, precision: int, lens: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward(self, wav: torch.Tensor, head: int, precision: int, lens: Optional[torch.Tensor] = None, retain: bool = False) -> torch.Tensor:
+        """``retain=True`` (``head | SLSB_HEAD_RETAIN``) keeps layer results / SAE activations / selection of this forward readable
+        through ``get_tensor`` / ``get_sparse`` / ``sae_loss``; the plain scoring forward does not pay for them."""
         B, S = wav.shape
         out = torch.empty(B, 2, device=wav.device, dtype=torch.float32)
-        check(self.lib.slsb_forward(self._h, ptr(wav), ptr(lens), B, S, head, precision, ptr(out), stream_ptr(wav.device)), "slsb_forward")
+        check(self.lib.slsb_forward(self._h, ptr(wav), ptr(lens), B, S, head | (HEAD_RETAIN if retain else 0), precision, ptr(out),
+                                    stream_ptr(wav.device)), "slsb_forward")
         return out
 
     def extract_feat(self, wav: torch.Tensor, precision: int, lens: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -185,4 +188,4 @@ class Engine:
         return int(self.lib.slsb_launch_count(self._h))
 
 
-__all__ = ["Engine", "make_config", "PRECISIONS", "HEAD_NONE", "HEAD_SAE", "HEAD_WINDOW", "HEAD_SLS", "PREC_FP32", "PREC_BF16"]
+__all__ = ["Engine", "make_config", "PRECISIONS", "HEAD_NONE", "HEAD_SAE", "HEAD_WINDOW", "HEAD_SLS", "HEAD_RETAIN", "PREC_FP32", "PREC_BF16"]

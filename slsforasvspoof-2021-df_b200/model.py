@@ -188,6 +188,9 @@ class Model(_EngineOwner, nn.Module):
                                         nn.Linear(256, 2))
         self.last_sparse_features = None
         self.last_feature_indices = None
+        # True: every forward keeps its layer results / SAE activations readable through the engine (get_tensor, last_sparse_code);
+        # forward sets it for the call when the caller asks for sae_loss / interpretability, which need them (model.py:224-240)
+        self.retain_intermediates = False
         self._input_dim = input_dim
         self._bind()
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._mark_dirty())
@@ -215,7 +218,8 @@ class Model(_EngineOwner, nn.Module):
         eng = self.engine()
         wav = _prep_wav(input_data)
         lens = None if sample_lengths is None else sample_lengths.to(device=wav.device, dtype=torch.int32).contiguous()
-        output = eng.forward(wav, self._head(), self._prec(), lens)
+        retain = self.retain_intermediates or (self.use_sae and (return_sae_loss or return_interpretability))
+        output = eng.forward(wav, self._head(), self._prec(), lens, retain=retain)
         sae_loss, interp = None, None
         if self.use_sae and return_sae_loss:
             sae_loss = eng.sae_loss(self._prec())                                       # model.py:224-225

@@ -158,9 +158,12 @@ def test_full_size_batch64_properties(sls, cuda):
         perm = torch.randperm(64, generator=torch.Generator().manual_seed(3)).to(cuda)
         shuffled = m(wav[perm].contiguous())
     fx = np.load(os.path.join(ROOT, "tests", "golden", "xlsr300m_sls_b2.npz"))
-    assert float(np.abs(full[:2].cpu().numpy() - fx["logprob"]).max()) <= 2e-2
-    assert torch.equal(full[:2], pair) and torch.equal(full[62:], tail)
-    assert torch.equal(shuffled, full[perm])
+    gerr = float(np.abs(full[:2].cpu().numpy() - fx["logprob"]).max())
+    assert gerr <= 2e-2, f"golden log-probs: {gerr}"
+    assert torch.equal(full[:2], pair), f"batch of 2 differs from the same clips in the batch of 64: {full[:2].tolist()} vs {pair.tolist()}"
+    assert torch.equal(full[62:], tail), f"tail pair differs: {full[62:].tolist()} vs {tail.tolist()}"
+    moved = (shuffled != full[perm]).any(-1).nonzero().flatten().tolist()
+    assert not moved, f"permuted batch: clips at positions {moved} changed, max |d| = {float((shuffled - full[perm]).abs().max()):.3e}"
     p = torch.exp(full)
     assert torch.isfinite(full).all() and float((p.sum(-1) - 1).abs().max()) < 1e-5
 

@@ -62,8 +62,13 @@ def test_logprob_parity_and_taps(sls, cuda, clips, case, precision):
     m = _product(sls, head, case["oracle"], precision)
     x = clips.to(cuda)
     with torch.no_grad():
+        if head != "sls":
+            fast = m(x, return_sae_loss=False).cpu()       # scoring forward: nothing retained, fused select + pool
+            m.retain_intermediates = True                  # the taps below read layer results / SAE codes of the forward
         out = m(x) if head == "sls" else m(x, return_sae_loss=False)
     out = out.cpu()
+    if head != "sls":
+        assert torch.equal(out, fast)                      # retaining intermediates does not change a single bit of the score
     eng = m.engine()
     B, T, D = 2, 201, 1024
     layer_rel = []

@@ -19,6 +19,7 @@ for prec in ("fp32", "bf16"):
         def cfgf(base=base):
             c = base(); c.attn_impl = attn; return c
         m._engine_config = cfgf
+    m.retain_intermediates = True
     ms[prec] = m.to("cuda").eval()
 ms["bf16"].load_state_dict(ms["fp32"].state_dict())
 eng0 = ms["fp32"].engine()
