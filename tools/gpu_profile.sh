@@ -4,7 +4,7 @@
 set -u
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --sustained-steps 0"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --sustained-steps 0 --prewarm-seconds 0 --legs none"
 $CMD > gpurun_out/bench_plain.log 2>&1 || { echo "plain bench failed"; tail -5 gpurun_out/bench_plain.log; exit 1; }
 tail -1 gpurun_out/bench_plain.log | cut -c1-160
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_bench.csv $CMD > gpurun_out/ncu_list.log 2>&1
