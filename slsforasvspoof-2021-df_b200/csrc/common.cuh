@@ -119,6 +119,15 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Release of a shared-memory ring stage that this warp has read with ORDINARY loads (LDS): the arrive must not be performed while
+// a load of the stage is still in flight - the mbarrier operation can overtake a pending LDS, the producer then sees the stage
+// empty and its next bulk copy overwrites the bytes the load was about to return (observed on B200 in ln_stream_kernel: about one
+// row segment per 10^4 launches carried the data of the stage's NEXT occupant).  `dep` must be a value computed from everything the
+// warp loaded (e.g. the result of a warp reduction over the loaded data): the instruction that produces it cannot issue before the
+// loads have returned, and it is issued before this arrive.
+__device__ __forceinline__ void mbar_arrive_after(uint64_t* bar, float dep) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)), "f"(dep) : "memory");
+}
 // arrive on an mbarrier given by a shared::cluster address (this CTA's own barrier or the cluster peer's)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");

@@ -325,6 +325,9 @@ static int pos_conv(slsb_engine* e, bool bf, const float* x, const void* Wp, con
 static int attention(slsb_engine* e, bool bf, const void* qkv, void* out, int B, int T, int H, const int* flens, cudaStream_t st) {
     ProfScope ps(e, st, PK_ATTN, 4.0 * (double)B * H * T * T * 64);
     int impl = e->cfg.attn_impl;
+    static int impl_env = -1;                     // SLSB_ATTN_IMPL=<1|2|3>: A/B override of an AUTO config (race hunts, profiling)
+    if (impl_env < 0) { const char* v = getenv("SLSB_ATTN_IMPL"); impl_env = v ? atoi(v) : 0; }
+    if (impl == SLSB_ATTN_AUTO && impl_env > 0) impl = impl_env;
     if (impl == SLSB_ATTN_AUTO) impl = (bf && T <= 512) ? SLSB_ATTN_TC : SLSB_ATTN_SIMT;      // 512 frames = 10.2 s: bf16 never leaves tcgen05 (config 4)
     if ((impl == SLSB_ATTN_TC && T > 512) || (impl == SLSB_ATTN_TC_V1 && T > 256)) impl = SLSB_ATTN_SIMT;
     if (impl == SLSB_ATTN_TC && bf) LAUNCH(attention_tc(qkv, out, B, T, H, flens, e->num_sms, st));

@@ -241,10 +241,13 @@ __global__ void __launch_bounds__(kLsThreads, 2) ln_stream_kernel(const float* _
 #pragma unroll
             for (int i = 0; i < NVH; ++i) load4<float>(x + 128 * i, v[i]);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[stage]);                 // the half row is in registers: the stage may be refilled
+        uint64_t* release = &empty_bar[stage];
         if (++stage == kLsStages) { stage = 0; phase ^= 1; }
-        if (row >= rows) continue;                                      // both warps of the row skip together
+        if (row >= rows) {                                              // both warps of the row skip together; nothing was read
+            __syncwarp();
+            if (lane == 0) mbar_arrive(release);
+            continue;
+        }
         float s = 0.f, dot = 0.f;
 #pragma unroll
         for (int i = 0; i < NVH; ++i) {
@@ -257,6 +260,9 @@ __global__ void __launch_bounds__(kLsThreads, 2) ln_stream_kernel(const float* _
         }
         s = warp_sum(s);                                                // fixed shuffle trees + fixed half order: bit-stable
         if constexpr (DOT) dot = warp_sum(dot);
+        // the stage is released only now: the reduction above consumed every value the warp loaded, so no LDS of the stage is in
+        // flight any more (an arrive issued right after the loads let the next bulk copy overwrite bytes that had not been read yet)
+        if (lane == 0) mbar_arrive_after(release, s);
         if (lane == 0) { xch[r * 2 + h].x = s; xch[r * 2 + h].y = dot; }
         asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
         const float mean = (xch[r * 2].x + xch[r * 2 + 1].x) * (1.0f / C);

@@ -157,6 +157,234 @@ __global__ void mean_pool_kept_kernel(const float* __restrict__ acts, const floa
     pooled[(long long)b * D + f] = s / (float)len;
 }
 
+// =================================================================================================
+// Fused selection + pooling (the scoring path of H-SAE and H-WIN): the fp32 activations are read ONCE per selection, the
+// selection runs on register-resident rows, and neither window sums, votes nor dense codes reach HBM.
+//
+//   canonical pooling order (every path uses it, so retained and non-retained forwards give identical bits): an utterance is
+//   cut into chunks of kSelRows frames; a chunk's kept activations are summed per feature in frame order (registers), the
+//   chunk partials [B][n_chunks][D] are then summed in chunk order and divided by the frame count (pool_finish_kernel).
+//   Chunk boundaries depend on T alone: a clip's pooled vector does not depend on the batch around it.
+//
+//   block = 256 threads, thread t owns the contiguous feature slice [t * EPT, (t + 1) * EPT) of every row it touches, so the
+//   per-window keep masks (one 32-bit word per thread and window) never leave the thread that produced them.
+// =================================================================================================
+constexpr int kSelRows = 8;
+
+struct SelSmem {
+    int hist[256];
+    int scratch[2][8];
+    uint32_t prefix;
+    int krem;
+    int cut;
+};
+
+// exact k-th largest key of the block's row (keys in registers) + tie cut, 4 radix passes of 8 bits; all 256 threads call it.
+// 4 barriers per pass: the histogram is cleared right after the barrier that published the previous digit, and the suffix-sum
+// scratch is double-buffered by pass.
+template <int EPT>
+__device__ __forceinline__ void block_select(const uint32_t (&key)[EPT], int k, SelSmem& sm, uint32_t& thr_key, int& cut) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t prefix = 0, mask = 0;
+    int krem = k;
+#pragma unroll 1
+    for (int shift = 24, pass = 0; shift >= 0; shift -= 8, ++pass) {
+        sm.hist[tid] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < EPT; ++i)
+            if ((key[i] & mask) == prefix) atomicAdd(&sm.hist[(key[i] >> shift) & 255], 1);
+        __syncthreads();
+        const int h = sm.hist[tid];
+        int sfx = h;                                          // inclusive suffix sum over the 256 digits
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_down_sync(0xffffffffu, sfx, o);
+            if (lane + o < 32) sfx += n;
+        }
+        if (lane == 0) sm.scratch[pass & 1][warp] = sfx;
+        __syncthreads();
+        for (int w = warp + 1; w < 8; ++w) sfx += sm.scratch[pass & 1][w];
+        if (sfx >= krem && sfx - h < krem) {                  // exactly one digit holds the k-th largest key
+            sm.prefix = prefix | (uint32_t(tid) << shift);
+            sm.krem = krem - (sfx - h);
+        }
+        __syncthreads();
+        prefix = sm.prefix; krem = sm.krem;
+        mask |= 255u << shift;
+    }
+    // krem (>= 1) of the entries equal to the threshold are kept, lowest indices first
+    int eq = 0;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) eq += (key[i] == prefix);
+    int inc = eq;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) sm.scratch[0][warp] = inc;
+    __syncthreads();
+    int before = inc - eq;
+    for (int w = 0; w < warp; ++w) before += sm.scratch[0][w];
+    if (before < krem && before + eq >= krem) {
+        int need = krem - before, c = 0;
+#pragma unroll
+        for (int i = 0; i < EPT; ++i)
+            if (key[i] == prefix && need > 0) { --need; c = tid * EPT + i + 1; }
+        sm.cut = c;
+    }
+    __syncthreads();
+    thr_key = prefix;
+    cut = sm.cut;
+}
+
+template <int EPT>
+__device__ __forceinline__ void load_row(const float* __restrict__ p, float (&v)[EPT]) {
+#pragma unroll
+    for (int i = 0; i < EPT; i += 4) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(p + threadIdx.x * EPT + i));
+        v[i] = q.x; v[i + 1] = q.y; v[i + 2] = q.z; v[i + 3] = q.w;
+    }
+}
+
+// H-SAE: grid (n_chunks, B).  Per row: select on the activations, thr / tie_cut written for the on-request consumers (dense /
+// compact codes), kept activations of frames < len added to the chunk partial.  partial == nullptr: selection only.
+template <int EPT>
+__global__ void __launch_bounds__(256) topk_pool_kernel(const float* __restrict__ acts, int T, int k, const int* __restrict__ lens,
+                                                        float* __restrict__ thr, int* __restrict__ tie_cut, float* __restrict__ partial) {
+    __shared__ SelSmem sm;
+    constexpr int D = EPT * 256;
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int len = lens ? min(lens[b], T) : T;
+    const int t0 = chunk * kSelRows, t1 = min(t0 + kSelRows, T);
+    float pool[EPT];
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) pool[i] = 0.f;
+    float nxt[EPT];
+    load_row<EPT>(acts + ((long long)b * T + t0) * D, nxt);
+#pragma unroll 1
+    for (int t = t0; t < t1; ++t) {
+        const long long row = (long long)b * T + t;
+        float v[EPT];
+        uint32_t key[EPT];
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) { v[i] = nxt[i]; key[i] = order_key(v[i]); }
+        if (t + 1 < t1) load_row<EPT>(acts + (row + 1) * D, nxt);       // next row in flight behind this row's selection
+        uint32_t tk; int cut;
+        block_select<EPT>(key, k, sm, tk, cut);
+        const float th = key_to_float(tk);
+        if (threadIdx.x == 0) { thr[row] = th; tie_cut[row] = cut; }
+        if (partial != nullptr && t < len) {
+#pragma unroll
+            for (int i = 0; i < EPT; ++i)
+                if (kept(v[i], threadIdx.x * EPT + i, th, cut)) pool[i] += v[i];
+        }
+    }
+    if (partial != nullptr) {
+        float* dst = partial + ((long long)b * gridDim.x + chunk) * D + threadIdx.x * EPT;
+#pragma unroll
+        for (int i = 0; i < EPT; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(pool[i], pool[i + 1], pool[i + 2], pool[i + 3]);
+    }
+}
+
+// pooled[b][f] = (sum over chunks, in chunk order, of partial[b][c][f]) / len_b
+__global__ void pool_finish_kernel(const float* __restrict__ partial, int n_chunks, int T, int D, const int* __restrict__ lens, float* __restrict__ pooled) {
+    const int b = blockIdx.y;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= D) return;
+    const int len = lens ? min(lens[b], T) : T;
+    float s = 0.f;
+    for (int c = 0; c < n_chunks; ++c) s += partial[((long long)b * n_chunks + c) * D + f];
+    pooled[(long long)b * D + f] = s / (float)len;
+}
+
+// H-WIN step 1 (model_window_topk.py:153-165): grid (nw, B).  Window sums in frame order (registers), per-window top-k, and the
+// keep decision of this thread's EPT features as one 32-bit word: wmask[(b * nw + w) * 256 + t].
+template <int EPT>
+__global__ void __launch_bounds__(256) window_select_kernel(const float* __restrict__ acts, int T, int k, int window, int stride, int nw,
+                                                            uint32_t* __restrict__ wmask) {
+    static_assert(EPT <= 32, "one mask word per thread");
+    __shared__ SelSmem sm;
+    constexpr int D = EPT * 256;
+    const int b = blockIdx.y, w = blockIdx.x;
+    float s[EPT];
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) s[i] = 0.f;
+    const float* base = acts + ((long long)b * T + (long long)w * stride) * D;
+#pragma unroll 2
+    for (int j = 0; j < window; ++j) {
+        float v[EPT];
+        load_row<EPT>(base + (long long)j * D, v);
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) s[i] += v[i];
+    }
+    uint32_t key[EPT];
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) key[i] = order_key(s[i]);
+    uint32_t tk; int cut;
+    block_select<EPT>(key, k, sm, tk, cut);
+    const float th = key_to_float(tk);
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) m |= kept(s[i], threadIdx.x * EPT + i, th, cut) ? (1u << i) : 0u;
+    wmask[((long long)b * nw + w) * 256 + threadIdx.x] = m;
+}
+
+// H-WIN step 2 (model_window_topk.py:167-197): grid (n_chunks, B).  Per frame: votes = activation x (number of covering windows
+// that selected the feature), accumulated in window order as the reference does; per-frame top-k on the votes; kept ACTIVATIONS
+// pooled.  votes_out (optional, on request only) materialises the votes for the dense / compact code consumers.
+template <int EPT>
+__global__ void __launch_bounds__(256) window_vote_pool_kernel(const float* __restrict__ acts, const uint32_t* __restrict__ wmask, int T, int k,
+                                                               int window, int stride, int nw, float* __restrict__ thr, int* __restrict__ tie_cut,
+                                                               float* __restrict__ votes_out, float* __restrict__ partial) {
+    __shared__ SelSmem sm;
+    constexpr int D = EPT * 256;
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int t0 = chunk * kSelRows, t1 = min(t0 + kSelRows, T);
+    float pool[EPT];
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) pool[i] = 0.f;
+    float nxt[EPT];
+    load_row<EPT>(acts + ((long long)b * T + t0) * D, nxt);
+#pragma unroll 1
+    for (int t = t0; t < t1; ++t) {
+        const long long row = (long long)b * T + t;
+        float a[EPT], v[EPT];
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) { a[i] = nxt[i]; v[i] = 0.f; }
+        if (t + 1 < t1) load_row<EPT>(acts + (row + 1) * D, nxt);
+        const int w_hi = min(t / stride, nw - 1);
+        const int w_lo = (t - window + 1 > 0) ? (t - window + stride) / stride : 0;
+        for (int w = w_lo; w <= w_hi; ++w) {                   // ascending window order (:175-185)
+            const uint32_t m = __ldg(wmask + ((long long)b * nw + w) * 256 + threadIdx.x);
+#pragma unroll
+            for (int i = 0; i < EPT; ++i)
+                if ((m >> i) & 1u) v[i] += a[i];
+        }
+        uint32_t key[EPT];
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) key[i] = order_key(v[i]);
+        uint32_t tk; int cut;
+        block_select<EPT>(key, k, sm, tk, cut);
+        const float th = key_to_float(tk);
+        if (threadIdx.x == 0) { thr[row] = th; tie_cut[row] = cut; }
+        if (votes_out != nullptr) {
+            float* dst = votes_out + row * D + threadIdx.x * EPT;
+#pragma unroll
+            for (int i = 0; i < EPT; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+#pragma unroll
+        for (int i = 0; i < EPT; ++i)
+            if (kept(v[i], threadIdx.x * EPT + i, th, cut)) pool[i] += a[i];
+    }
+    if (partial != nullptr) {
+        float* dst = partial + ((long long)b * gridDim.x + chunk) * D + threadIdx.x * EPT;
+#pragma unroll
+        for (int i = 0; i < EPT; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(pool[i], pool[i + 1], pool[i + 2], pool[i + 3]);
+    }
+}
+
 __global__ void mean_pool_kernel(const float* __restrict__ x, float* __restrict__ pooled, int T, int D, const int* __restrict__ lens) {
     const int b = blockIdx.y;
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
@@ -427,8 +655,10 @@ __global__ void __launch_bounds__(160) sls_fuse_pool_tma_kernel(LayerPtrs L, int
                     s[di][2 * e + 1] = fmaf(__high2float(h[e]), w, s[di][2 * e + 1]);
                 }
             }
+            // release the chunk only after its three loads have returned (see mbar_arrive_after): the value depends on all of them
+            const float dep = (s[0][0] + s[1][0]) + s[2][0];
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            if (lane == 0) mbar_arrive_after(&empty_bar[stage], dep);
             if (++stage == kPtStages) { stage = 0; phase ^= 1; }
         }
         const float g = bn[0] / sqrtf(bn[3] + bn_eps), beta = bn[1], rm = bn[2];
@@ -534,6 +764,43 @@ int topk_mean_pool(const float* acts, const float* thr, const int* tie_cut, floa
 int votes_mean_pool(const float* acts, const float* votes, const float* thr, const int* tie_cut, float* pooled, int B, int T, int D, const int* lens, cudaStream_t stream) {
     dim3 grid((D + 127) / 128, B);
     mean_pool_kept_kernel<<<grid, 128, 0, stream>>>(acts, votes, thr, tie_cut, pooled, T, D, lens);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+int sel_chunks(int T) { return (T + kSelRows - 1) / kSelRows; }
+
+#define SLSB_EPT_DISPATCH(D_, CALL)                                                                    \
+    switch (D_) {                                                                                      \
+        case 1024: { constexpr int EPT = 4; CALL; break; }                                             \
+        case 2048: { constexpr int EPT = 8; CALL; break; }                                             \
+        case 4096: { constexpr int EPT = 16; CALL; break; }                                            \
+        case 8192: { constexpr int EPT = 32; CALL; break; }                                            \
+        default: set_error("top-k: dict size %d unsupported (1024/2048/4096/8192)", D_); return -1;    \
+    }
+
+int topk_select_pool(const float* acts, int B, int T, int D, int k, const int* lens, float* thr, int* tie_cut, float* partial, float* pooled,
+                     cudaStream_t stream) {
+    if (B <= 0 || T <= 0) return 0;
+    if (k < 1 || k > D) { set_error("topk: need 1 <= k <= D (k=%d, D=%d)", k, D); return -1; }
+    if ((partial == nullptr) != (pooled == nullptr)) { set_error("topk_select_pool: partial and pooled go together"); return -1; }
+    const int nc = sel_chunks(T);
+    dim3 grid(nc, B);
+    SLSB_EPT_DISPATCH(D, (topk_pool_kernel<EPT><<<grid, 256, 0, stream>>>(acts, T, k, lens, thr, tie_cut, partial)));
+    if (pooled) pool_finish_kernel<<<dim3((D + 255) / 256, B), 256, 0, stream>>>(partial, nc, T, D, lens, pooled);
+    SLSB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int window_select_pool(const float* acts, int B, int T, int D, int k, int window, int stride, int nw, uint32_t* wmask, float* thr, int* tie_cut,
+                       float* votes_or_null, float* partial, float* pooled, cudaStream_t stream) {
+    if (B <= 0 || T <= 0) return 0;
+    if (k < 1 || k > D) { set_error("topk: need 1 <= k <= D (k=%d, D=%d)", k, D); return -1; }
+    if ((partial == nullptr) != (pooled == nullptr)) { set_error("window_select_pool: partial and pooled go together"); return -1; }
+    const int nc = sel_chunks(T);
+    SLSB_EPT_DISPATCH(D, (window_select_kernel<EPT><<<dim3(nw, B), 256, 0, stream>>>(acts, T, k, window, stride, nw, wmask)));
+    SLSB_EPT_DISPATCH(D, (window_vote_pool_kernel<EPT><<<dim3(nc, B), 256, 0, stream>>>(acts, wmask, T, k, window, stride, nw, thr, tie_cut,
+                                                                                         votes_or_null, partial)));
+    if (pooled) pool_finish_kernel<<<dim3((D + 255) / 256, B), 256, 0, stream>>>(partial, nc, T, D, nullptr, pooled);
     SLSB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

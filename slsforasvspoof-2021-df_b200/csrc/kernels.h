@@ -112,7 +112,16 @@ int topk_threshold(const float* acts, long long rows, int D, int k, float* thr, 
 int topk_densify(const float* acts, const float* thr, const int* tie_cut, float* encoded, long long rows, int D, cudaStream_t stream);
 // pooled[b][f] = (1/len_b) * sum_{t < len_b} kept(acts[b,t,f])   (model.py:245), fixed summation order
 int topk_mean_pool(const float* acts, const float* thr, const int* tie_cut, float* pooled, int B, int T, int D, const int* lens, cudaStream_t stream);
-// window top-k (model_window_topk.py:118-203): window sums -> per-window top-k -> votes -> per-frame top-k
+// Fused scoring paths (activations read once per selection; canonical pooling order = chunks of 8 frames, see heads.cu):
+//   rows = B * T rows of `acts`; thr / tie_cut as topk_threshold; partial: [B, sel_chunks(T), D] scratch; pooled: [B, D] mean of the
+//   kept activations over the frames < len_b.  partial == pooled == nullptr: selection only.
+int sel_chunks(int T);
+int topk_select_pool(const float* acts, int B, int T, int D, int k, const int* lens, float* thr, int* tie_cut, float* partial, float* pooled,
+                     cudaStream_t stream);
+//   window variant: wmask [B, nw, 256] words of scratch; votes_or_null [B*T, D] is written only when the caller wants the votes
+int window_select_pool(const float* acts, int B, int T, int D, int k, int window, int stride, int nw, uint32_t* wmask, float* thr, int* tie_cut,
+                       float* votes_or_null, float* partial, float* pooled, cudaStream_t stream);
+// window top-k (model_window_topk.py:118-203): window sums -> per-window top-k -> votes -> per-frame top-k (unfused reference kernels)
 int window_sums(const float* acts, float* sums, int B, int T, int D, int window, int stride, int nw, cudaStream_t stream);
 int window_votes(const float* acts, const float* sums, const float* thr_w, const int* cut_w, float* votes,
                  int B, int T, int D, int window, int stride, int nw, cudaStream_t stream);
