@@ -406,6 +406,25 @@ def leg_ingest(ctx, sls_b200, model, args, n_clips):
         dt = time.perf_counter() - t0
         rec["flac_decode_only"] = {"value": n_flac * reps / dt, "unit": "clips/s", "decode_workers": workers}
         assert bool(ctx.torch.equal(a[:n_flac], b[:n_flac]))                    # FLAC path == PCM-shard path, bit for bit
+        # the same files with the decode ON THE DEVICE (one GPU thread per FLAC frame; the host only scans frame boundaries + CRCs)
+        stats = {}
+        sls_b200.score_flac_files_device(model, paths[:args.batch], batch=args.batch, workers=workers)
+        t0 = time.perf_counter()
+        c = sls_b200.score_flac_files_device(model, paths * reps, batch=args.batch, workers=workers, stats=stats)
+        dt = time.perf_counter() - t0
+        rec["flac_files_device_decode"] = {"value": n_flac * reps / dt, "unit": "utt/s", "clips": n_flac * reps, "seconds": dt, "scan_workers": workers,
+                                           "h2d_bytes_per_clip": stats["flac_bytes"] / max(1, n_flac * reps), "device_batches": stats["device_batches"],
+                                           "host_fallback_batches": stats["host_batches"],
+                                           "note": "slsb_flac_scan on the host (frame table, CRC-8 / CRC-16), compressed frames uploaded, Rice + LPC restore on the GPU "
+                                                   "(csrc/flac_gpu.cu), then device ingest + forward"}
+        assert bool(ctx.torch.equal(c[:n_flac], a[:n_flac]))
+        blobs = [open(pth, "rb").read() for pth in paths]
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            for blob in blobs:
+                sls_b200.scan_flac_bytes(blob, 64600)
+        dt = time.perf_counter() - t0
+        rec["flac_scan_only"] = {"value": n_flac * reps / dt, "unit": "clips/s", "threads": 1, "note": "host work left per clip when the device decodes"}
     return rec
 
 

@@ -148,6 +148,38 @@ int64_t slsb_flac_decode(const uint8_t* data, int64_t nbytes, int64_t max_sample
 int64_t slsb_flac_decode_mono16(const uint8_t* data, int64_t nbytes, int64_t max_samples, int verify_md5, int16_t* pcm_out,
                                 int64_t pcm_capacity, int32_t* sample_rate);
 
+/* ---- device FLAC decode (csrc/flac_gpu.cu, csrc/flac_frame.h): replaces the per-item librosa decode of data_utils_SSL.py:109-113 for
+ * the corpus format (16-bit mono FLAC).  The host scans a stream once (frame boundaries, header CRC-8, frame CRC-16, no sample is
+ * decoded); the device decodes one frame per thread.
+ *  slsb_flac_scan: frame table of the frames covering the first max_samples samples (0 = all).  info int32 [8] = {sample rate, channels,
+ *    bits per sample, total samples (low 31 bits), max block size, total >> 31, samples covered by the table (capped at max_samples), 0}.
+ *    frame_off / frame_len: byte offset of each frame's sync code in `data` and its length incl. the CRC-16; frame_samples: block sizes.
+ *    Returns the number of frames (<= cap) or a negative FLAC error code (same codes as slsb_flac_decode).
+ *  slsb_flac_frame: one decode job.  byte_off: frame start in the byte buffer (which must stay readable 8 bytes past its last frame);
+ *    keep: samples of the frame to store (the clip head may end inside its last frame); out_off: first output sample in pcm; bps: STREAMINFO's.
+ *  slsb_flac_decode_frames: device buffers; status[i] = block size of frame i (> 0) or a negative error (-9: not 16-bit mono - decode this
+ *    clip with slsb_flac_decode_mono16 instead).  slsb_flac_decode_frames_host: the same frame core on host buffers (test twin). */
+typedef struct slsb_flac_frame {
+    int64_t byte_off;
+    int64_t out_off;
+    int32_t byte_len;
+    int32_t keep;
+    int32_t bps;
+    int32_t reserved;
+} slsb_flac_frame;
+int64_t slsb_flac_scan(const uint8_t* data, int64_t nbytes, int64_t max_samples, int32_t* info, int64_t* frame_off, int32_t* frame_len,
+                       int32_t* frame_samples, int64_t cap);
+int slsb_flac_decode_frames(const uint8_t* bytes_dev, const slsb_flac_frame* frames_dev, int n_frames, int16_t* pcm_dev, int32_t* status_dev,
+                            void* stream);
+/* FLAC bytes -> scores: the compressed frames of B clips (frame table from slsb_flac_scan, out_off / offsets / lens in samples of one
+ * int16 buffer of total_samples) are uploaded, decoded on the device, converted + padded like slsb_score_pcm16_host and scored.
+ * status_host int32 [n_frames] receives the per-frame decoder status.  Returns 0, -1 (error) or -2 (a frame was refused by the device
+ * decoder: the scores are void, decode this batch on the host instead). */
+int slsb_score_flac_host(slsb_engine* e, const uint8_t* bytes_host, int64_t nbytes, const slsb_flac_frame* frames_host, int n_frames,
+                         int64_t total_samples, const int64_t* offsets_host, const int32_t* lens_host, int B, int S, int head, int precision,
+                         float* scores_host, int32_t* status_host, void* stream);
+int slsb_flac_decode_frames_host(const uint8_t* bytes, const slsb_flac_frame* frames, int n_frames, int16_t* pcm, int32_t* status);
+
 /* synthetic clips keyed by utterance index, bit-identical to oracle.trunk.synth_clips */
 int slsb_synth_clips(float* wav_dev, int64_t first_utt, int count, int samples, void* stream);
 
@@ -202,6 +234,15 @@ int slsb_op_attention(int impl, int io_bf16, const void* qkv, void* out, int B, 
  *  7 O seen, 8 epilogue done, 9 stage free seen by producer, 10 loads landed) -- tuning hook, no reference counterpart */
 int slsb_op_attention_trace(const void* qkv, void* out, int B, int T, int H, int64_t* trace_dev, void* stream);
 int slsb_op_topk(const float* x, int64_t rows, int D, int k, float* thr, int32_t* tie_cut, float* encoded_or_null, void* stream);
+/* Fused scoring paths of H-SAE / H-WIN (heads.cu): exact per-frame top-k of acts [B*T, D] (D in 1024/2048/4096/8192) and the mean of the
+ * kept activations over the frames < lens[b] (lens may be NULL), summed in the canonical order: chunks of 8 frames in frame order, then
+ * the chunk partials in chunk order.  partial: [B, slsb_op_pool_chunks(T), D] scratch.  Mirrors model.py:68-79 + :245 (H-SAE) and
+ * model_window_topk.py:118-203 + :365 (H-WIN; wmask: [B, nw, 256] words of scratch, votes_or_null [B*T, D] optional). */
+int slsb_op_topk_pool(const float* acts, int B, int T, int D, int k, const int32_t* lens, float* thr, int32_t* tie_cut, float* partial, float* pooled,
+                      void* stream);
+int slsb_op_window_pool(const float* acts, int B, int T, int D, int k, int window, uint32_t* wmask, float* thr, int32_t* tie_cut, float* votes_or_null,
+                        float* partial, float* pooled, void* stream);
+int slsb_op_pool_chunks(int T);
 
 #ifdef __cplusplus
 }

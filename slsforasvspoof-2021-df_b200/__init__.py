@@ -20,7 +20,8 @@ from .scoring import (produce_evaluation_file, score_synthetic_shard, gather_sco
 from .data_utils import genSpoof_list, pad, Dataset_ASVspoof2021_eval, Dataset_in_the_wild_eval
 from .ingest import (read_wav_pcm16, write_wav_pcm16, decode_wav_files, write_pcm_shard, wav_files_to_shard, PcmShard,
                      score_pcm_shard, AudioFormatError, decode_flac_bytes, read_flac_pcm16, read_audio_pcm16, read_audio_float32, decode_audio_files,
-                     audio_files_to_shard, score_audio_files)
+                     audio_files_to_shard, score_audio_files, score_flac_files_device, scan_flac_bytes, pack_flac_batch,
+                     decode_flac_frames_host, FRAME_DTYPE)
 
 __all__ = ["Model", "ModelWindowTopK", "ModelSLS", "SSLModel", "AutoEncoderTopK", "getAttenF", "Engine", "make_config",
            "TrunkGeometry", "TrunkParams", "pack_state_dict", "load_checkpoint_tensors", "load_model_checkpoint", "fix_module_prefix", "produce_evaluation_file", "score_synthetic_shard",
@@ -29,5 +30,5 @@ __all__ = ["Model", "ModelWindowTopK", "ModelSLS", "SSLModel", "AutoEncoderTopK"
            "load_library", "LIB_PATH", "EXPORTED_SYMBOLS", "PRECISIONS", "HEAD_NONE", "HEAD_SAE", "HEAD_WINDOW",
            "HEAD_SLS", "HEAD_RETAIN", "PREC_FP32", "PREC_BF16", "read_wav_pcm16", "write_wav_pcm16", "decode_wav_files", "write_pcm_shard",
            "wav_files_to_shard", "PcmShard", "score_pcm_shard", "AudioFormatError", "decode_flac_bytes", "read_flac_pcm16",
-           "read_audio_pcm16", "read_audio_float32", "decode_audio_files", "audio_files_to_shard", "score_audio_files", "genSpoof_list", "pad", "Dataset_ASVspoof2021_eval",
+           "read_audio_pcm16", "read_audio_float32", "decode_audio_files", "audio_files_to_shard", "score_audio_files", "score_flac_files_device", "scan_flac_bytes", "pack_flac_batch", "decode_flac_frames_host", "FRAME_DTYPE", "genSpoof_list", "pad", "Dataset_ASVspoof2021_eval",
            "Dataset_in_the_wild_eval"]

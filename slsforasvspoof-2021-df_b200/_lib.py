@@ -72,11 +72,18 @@ _SIGNATURES = {
     "slsb_op_layernorm": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _P]),
     "slsb_flac_decode": (C.c_int64, [_P, C.c_int64, C.c_int64, C.c_int, _P, C.c_int64, _P]),
     "slsb_flac_decode_mono16": (C.c_int64, [_P, C.c_int64, C.c_int64, C.c_int, _P, C.c_int64, _P]),
+    "slsb_score_flac_host": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int, C.c_int64, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "slsb_flac_scan": (C.c_int64, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, C.c_int64]),
+    "slsb_flac_decode_frames": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
+    "slsb_flac_decode_frames_host": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "slsb_debug_pair_schedule": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, C.c_int, _P]),
     "slsb_op_layernorm_taps": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, _P]),
     "slsb_op_attention": (C.c_int, [C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "slsb_op_attention_trace": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "slsb_op_topk": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "slsb_op_topk_pool": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
+    "slsb_op_window_pool": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "slsb_op_pool_chunks": (C.c_int, [C.c_int]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

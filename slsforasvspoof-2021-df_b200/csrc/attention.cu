@@ -318,7 +318,21 @@ template <bool kWide> struct AttnGeo {
     static constexpr int BAR_OFFSET = OUT_OFFSET + 2 * 16384;
     static constexpr int SMEM = BAR_OFFSET + 256;
 };
-constexpr int P_THREADS = 352;                // 8 softmax warps + TMA producer + 2 MMA issuers
+constexpr int P_THREADS = 384;                // 3 warpgroups: 2 x 4 softmax warps, then {TMA producer, 2 MMA issuers, 1 spare warp}
+// Register re-allocation between the warpgroups (setmaxnreg): the kernel is compiled for 168 registers (65536 / 384); the service
+// warpgroup gives registers back (56 are plenty for its descriptor arithmetic) and the two softmax warpgroups grow to 224, which
+// keeps both TMEM load buffers, the exponentials and the 64 output values of a row in registers.  With a flat 168 the prefetched
+// TMEM chunk was spilled to local memory right after every tcgen05.ld (8 STL.64 + 16 LDL per 16 scores: a third of the loop).
+constexpr int P_REGS_SERVICE = 56, P_REGS_SOFTMAX = 224;
+static_assert(128 * (168 - P_REGS_SERVICE) >= 2 * 128 * (P_REGS_SOFTMAX - 168), "register budget of the three warpgroups");
+template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+// three-input maximum (FMNMX3): half the instructions of the row-max pass
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
 constexpr int P_OCOL = 192;                   // O accumulator columns inside a TMEM half
 constexpr int P_KB_MAX = 192;                 // widest key block when an item needs several (S must stay clear of the live O columns)
 
@@ -326,7 +340,9 @@ constexpr int P_KB_MAX = 192;                 // widest key block when an item n
 __device__ __forceinline__ void max32(const uint32_t (&a)[32], int col0, int lim, float (&mx)[4]) {
     if (col0 + 32 <= lim) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mx[j & 3] = fmaxf(mx[j & 3], __uint_as_float(a[j]));
+        for (int j = 0; j < 32; j += 8)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mx[q] = max3(mx[q], __uint_as_float(a[j + q]), __uint_as_float(a[j + 4 + q]));
     } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) if (col0 + j < lim) mx[j & 3] = fmaxf(mx[j & 3], __uint_as_float(a[j]));
@@ -385,6 +401,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     const uint32_t tmem = *tmem_ptr;
     griddep_wait();                     // the prologue overlapped the QKV GEMM's tail; qkv is visible from here
 
+    if (warp >= 8) {
+        reg_dealloc<P_REGS_SERVICE>();
     if (warp == 8) {
         // ===================== TMA producer =====================
         if (lane == 0) {
@@ -405,7 +423,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                 }
             }
         }
-    } else if (warp >= 9) {
+    } else if (warp == 9 || warp == 10) {
         // ===================== MMA issuers: warp 9 serves TMEM half 0, warp 10 half 1 (one thread each) =====================
         // Two independent issuers: issuing the 13 TS-MMAs of one half (~1k cycles of issue back-pressure) never delays the other
         // half's S, and neither warpgroup waits behind the other one's barrier.  `stagger` (SLSB_ATTN_STAGGER, default 0) can
@@ -460,7 +478,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                 ATT_TRACE(u, 3);
             }
         }
+    }
     } else {
+        reg_alloc<P_REGS_SOFTMAX>();
         // ===================== softmax + epilogue warpgroups: thread == query row == TMEM lane =====================
         const int w = warp >> 2, q = warp & 3;
         const int r = q * 32 + lane;
@@ -493,18 +513,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                     if (do_max) {
                         // ---- row max, 32-column TMEM loads double-buffered in registers (a piece may run past the block into stale
                         // columns of the half: masked by lim)
-                        uint32_t a0[32], a1[32];
-                        tmem_ld_32x32b_x32(trow, a0);
-                        tmem_ld_wait();
+                        // three pieces in flight per wait (96 registers: the softmax warpgroups own 224 each): one piece per wait
+                        // made this pass a chain of TMEM load latencies (~210 cycles per piece, 1.5k cycles per unit)
+                        uint32_t a[3][32];
 #pragma unroll 1
-                        for (int c = 0; c < npiece; c += 2) {
-                            if (c + 1 < npiece) tmem_ld_32x32b_x32(trow + (c + 1) * 32, a1);
-                            max32(a0, c * 32, lim, mx4);
+                        for (int c = 0; c < npiece; c += 3) {
+#pragma unroll
+                            for (int g = 0; g < 3; ++g)
+                                if (c + g < npiece) tmem_ld_32x32b_x32(trow + (c + g) * 32, a[g]);
                             tmem_ld_wait();
-                            if (c + 1 >= npiece) break;
-                            if (c + 2 < npiece) tmem_ld_32x32b_x32(trow + (c + 2) * 32, a0);
-                            max32(a1, (c + 1) * 32, lim, mx4);
-                            tmem_ld_wait();
+#pragma unroll
+                            for (int g = 0; g < 3; ++g)
+                                if (c + g < npiece) max32(a[g], (c + g) * 32, lim, mx4);
                         }
                         if (issuer && p == 0) ATT_TRACE(u, 5);
                     }

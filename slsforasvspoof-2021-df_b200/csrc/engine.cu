@@ -131,7 +131,7 @@ struct slsb_engine {
     bool finalized = false;
     int64_t launches = 0;
     // workspace
-    Buf fe[2], lnbuf, qkv, attn, ffn, xmid, xfinal, xc, xpad, acts, encoded, sums, votes, thr, cut, thr_w, cut_w, pooled, logprob,
+    Buf fe[2], lnbuf, qkv, attn, ffn, xmid, xfinal, xc, xpad, acts, encoded, sums, votes, thr, cut, thr_w, cut_w, pool_part, wmask, flac_bytes, flac_frames, flac_status, pooled, logprob,
         sls_w, sls_in, sls_part, sls_dots, zeros, scratch, flens, wav_stage[2], lens_stage[2], score_stage[4], recon, tmp_bf16, im2col, conv0_w64, ybuf, pcm_stage, off_stage;
     // pipelined host scoring (slsb_score_submit / slsb_score_wait): uploads run on a private copy stream into two staging
     // slots so the H2D copy of batch i+1 overlaps the forward of batch i; up to 4 submissions may be in flight
@@ -351,7 +351,7 @@ static int ln_gemm_dispatch(const TcLnGemmArgs& g, int num_sms, cudaStream_t st)
 static int layernorm_timed(slsb_engine* e, const LnArgs& a, cudaStream_t st) {
     const double n = (double)a.rows * a.C;
     const double bytes = n * ((a.in_bf16 ? 2 : 4) + (a.add ? 2 : 0) + (a.sum_out ? 4 : 0) + (a.out ? (a.out_bf16 ? 2 : 4) : 0) +
-                              (a.out2 ? (a.out2_bf16 ? 2 : 4) : 0));
+                              (a.out2 ? (a.out2_bf16 ? 2 : 4) : 0) + (a.copy_out ? 2 : 0));      // copy_out: the bf16 layer-result snapshot
     ProfScope ps(e, st, PK_LN, bytes);
     LAUNCH(layernorm(a, st));
     return 0;
@@ -573,29 +573,41 @@ static int sae_acts(slsb_engine* e, bool bf, const void* xc, long long rows, cud
     return linear(e, bf, xc, c.embed_dim, "sae.enc.w", c.sae_dict, c.embed_dim, rows, W32("sae.enc.b"), nullptr, 0, e->acts.p, c.sae_dict, 0, ACT_RELU, st, PK_SAE_GEMM);
 }
 
-// selection pass: fills thr/cut (and votes for the window variant); `sel` is what the keep-rule looks at
-static int sae_select(slsb_engine* e, long long rows, int T, int window, const float** sel_out, cudaStream_t st) {
+// selection (+ pooling) pass: fills thr / cut; `pooled` (optional) receives the mean of the kept activations over the valid frames
+// (model.py:245); the window variant materialises its votes only when `want_votes` (dense / compact code consumers).  `sel_out` is
+// what the keep-rule looks at (activations, or the votes; nullptr when the votes were not kept).
+static int sae_select(slsb_engine* e, long long rows, int T, int window, bool want_votes, float* pooled, const int* flens, const float** sel_out,
+                      cudaStream_t st) {
     const slsb_config& c = e->cfg;
     const int Dd = c.sae_dict, k = c.sae_k;
+    if (rows % T != 0) { set_error("top-k: rows=%lld is not a multiple of T=%d", rows, T); return -1; }
+    const int B = (int)(rows / T);
     if (e->thr.reserve((size_t)rows * 4) || e->cut.reserve((size_t)rows * 4)) return -1;
+    float* partial = nullptr;
+    if (pooled) {
+        if (e->pool_part.reserve((size_t)B * sel_chunks(T) * Dd * 4)) return -1;
+        partial = e->pool_part.as<float>();
+    }
     const float* acts = e->acts.as<float>();
     if (window <= 1) {
-        LAUNCH(topk_threshold(acts, rows, Dd, k, e->thr.as<float>(), e->cut.as<int>(), st));
+        LAUNCH(topk_select_pool(acts, B, T, Dd, k, flens, e->thr.as<float>(), e->cut.as<int>(), partial, pooled, st));
+        if (pooled) ++e->launches;
         *sel_out = acts;
         return 0;
     }
     const int stride = window / 2 > 0 ? window / 2 : 1;
-    if (rows % T != 0) { set_error("window top-k: rows=%lld is not a multiple of T=%d", rows, T); return -1; }
     if (T < window || stride >= T) { set_error("window top-k: T=%d shorter than window %d", T, window); return -1; }
-    const int B = (int)(rows / T);
     const int nw = (T - window) / stride + 1;                                  // model_window_topk.py:141
-    if (e->sums.reserve((size_t)B * nw * Dd * 4) || e->votes.reserve((size_t)rows * Dd * 4) ||
-        e->thr_w.reserve((size_t)B * nw * 4) || e->cut_w.reserve((size_t)B * nw * 4)) return -1;
-    LAUNCH(window_sums(acts, e->sums.as<float>(), B, T, Dd, window, stride, nw, st));
-    LAUNCH(topk_threshold(e->sums.as<float>(), (long long)B * nw, Dd, k, e->thr_w.as<float>(), e->cut_w.as<int>(), st));
-    LAUNCH(window_votes(acts, e->sums.as<float>(), e->thr_w.as<float>(), e->cut_w.as<int>(), e->votes.as<float>(), B, T, Dd, window, stride, nw, st));
-    LAUNCH(topk_threshold(e->votes.as<float>(), rows, Dd, k, e->thr.as<float>(), e->cut.as<int>(), st));
-    *sel_out = e->votes.as<float>();
+    if (e->wmask.reserve((size_t)B * nw * 256 * 4)) return -1;
+    float* votes = nullptr;
+    if (want_votes) {
+        if (e->votes.reserve((size_t)rows * Dd * 4)) return -1;
+        votes = e->votes.as<float>();
+    }
+    LAUNCH(window_select_pool(acts, B, T, Dd, k, window, stride, nw, e->wmask.as<uint32_t>(), e->thr.as<float>(), e->cut.as<int>(), votes,
+                              partial, pooled, st));
+    e->launches += pooled ? 2 : 1;
+    *sel_out = votes;
     return 0;
 }
 
@@ -603,7 +615,6 @@ static int run_head(slsb_engine* e, int head_flags, int prec, float* logprob, cu
     const slsb_config& c = e->cfg;
     const int head = head_flags & 0xFF;
     const bool retain = (head_flags & SLSB_HEAD_RETAIN) != 0;
-    (void)retain;
     const bool bf = prec == SLSB_PREC_BF16;
     const int B = e->B, T = e->T, D = c.embed_dim;
     const long long M = (long long)B * T;
@@ -618,10 +629,9 @@ static int run_head(slsb_engine* e, int head_flags, int prec, float* logprob, cu
             const float* sel = nullptr;
             {   // algorithmic bytes of selection + pooling: the fp32 activations read once
                 ProfScope ps(e, st, PK_SAE_SELECT, (double)M * c.sae_dict * 4);
-                if (sae_select(e, M, T, window, &sel, st)) return -1;
-                e->have_acts = true; e->have_sel = true;
-                if (c.cls_in == c.sae_dict)
-                    LAUNCH(votes_mean_pool(e->acts.as<float>(), sel, e->thr.as<float>(), e->cut.as<int>(), e->pooled.as<float>(), B, T, c.sae_dict, flens, st));
+                const bool dense_next = c.cls_in != c.sae_dict;               // use_sparse_features=False densifies below
+                if (sae_select(e, M, T, window, retain || dense_next, dense_next ? nullptr : e->pooled.as<float>(), flens, &sel, st)) return -1;
+                e->have_acts = true; e->have_sel = sel != nullptr;
             }
             if (c.cls_in == c.sae_dict) {
             } else {
@@ -733,7 +743,7 @@ int slsb_destroy(slsb_engine* e) {
     cudaDeviceSynchronize();
     for (auto& kv : e->w) { if (kv.second.f32) cudaFree(kv.second.f32); if (kv.second.b16) cudaFree(kv.second.b16); }
     Buf* bufs[] = {&e->fe[0], &e->fe[1], &e->lnbuf, &e->qkv, &e->attn, &e->ffn, &e->xmid, &e->xfinal, &e->xc, &e->xpad, &e->acts, &e->encoded,
-                   &e->sums, &e->votes, &e->thr, &e->cut, &e->thr_w, &e->cut_w, &e->pooled, &e->logprob, &e->sls_w, &e->sls_in, &e->sls_part, &e->sls_dots,
+                   &e->sums, &e->votes, &e->thr, &e->cut, &e->thr_w, &e->cut_w, &e->pool_part, &e->wmask, &e->flac_bytes, &e->flac_frames, &e->flac_status, &e->pooled, &e->logprob, &e->sls_w, &e->sls_in, &e->sls_part, &e->sls_dots,
                    &e->zeros, &e->scratch, &e->flens, &e->wav_stage[0], &e->wav_stage[1], &e->lens_stage[0], &e->lens_stage[1], &e->score_stage[0],
                    &e->score_stage[1], &e->score_stage[2], &e->score_stage[3], &e->recon, &e->tmp_bf16, &e->im2col, &e->conv0_w64, &e->ybuf,
                    &e->pcm_stage, &e->off_stage};
@@ -838,7 +848,7 @@ int slsb_get_tensor(slsb_engine* e, const char* name, float* dst, int64_t numel,
     else if (n == "pooled") { src = e->pooled.p; want = (int64_t)e->B * c.cls_in; }
     else if (n == "sls_weights") { src = e->sls_w.p; want = (int64_t)e->B * c.n_layers; }
     else if (n == "encoded") {
-        if (!e->have_sel) { set_error("no SAE selection: last forward ran no SAE head"); return -1; }
+        if (!e->have_sel) { set_error(e->have_acts ? "the window head keeps its votes only on request: run the forward with head | SLSB_HEAD_RETAIN" : "no SAE selection: last forward ran no SAE head"); return -1; }
         want = M * c.sae_dict;
         if (numel != want) { set_error("slsb_get_tensor: '%s' has %lld elements, caller gave %lld", name, (long long)want, (long long)numel); return -1; }
         const float* sel = (e->head == SLSB_HEAD_WINDOW && c.sae_window > 1) ? e->votes.as<float>() : e->acts.as<float>();
@@ -858,7 +868,7 @@ int slsb_get_tensor(slsb_engine* e, const char* name, float* dst, int64_t numel,
 int slsb_get_sparse(slsb_engine* e, int32_t* idx_dev, float* val_dev, int32_t* count_dev, void* stream) {
     if (!e || !idx_dev || !val_dev) { set_error("slsb_get_sparse: null argument"); return -1; }
     DeviceGuard guard(e->device);
-    if (!e->have_sel) { set_error("slsb_get_sparse: last forward ran no SAE head"); return -1; }
+    if (!e->have_sel) { set_error(e->have_acts ? "slsb_get_sparse: the window head keeps its votes only on request (head | SLSB_HEAD_RETAIN)" : "slsb_get_sparse: last forward ran no SAE head"); return -1; }
     const slsb_config& c = e->cfg;
     const long long M = (long long)e->B * e->T;
     const float* sel = (e->head == SLSB_HEAD_WINDOW && c.sae_window > 1) ? e->votes.as<float>() : e->acts.as<float>();
@@ -882,7 +892,7 @@ int slsb_sae_encode(slsb_engine* e, const float* x_dev, int64_t rows, int T, int
     SLSB_CUDA_CHECK(cudaGetLastError());
     if (sae_acts(e, bf, e->xc.p, rows, st)) return -1;
     const float* sel = nullptr;
-    if (sae_select(e, rows, T > 0 ? T : 1, window, &sel, st)) return -1;
+    if (sae_select(e, rows, T > 0 ? T : 1, window, true, nullptr, nullptr, &sel, st)) return -1;
     LAUNCH(votes_densify(e->acts.as<float>(), sel, e->thr.as<float>(), e->cut.as<int>(), encoded_dev, rows, c.sae_dict, st));
     return 0;
 }
@@ -908,7 +918,7 @@ int slsb_sae_loss(slsb_engine* e, int precision, float* loss_dev, void* stream) 
     if (check_ready(e)) return -1;
     DeviceGuard guard(e->device);
     const slsb_config& c = e->cfg;
-    if (!e->have_sel) { set_error("slsb_sae_loss: last forward ran no SAE head"); return -1; }
+    if (!e->have_sel) { set_error(e->have_acts ? "slsb_sae_loss: the window head keeps its votes only on request (head | SLSB_HEAD_RETAIN)" : "slsb_sae_loss: last forward ran no SAE head"); return -1; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long M = (long long)e->B * e->T;
     if (e->encoded.reserve((size_t)M * c.sae_dict * 4) || e->recon.reserve((size_t)M * c.embed_dim * 4) || e->scratch.reserve((size_t)(e->B * c.cls_hidden + 1024) * 4)) return -1;
@@ -1008,6 +1018,55 @@ int slsb_score_pcm16_host(slsb_engine* e, const int16_t* pcm_host, int64_t total
     LAUNCH(scores_from_logprob(e->logprob.as<float>(), e->score_stage[0].as<float>(), B, st));
     SLSB_CUDA_CHECK(cudaMemcpyAsync(scores_host, e->score_stage[0].p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
     SLSB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int slsb_score_flac_host(slsb_engine* e, const uint8_t* bytes_host, int64_t nbytes, const slsb_flac_frame* frames_host, int n_frames,
+                         int64_t total_samples, const int64_t* offsets_host, const int32_t* lens_host, int B, int S, int head, int precision,
+                         float* scores_host, int32_t* status_host, void* stream) {
+    if (check_ready(e)) return -1;
+    DeviceGuard guard(e->device);
+    if (!bytes_host || !frames_host || !offsets_host || !lens_host || !scores_host || !status_host) { set_error("slsb_score_flac_host: null buffer"); return -1; }
+    if ((head & 0xFF) == SLSB_HEAD_NONE) { set_error("slsb_score_flac_host: a classifier head is required"); return -1; }
+    if (n_frames < 1 || nbytes < 1) { set_error("slsb_score_flac_host: empty batch"); return -1; }
+    for (int b = 0; b < B; ++b) {
+        if (lens_host[b] < 1 || offsets_host[b] < 0 || offsets_host[b] + lens_host[b] > total_samples) {
+            set_error("slsb_score_flac_host: clip %d (offset %lld, %d samples) is empty or outside the %lld-sample buffer", b,
+                      (long long)offsets_host[b], lens_host[b], (long long)total_samples);
+            return -1;
+        }
+    }
+    for (int i = 0; i < n_frames; ++i) {
+        const slsb_flac_frame& f = frames_host[i];
+        if (f.byte_off < 0 || f.byte_len < 1 || f.byte_off + f.byte_len > nbytes || f.keep < 0 || f.out_off < 0 || f.out_off + f.keep > total_samples) {
+            set_error("slsb_score_flac_host: frame %d lies outside its buffers", i);
+            return -1;
+        }
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (e->flac_bytes.reserve((size_t)nbytes + 8) || e->flac_frames.reserve((size_t)n_frames * sizeof(slsb_flac_frame)) ||
+        e->flac_status.reserve((size_t)n_frames * 4) || e->pcm_stage.reserve((size_t)total_samples * 2) || e->off_stage.reserve((size_t)B * 8) ||
+        e->lens_stage[0].reserve((size_t)B * 4) || e->wav_stage[0].reserve((size_t)B * S * 4) || e->logprob.reserve((size_t)B * 2 * 4) ||
+        e->score_stage[0].reserve((size_t)B * 4)) return -1;
+    SLSB_CUDA_CHECK(cudaMemcpyAsync(e->flac_bytes.p, bytes_host, (size_t)nbytes, cudaMemcpyHostToDevice, st));
+    SLSB_CUDA_CHECK(cudaMemsetAsync(static_cast<uint8_t*>(e->flac_bytes.p) + nbytes, 0, 8, st));          // the word reader may touch the next 4-byte boundary
+    SLSB_CUDA_CHECK(cudaMemcpyAsync(e->flac_frames.p, frames_host, (size_t)n_frames * sizeof(slsb_flac_frame), cudaMemcpyHostToDevice, st));
+    SLSB_CUDA_CHECK(cudaMemcpyAsync(e->off_stage.p, offsets_host, (size_t)B * 8, cudaMemcpyHostToDevice, st));
+    SLSB_CUDA_CHECK(cudaMemcpyAsync(e->lens_stage[0].p, lens_host, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    LAUNCH(flac_decode_frames(e->flac_bytes.as<uint8_t>(), e->flac_frames.as<slsb_flac_frame>(), n_frames, e->pcm_stage.as<int16_t>(),
+                              e->flac_status.as<int32_t>(), st));
+    SLSB_CUDA_CHECK(cudaMemcpyAsync(status_host, e->flac_status.p, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, st));
+    LAUNCH(ingest_pcm16(e->pcm_stage.as<int16_t>(), e->off_stage.as<long long>(), e->lens_stage[0].as<int>(), B, S, e->wav_stage[0].as<float>(), st));
+    if (slsb_forward(e, e->wav_stage[0].as<float>(), nullptr, B, S, head, precision, e->logprob.as<float>(), stream)) return -1;
+    LAUNCH(scores_from_logprob(e->logprob.as<float>(), e->score_stage[0].as<float>(), B, st));
+    SLSB_CUDA_CHECK(cudaMemcpyAsync(scores_host, e->score_stage[0].p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    SLSB_CUDA_CHECK(cudaStreamSynchronize(st));
+    for (int i = 0; i < n_frames; ++i) {
+        if (status_host[i] < 0) {       // the scores of this call are void: the caller decodes the batch on the host (slsb_score_pcm16_host)
+            set_error("slsb_score_flac_host: frame %d was refused by the device decoder (code %d)", i, status_host[i]);
+            return -2;
+        }
+    }
     return 0;
 }
 
@@ -1161,5 +1220,20 @@ int slsb_op_topk(const float* x, int64_t rows, int D, int k, float* thr, int32_t
     if (encoded_or_null) return topk_densify(x, thr, tie_cut, encoded_or_null, rows, D, st);
     return 0;
 }
+
+int slsb_op_topk_pool(const float* acts, int B, int T, int D, int k, const int32_t* lens, float* thr, int32_t* tie_cut, float* partial, float* pooled,
+                      void* stream) {
+    return topk_select_pool(acts, B, T, D, k, lens, thr, tie_cut, partial, pooled, static_cast<cudaStream_t>(stream));
+}
+
+int slsb_op_window_pool(const float* acts, int B, int T, int D, int k, int window, uint32_t* wmask, float* thr, int32_t* tie_cut, float* votes_or_null,
+                        float* partial, float* pooled, void* stream) {
+    const int stride = window / 2 > 0 ? window / 2 : 1;
+    if (window < 2 || T < window || stride >= T) { set_error("slsb_op_window_pool: need 2 <= window <= T"); return -1; }
+    const int nw = (T - window) / stride + 1;
+    return window_select_pool(acts, B, T, D, k, window, stride, nw, wmask, thr, tie_cut, votes_or_null, partial, pooled, static_cast<cudaStream_t>(stream));
+}
+
+int slsb_op_pool_chunks(int T) { return sel_chunks(T); }
 
 }  // extern "C"

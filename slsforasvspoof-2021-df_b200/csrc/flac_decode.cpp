@@ -90,8 +90,7 @@ void init_tables() {
     (void)once;
 }
 uint8_t crc8(const uint8_t* p, int64_t n) { uint8_t c = 0; for (int64_t i = 0; i < n; ++i) c = crc8_table[c ^ p[i]]; return c; }
-uint16_t crc16(const uint8_t* p, int64_t n) {
-    uint16_t c = 0;
+uint16_t crc16_update(uint16_t c, const uint8_t* p, int64_t n) {
     int64_t i = 0;
     for (; i + 8 <= n; i += 8)
         c = (uint16_t)(crc16_slice[7][p[i] ^ (c >> 8)] ^ crc16_slice[6][p[i + 1] ^ (c & 0xFF)] ^ crc16_slice[5][p[i + 2]] ^ crc16_slice[4][p[i + 3]] ^
@@ -99,6 +98,7 @@ uint16_t crc16(const uint8_t* p, int64_t n) {
     for (; i < n; ++i) c = (uint16_t)((c << 8) ^ crc16_table[(c >> 8) ^ p[i]]);
     return c;
 }
+uint16_t crc16(const uint8_t* p, int64_t n) { return crc16_update(0, p, n); }
 
 // ---- MD5 (RFC 1321) of the interleaved little-endian PCM, as STREAMINFO stores it ----
 struct Md5 {
@@ -322,8 +322,8 @@ int decode(const uint8_t* data, int64_t n, int64_t max_samples, bool verify_md5,
     const bool whole = d.si.total == 0 || want >= d.si.total;
     const size_t stride = (size_t)(d.si.max_block > 16 ? d.si.max_block : 16);
     std::vector<int64_t> chan((size_t)ch * stride);
-    if (want != INT64_MAX && !d.mono16) d.pcm.reserve((size_t)(want < (1 << 24) ? want : (1 << 24)) * ch);   // STREAMINFO is untrusted input
     if (info_only) return FLAC_OK;
+    if (want != INT64_MAX && !d.mono16) d.pcm.reserve((size_t)(want < (1 << 24) ? want : (1 << 24)) * ch);   // STREAMINFO is untrusted input
     Md5 md5;
     std::vector<uint8_t> md5_buf;
     bool cut_short = false;      // a stream of unknown length (total == 0) stopped by max_samples: the MD5 covers only a head
@@ -438,9 +438,105 @@ int decode(const uint8_t* data, int64_t n, int64_t max_samples, bool verify_md5,
     return FLAC_OK;
 }
 
+// ---- frame table for the device decoder (flac_gpu.cu) --------------------------------------------------------------
+// Parses a frame header at data[pos..]; returns its length in bytes (incl. the CRC-8) or 0 if this is not a valid header.
+// number: the coded frame number (fixed block size) or first sample number (variable block size).
+int64_t parse_frame_header(const uint8_t* data, int64_t n, int64_t pos, int* blocksize, int* variable, uint64_t* number, int* ch_code, int* ss_code) {
+    if (pos + 5 > n || data[pos] != 0xFF || (data[pos + 1] & 0xFE) != 0xF8) return 0;
+    BitReader br(data + pos, n - pos);
+    br.bits(15);
+    *variable = (int)br.bits(1);
+    const int bs_code = (int)br.bits(4), sr_code = (int)br.bits(4);
+    *ch_code = (int)br.bits(4); *ss_code = (int)br.bits(3);
+    if (br.bits(1)) return 0;
+    if (bs_code == 0 || sr_code == 15 || *ch_code > 10 || *ss_code == 3) return 0;
+    const uint32_t b0 = br.bits(8);
+    int extra = 0;
+    if (b0 == 0xFF) return 0;
+    uint64_t v = b0;
+    if (b0 & 0x80) {
+        uint32_t m = 0x40;
+        while (b0 & m) { ++extra; m >>= 1; }
+        if (extra == 0) return 0;
+        v = b0 & (m - 1);
+    }
+    for (int i = 0; i < extra; ++i) { const uint32_t c = br.bits(8); if ((c & 0xC0) != 0x80) return 0; v = (v << 6) | (c & 0x3F); }
+    *number = v;
+    if (bs_code == 1) *blocksize = 192;
+    else if (bs_code <= 5) *blocksize = 576 << (bs_code - 2);
+    else if (bs_code == 6) *blocksize = (int)br.bits(8) + 1;
+    else if (bs_code == 7) *blocksize = (int)br.bits(16) + 1;
+    else *blocksize = 256 << (bs_code - 8);
+    if (sr_code == 12) br.bits(8); else if (sr_code == 13 || sr_code == 14) br.bits(16);
+    if (br.fail) return 0;
+    const int64_t hdr = br.bitpos() >> 3;
+    if (pos + hdr + 1 > n || crc8(data + pos, hdr) != data[pos + hdr]) return 0;
+    return hdr + 1;
+}
+
 }  // namespace
 
 extern "C" {
+
+int64_t slsb_flac_scan(const uint8_t* data, int64_t nbytes, int64_t max_samples, int32_t* info, int64_t* frame_off, int32_t* frame_len,
+                       int32_t* frame_samples, int64_t cap) {
+    if (!data || nbytes <= 0 || !info || !frame_off || !frame_len || !frame_samples || cap <= 0) return FLAC_E_ARG;
+    init_tables();
+    Decoded d;
+    const int rc = decode(data, nbytes, 0, false, d, true);              // STREAMINFO (+ leading ID3v2 tag / metadata checks)
+    info[0] = d.si.rate; info[1] = d.si.channels; info[2] = d.si.bps; info[3] = (int32_t)(d.si.total & 0x7fffffff);
+    info[4] = d.si.max_block; info[5] = (int32_t)(d.si.total >> 31);
+    if (rc != FLAC_OK) return rc;
+    // first audio frame: behind the metadata blocks
+    int64_t pos = 0;
+    if (nbytes >= 10 && memcmp(data, "ID3", 3) == 0) {
+        const int64_t sz = ((int64_t)(data[6] & 0x7f) << 21) | ((int64_t)(data[7] & 0x7f) << 14) | ((int64_t)(data[8] & 0x7f) << 7) | (data[9] & 0x7f);
+        pos = 10 + sz + ((data[5] & 0x10) ? 10 : 0);
+    }
+    pos += 4;
+    for (bool last = false; !last;) {
+        last = (data[pos] & 0x80) != 0;
+        pos += 4 + (((int64_t)data[pos + 1] << 16) | ((int64_t)data[pos + 2] << 8) | data[pos + 3]);
+    }
+    int64_t nf = 0, samples = 0;
+    int bs = 0, var = 0, chc = 0, ssc = 0; uint64_t num = 0;
+    int64_t hdr = parse_frame_header(data, nbytes, pos, &bs, &var, &num, &chc, &ssc);
+    if (!hdr) return FLAC_E_HEADER;
+    const int64_t want = max_samples > 0 ? max_samples : INT64_MAX;
+    while (samples < want) {
+        if (nf >= cap) return FLAC_E_ARG;
+        if ((size_t)bs > (size_t)(d.si.max_block > 16 ? d.si.max_block : 16)) return FLAC_E_UNSUPPORTED;
+        // the frame ends where the next frame's header starts (sync code, valid CRC-8, consecutive number) AND the two bytes in
+        // front of it are the CRC-16 of everything since this frame's sync code; a sync-like pattern inside the frame fails both
+        const uint64_t next_num = var ? num + (uint64_t)bs : num + 1;
+        int64_t end = -1;
+        int nbs = 0, nvar = 0, nch = 0, nss = 0; uint64_t nnum = 0; int64_t nhdr = 0;
+        uint16_t crc = 0; int64_t crc_upto = pos;                          // running CRC-16 over data[pos .. crc_upto)
+        for (int64_t q = pos + hdr + 2; q + 1 < nbytes; ++q) {
+            const uint8_t* f = static_cast<const uint8_t*>(memchr(data + q, 0xFF, (size_t)(nbytes - 1 - q)));
+            if (!f) break;
+            q = f - data;
+            if ((data[q + 1] & 0xFE) != 0xF8) continue;
+            nhdr = parse_frame_header(data, nbytes, q, &nbs, &nvar, &nnum, &nch, &nss);
+            if (!nhdr || nvar != var || nnum != next_num) continue;
+            if (crc_upto < q - 2) { crc = crc16_update(crc, data + crc_upto, q - 2 - crc_upto); crc_upto = q - 2; }
+            if (crc_upto == q - 2 && crc == (uint16_t)((data[q - 2] << 8) | data[q - 1])) { end = q; break; }
+        }
+        bool is_last = false;
+        if (end < 0) {                                                      // last frame of the stream: it ends with the data
+            if (crc16(data + pos, nbytes - pos - 2) != (uint16_t)((data[nbytes - 2] << 8) | data[nbytes - 1])) return FLAC_E_CRC16;
+            end = nbytes; is_last = true;
+        }
+        frame_off[nf] = pos; frame_len[nf] = (int32_t)(end - pos); frame_samples[nf] = bs;
+        if (chc != 0) info[1] = info[1] > 1 ? info[1] : 2;                 // a multi-channel frame: the device decoder is mono only
+        ++nf; samples += bs;
+        if (is_last) break;
+        pos = end; hdr = nhdr; bs = nbs; num = nnum; chc = nch; ssc = nss;
+    }
+    info[6] = (int32_t)(samples < want ? samples : want);
+    (void)ssc;
+    return nf;
+}
 
 int64_t slsb_flac_decode(const uint8_t* data, int64_t nbytes, int64_t max_samples, int verify_md5, int32_t* pcm_out, int64_t pcm_capacity,
                          int32_t* info) {

@@ -52,57 +52,6 @@ __device__ __forceinline__ int block_prefix_excl_256(int v, int* scratch) {
     return s + add - v;
 }
 
-// One block (256 threads) per row; thread t owns the contiguous slice [t * EPT, (t + 1) * EPT).
-template <int EPT>
-__global__ void __launch_bounds__(256) topk_threshold_kernel(const float* __restrict__ x, int D, int k, float* __restrict__ thr, int* __restrict__ tie_cut) {
-    __shared__ int hist[256];
-    __shared__ int scratch[8];
-    __shared__ uint32_t s_prefix;
-    __shared__ int s_krem;
-    const long long row = blockIdx.x;
-    const float* xr = x + row * D;
-    uint32_t key[EPT];
-#pragma unroll
-    for (int i = 0; i < EPT; i += 4) {
-        const float4 v = *reinterpret_cast<const float4*>(xr + threadIdx.x * EPT + i);
-        key[i] = order_key(v.x); key[i + 1] = order_key(v.y); key[i + 2] = order_key(v.z); key[i + 3] = order_key(v.w);
-    }
-    uint32_t prefix = 0, mask = 0;
-    int krem = k;
-#pragma unroll 1
-    for (int shift = 24; shift >= 0; shift -= 8) {
-        hist[threadIdx.x] = 0;
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < EPT; ++i)
-            if ((key[i] & mask) == prefix) atomicAdd(&hist[(key[i] >> shift) & 255], 1);
-        __syncthreads();
-        const int h = hist[threadIdx.x];
-        const int suf = block_suffix_sum_256(h, scratch);      // elements with digit >= t
-        if (suf >= krem && suf - h < krem) {                    // exactly one thread
-            s_prefix = prefix | (uint32_t(threadIdx.x) << shift);
-            s_krem = krem - (suf - h);
-        }
-        __syncthreads();
-        prefix = s_prefix; krem = s_krem;
-        mask |= 255u << shift;
-        __syncthreads();
-    }
-    // prefix == key of the k-th largest value; krem (>= 1) of the entries equal to it are kept, lowest indices first
-    int eq = 0;
-#pragma unroll
-    for (int i = 0; i < EPT; ++i) eq += (key[i] == prefix);
-    const int before = block_prefix_excl_256(eq, scratch);
-    if (before < krem && before + eq >= krem) {
-        int need = krem - before, cut = 0;
-#pragma unroll
-        for (int i = 0; i < EPT; ++i)
-            if (key[i] == prefix && need > 0) { --need; cut = threadIdx.x * EPT + i + 1; }
-        thr[row] = key_to_float(prefix);
-        tie_cut[row] = cut;
-    }
-}
-
 __device__ __forceinline__ bool kept(float sel, int idx, float thr, int cut) { return sel > thr || (sel == thr && idx < cut); }
 
 __global__ void densify_kernel(const float* __restrict__ acts, const float* __restrict__ sel, const float* __restrict__ thr,
@@ -187,13 +136,24 @@ __device__ __forceinline__ void block_select(const uint32_t (&key)[EPT], int k, 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t prefix = 0, mask = 0;
     int krem = k;
+    constexpr uint32_t kZeroKey = 0x80000000u;                // order_key(+0.0f)
+    int zc = 0;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) zc += (key[i] == kZeroKey);
+    const int zc_warp = __reduce_add_sync(0xffffffffu, zc);
 #pragma unroll 1
     for (int shift = 24, pass = 0; shift >= 0; shift -= 8, ++pass) {
         sm.hist[tid] = 0;
         __syncthreads();
+        // Post-ReLU rows are about half exact zeros: as plain shared-memory atomics they all hit ONE bin and serialise 32 ways
+        // per warp instruction (the first pass alone cost ~4 us per row).  The zeros are counted once per row (warp reduction,
+        // above the loop) and enter the histogram with one atomic per warp; the other elements spread over the exponent bins.
+        // (A __match_any_sync aggregation of every digit was measured slower than the plain atomics: 0.39 vs 0.26 ms per batch.)
+        const bool zeros_in = (kZeroKey & mask) == prefix;
 #pragma unroll
         for (int i = 0; i < EPT; ++i)
-            if ((key[i] & mask) == prefix) atomicAdd(&sm.hist[(key[i] >> shift) & 255], 1);
+            if (key[i] != kZeroKey && (key[i] & mask) == prefix) atomicAdd(&sm.hist[(key[i] >> shift) & 255], 1);
+        if (zeros_in && lane == 0 && zc_warp) atomicAdd(&sm.hist[(kZeroKey >> shift) & 255], zc_warp);
         __syncthreads();
         const int h = sm.hist[tid];
         int sfx = h;                                          // inclusive suffix sum over the 256 digits
@@ -248,10 +208,25 @@ __device__ __forceinline__ void load_row(const float* __restrict__ p, float (&v)
     }
 }
 
+// stand-alone selection (slsb_op_topk, other callers): one block (256 threads) per row
+template <int EPT>
+__global__ void __launch_bounds__(256) topk_threshold_kernel(const float* __restrict__ x, int D, int k, float* __restrict__ thr, int* __restrict__ tie_cut) {
+    __shared__ SelSmem sm;
+    const long long row = blockIdx.x;
+    float v[EPT];
+    load_row<EPT>(x + row * D, v);
+    uint32_t key[EPT];
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) key[i] = order_key(v[i]);
+    uint32_t tk; int cut;
+    block_select<EPT>(key, k, sm, tk, cut);
+    if (threadIdx.x == 0) { thr[row] = key_to_float(tk); tie_cut[row] = cut; }
+}
+
 // H-SAE: grid (n_chunks, B).  Per row: select on the activations, thr / tie_cut written for the on-request consumers (dense /
 // compact codes), kept activations of frames < len added to the chunk partial.  partial == nullptr: selection only.
 template <int EPT>
-__global__ void __launch_bounds__(256) topk_pool_kernel(const float* __restrict__ acts, int T, int k, const int* __restrict__ lens,
+__global__ void __launch_bounds__(256, EPT <= 16 ? 3 : 1) topk_pool_kernel(const float* __restrict__ acts, int T, int k, const int* __restrict__ lens,
                                                         float* __restrict__ thr, int* __restrict__ tie_cut, float* __restrict__ partial) {
     __shared__ SelSmem sm;
     constexpr int D = EPT * 256;
@@ -266,10 +241,9 @@ __global__ void __launch_bounds__(256) topk_pool_kernel(const float* __restrict_
 #pragma unroll 1
     for (int t = t0; t < t1; ++t) {
         const long long row = (long long)b * T + t;
-        float v[EPT];
-        uint32_t key[EPT];
+        uint32_t key[EPT];                                              // the row lives in registers as its order keys (a bijection)
 #pragma unroll
-        for (int i = 0; i < EPT; ++i) { v[i] = nxt[i]; key[i] = order_key(v[i]); }
+        for (int i = 0; i < EPT; ++i) key[i] = order_key(nxt[i]);
         if (t + 1 < t1) load_row<EPT>(acts + (row + 1) * D, nxt);       // next row in flight behind this row's selection
         uint32_t tk; int cut;
         block_select<EPT>(key, k, sm, tk, cut);
@@ -277,8 +251,10 @@ __global__ void __launch_bounds__(256) topk_pool_kernel(const float* __restrict_
         if (threadIdx.x == 0) { thr[row] = th; tie_cut[row] = cut; }
         if (partial != nullptr && t < len) {
 #pragma unroll
-            for (int i = 0; i < EPT; ++i)
-                if (kept(v[i], threadIdx.x * EPT + i, th, cut)) pool[i] += v[i];
+            for (int i = 0; i < EPT; ++i) {
+                const float v = key_to_float(key[i]);
+                if (kept(v, threadIdx.x * EPT + i, th, cut)) pool[i] += v;
+            }
         }
     }
     if (partial != nullptr) {
@@ -335,7 +311,7 @@ __global__ void __launch_bounds__(256) window_select_kernel(const float* __restr
 // that selected the feature), accumulated in window order as the reference does; per-frame top-k on the votes; kept ACTIVATIONS
 // pooled.  votes_out (optional, on request only) materialises the votes for the dense / compact code consumers.
 template <int EPT>
-__global__ void __launch_bounds__(256) window_vote_pool_kernel(const float* __restrict__ acts, const uint32_t* __restrict__ wmask, int T, int k,
+__global__ void __launch_bounds__(256, EPT <= 16 ? 3 : 1) window_vote_pool_kernel(const float* __restrict__ acts, const uint32_t* __restrict__ wmask, int T, int k,
                                                                int window, int stride, int nw, float* __restrict__ thr, int* __restrict__ tie_cut,
                                                                float* __restrict__ votes_out, float* __restrict__ partial) {
     __shared__ SelSmem sm;
@@ -365,18 +341,18 @@ __global__ void __launch_bounds__(256) window_vote_pool_kernel(const float* __re
         uint32_t key[EPT];
 #pragma unroll
         for (int i = 0; i < EPT; ++i) key[i] = order_key(v[i]);
-        uint32_t tk; int cut;
-        block_select<EPT>(key, k, sm, tk, cut);
-        const float th = key_to_float(tk);
-        if (threadIdx.x == 0) { thr[row] = th; tie_cut[row] = cut; }
         if (votes_out != nullptr) {
             float* dst = votes_out + row * D + threadIdx.x * EPT;
 #pragma unroll
             for (int i = 0; i < EPT; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
+        uint32_t tk; int cut;
+        block_select<EPT>(key, k, sm, tk, cut);                        // the votes live on as their order keys (a bijection)
+        const float th = key_to_float(tk);
+        if (threadIdx.x == 0) { thr[row] = th; tie_cut[row] = cut; }
 #pragma unroll
         for (int i = 0; i < EPT; ++i)
-            if (kept(v[i], threadIdx.x * EPT + i, th, cut)) pool[i] += a[i];
+            if (kept(key_to_float(key[i]), threadIdx.x * EPT + i, th, cut)) pool[i] += a[i];
     }
     if (partial != nullptr) {
         float* dst = partial + ((long long)b * gridDim.x + chunk) * D + threadIdx.x * EPT;

@@ -150,4 +150,10 @@ int scores_from_logprob(const float* logprob, float* scores, int B, cudaStream_t
 // mse between recon and x (model.py:224-225), deterministic two-stage reduction
 int mse_loss(const float* a, const float* b, long long n, float* out_scalar, float* scratch, cudaStream_t stream);
 
+// ---------------------------------------------------------------- device FLAC decode (flac_gpu.cu)
+}  // namespace slsb
+#include "../../include/slsb200.h"
+namespace slsb {
+int flac_decode_frames(const uint8_t* bytes_dev, const slsb_flac_frame* frames_dev, int n_frames, int16_t* pcm_dev, int32_t* status_dev, cudaStream_t stream);
+
 }  // namespace slsb

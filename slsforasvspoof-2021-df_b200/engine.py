@@ -170,6 +170,24 @@ class Engine:
                                              precision, ptr(scores), stream_ptr(self.device)), "slsb_score_pcm16_host")
         return scores
 
+    def score_flac_arrays(self, data: torch.Tensor, frames: torch.Tensor, total_samples: int, offsets: torch.Tensor, lens: torch.Tensor,
+                          head: int, precision: int, samples: int = 64600):
+        """``slsb_score_flac_host``: data uint8 [nbytes] (the clips' FLAC frames), frames uint8 [n_frames * 32] (packed
+        ``slsb_flac_frame`` records), offsets int64 [B] / lens int32 [B] in samples of the decoded int16 buffer.  Returns
+        ``(scores or None, status int32 [n_frames])`` - None when the device decoder refused a frame (host fallback)."""
+        B = lens.numel()
+        n_frames = frames.numel() // 32
+        data = data if data.is_pinned() else data.pin_memory()
+        scores = torch.empty(B, dtype=torch.float32, pin_memory=True)
+        status = torch.empty(n_frames, dtype=torch.int32, pin_memory=True)
+        rc = self.lib.slsb_score_flac_host(self._h, ptr(data), data.numel(), ptr(frames.contiguous()), n_frames, int(total_samples),
+                                           ptr(offsets.contiguous()), ptr(lens.contiguous()), B, samples, head, precision, ptr(scores), ptr(status),
+                                           stream_ptr(self.device))
+        if rc == -2:
+            return None, status
+        check(rc, "slsb_score_flac_host")
+        return scores, status
+
     def synth_clips(self, first_utt: int, count: int, samples: int = 64600) -> torch.Tensor:
         wav = torch.empty(count, samples, device=self.device, dtype=torch.float32)
         check(self.lib.slsb_synth_clips(ptr(wav), first_utt, count, samples, stream_ptr(self.device)), "slsb_synth_clips")

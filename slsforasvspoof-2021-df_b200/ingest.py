@@ -145,6 +145,87 @@ def read_audio_float32(path: str, max_samples: Optional[int] = None) -> np.ndarr
     return np.mean(frames.astype(np.float32) / np.float32(32768.0), axis=1, dtype=np.float32)
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# Device FLAC decode: the host scans a stream once (frame boundaries + CRC-8 + CRC-16, csrc/flac_decode.cpp::slsb_flac_scan),
+# the GPU decodes one frame per thread (csrc/flac_gpu.cu).  FRAME_DTYPE is the C struct slsb_flac_frame (include/slsb200.h).
+# ------------------------------------------------------------------------------------------------------------------
+FRAME_DTYPE = np.dtype([("byte_off", "<i8"), ("out_off", "<i8"), ("byte_len", "<i4"), ("keep", "<i4"), ("bps", "<i4"), ("reserved", "<i4")])
+assert FRAME_DTYPE.itemsize == 32
+
+
+class FlacScan:
+    """Frame table of one FLAC stream: ``device_ok`` says whether the device decoder takes it (16-bit mono at ``sample_rate``)."""
+    __slots__ = ("data", "rate", "channels", "bps", "total", "samples", "off", "len", "blocks", "device_ok")
+
+
+def scan_flac_bytes(data, max_samples: Optional[int] = 64600, sample_rate: Optional[int] = SAMPLE_RATE) -> FlacScan:
+    """One pass over the bytes of a .flac file: STREAMINFO + the frames that cover its first ``max_samples`` samples, header CRC-8
+    and frame CRC-16 verified, nothing decoded.  Raises ``AudioFormatError`` on a damaged stream."""
+    import ctypes as C
+    from ._lib import load
+    lib = load()
+    buf = data if isinstance(data, np.ndarray) else np.frombuffer(data, dtype=np.uint8)
+    cap = 64 if max_samples else 4096
+    while True:
+        info = (C.c_int32 * 8)()
+        off = np.empty(cap, dtype=np.int64); ln = np.empty(cap, dtype=np.int32); blocks = np.empty(cap, dtype=np.int32)
+        n = int(lib.slsb_flac_scan(buf.ctypes.data, buf.size, int(max_samples or 0), info, off.ctypes.data, ln.ctypes.data, blocks.ctypes.data, cap))
+        if n == -11 and cap < (1 << 22):
+            cap *= 8                                              # more frames than slots (small block sizes): retry with a larger table
+            continue
+        break
+    if n < 0:
+        raise AudioFormatError(f"FLAC: {FLAC_ERRORS.get(n, n)}")
+    r = FlacScan()
+    r.data, r.rate, r.channels, r.bps = buf, int(info[0]), int(info[1]), int(info[2])
+    r.total = int(info[3]) | (int(info[5]) << 31)
+    r.samples = int(info[6])
+    r.off, r.len, r.blocks = off[:n], ln[:n], blocks[:n]
+    if sample_rate is not None and r.rate != sample_rate:
+        raise AudioFormatError(f"FLAC: need {sample_rate} Hz, got {r.rate} Hz")
+    r.device_ok = r.channels == 1 and r.bps == 16 and r.samples > 0
+    return r
+
+
+def pack_flac_batch(scans: Sequence[FlacScan], max_samples: int = 64600):
+    """Frame jobs of a batch of scanned streams: (bytes uint8 [nbytes] - only the frames that are needed, back to back -, frames
+    FRAME_DTYPE [n_frames], total_samples, offsets int64 [B], lens int32 [B])."""
+    chunks, jobs, offsets, lens = [], [], [], []
+    byte_pos = 0
+    sample_pos = 0
+    for sc in scans:
+        keep_total = min(sc.samples, max_samples)
+        a, b = int(sc.off[0]), int(sc.off[-1] + sc.len[-1])
+        chunks.append(sc.data[a:b])
+        left = keep_total
+        first = sample_pos
+        for o, l, bs in zip(sc.off.tolist(), sc.len.tolist(), sc.blocks.tolist()):
+            k = min(bs, left)
+            jobs.append((byte_pos + (o - a), sample_pos, l, k, sc.bps, 0))
+            sample_pos += k
+            left -= k
+        offsets.append(first)
+        lens.append(keep_total)
+        byte_pos += b - a
+    frames = np.array(jobs, dtype=FRAME_DTYPE)
+    data = np.concatenate(chunks) if chunks else np.zeros(0, np.uint8)
+    return data, frames, sample_pos, np.array(offsets, dtype=np.int64), np.array(lens, dtype=np.int32)
+
+
+def decode_flac_frames_host(data: np.ndarray, frames: np.ndarray, total_samples: int):
+    """CPU twin of the device decoder (the same frame core compiled for the host): (pcm int16 [total_samples], status int32 [n])."""
+    from ._lib import load
+    lib = load()
+    padded = np.zeros(data.size + 8, dtype=np.uint8)
+    padded[:data.size] = data
+    pcm = np.zeros(total_samples, dtype=np.int16)
+    status = np.zeros(len(frames), dtype=np.int32)
+    rc = lib.slsb_flac_decode_frames_host(padded.ctypes.data, np.ascontiguousarray(frames).ctypes.data, len(frames), pcm.ctypes.data, status.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("slsb_flac_decode_frames_host failed")
+    return pcm, status
+
+
 def decode_audio_files(paths: Sequence[str], workers: int = 6, max_samples: Optional[int] = None) -> List[np.ndarray]:
     """Thread pool over ``read_audio_pcm16`` (the ctypes call into the FLAC decoder releases the GIL); order preserved."""
     if workers <= 1 or len(paths) < 2:
@@ -260,6 +341,73 @@ def score_pcm_shard(model, shard: PcmShard, batch: int = 64, samples: int = 6460
     hi = len(shard) if hi is None else hi
     return _score_batches(model.engine(), model._head(), model._prec(), samples, batch, hi - lo,
                           lambda a, b: shard.batch(lo + a, lo + b, max_samples=samples))
+
+
+def score_flac_files_device(model, paths: Sequence[str], batch: int = 64, samples: int = 64600, workers: int = 6, ahead: int = 4,
+                            stats: Optional[dict] = None) -> torch.Tensor:
+    """FLAC files -> scores with the decode ON THE DEVICE: the worker pool only reads and scans the files (frame table, CRCs: ~10x
+    cheaper than decoding), a batch travels as its compressed frames (about half the bytes of its PCM) and is decoded one frame per
+    GPU thread in front of the forward (``slsb_score_flac_host``).  A batch holding a stream the device decoder does not take
+    (stereo, not 16-bit) - or one it refuses - is decoded by the host decoder instead; ``stats`` counts both kinds."""
+    n = len(paths)
+    eng, head, prec = model.engine(), model._head(), model._prec()
+    out = torch.empty(n, dtype=torch.float32)
+    if stats is not None:
+        stats.update(device_batches=0, host_batches=0, flac_bytes=0, pcm_bytes=0)
+
+    def load(p):
+        with open(p, "rb") as f:
+            return scan_flac_bytes(f.read(), samples)
+
+    def stage(j):
+        a, b = j * batch, min((j + 1) * batch, n)
+        scans = [futures.pop(i).result() for i in range(a, b)]
+        if all(s.device_ok for s in scans):
+            data, frames, total, off, lens = pack_flac_batch(scans, samples)
+            return a, b, scans, (torch.from_numpy(data), torch.from_numpy(frames.view(np.uint8).reshape(-1)), total, torch.from_numpy(off), torch.from_numpy(lens))
+        return a, b, scans, None
+
+    def host_decode(a, b, scans):
+        clips = [decode_flac_bytes(s.data.tobytes(), samples) for s in scans]
+        lens = np.array([c.size for c in clips], dtype=np.int32)
+        off = np.zeros(len(clips), dtype=np.int64)
+        np.cumsum(lens[:-1], out=off[1:])
+        return eng.score_pcm16_arrays(torch.from_numpy(np.concatenate(clips)), torch.from_numpy(off), torch.from_numpy(lens), head, prec, samples)
+
+    pool = cf.ThreadPoolExecutor(max_workers=max(1, workers))
+    futures = {}
+    submitted = 0
+    nb = (n + batch - 1) // batch
+    try:
+        with cf.ThreadPoolExecutor(max_workers=1) as stager:
+            def submit_upto(j_last):
+                nonlocal submitted
+                hi = min(n, (j_last + 1) * batch)
+                while submitted < hi:
+                    futures[submitted] = pool.submit(load, paths[submitted])
+                    submitted += 1
+            submit_upto(ahead)
+            nxt = stager.submit(stage, 0) if nb else None
+            for j in range(nb):
+                a, b, scans, packed = nxt.result()
+                submit_upto(j + 1 + ahead)
+                if j + 1 < nb:
+                    nxt = stager.submit(stage, j + 1)            # scan results of the next batch are packed while this one is on the device
+                scores = None
+                if packed is not None:
+                    scores, _ = eng.score_flac_arrays(*packed, head, prec, samples)
+                    if stats is not None and scores is not None:
+                        stats["device_batches"] += 1
+                        stats["flac_bytes"] += int(packed[0].numel())
+                        stats["pcm_bytes"] += int(packed[2]) * 2
+                if scores is None:
+                    scores = host_decode(a, b, scans)
+                    if stats is not None:
+                        stats["host_batches"] += 1
+                out[a:b] = scores
+        return out
+    finally:
+        pool.shutdown(wait=False, cancel_futures=True)
 
 
 def score_audio_files(model, paths: Sequence[str], batch: int = 64, samples: int = 64600, workers: int = 6, ahead: int = 4) -> torch.Tensor:

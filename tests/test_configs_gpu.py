@@ -374,3 +374,63 @@ def test_engine_runs_on_its_own_device_and_restores_the_callers(sls, cuda):
     assert torch.equal(a.cpu(), b.cpu())
     with torch.no_grad():
         assert torch.equal(m0(x, return_sae_loss=False), a)             # the cuda:0 engine still works afterwards
+
+
+def test_device_flac_decoder_is_bit_exact_and_scores_like_the_host_path(sls, cuda, tmp_path):
+    """next row N2 on the device: one GPU thread per FLAC frame (csrc/flac_gpu.cu) == the host decoder (csrc/flac_decode.cpp), sample for
+    sample, over every subframe type / Rice setting / block size; FLAC files -> scores with the decode on the device == the host-decode
+    pipeline bit for bit; a batch with a stream the device decoder does not take falls back to the host decoder."""
+    import ctypes as C
+    import flac_enc
+    from helpers import P, stream
+    lib = sls.load_library()
+    rs = np.random.RandomState(12)
+    scans, refs = [], []
+    kinds = ["verbatim", "fixed0", "fixed1", "fixed2", "fixed3", "fixed4", "lpc1", "lpc4", "lpc8", "lpc12", "lpc13", "lpc32"]
+    for i in range(48):
+        n = int(rs.randint(1, 70000))
+        amp = float(rs.choice([3, 300, 12000]))
+        x = np.clip(amp * np.sin(np.arange(n) * rs.uniform(0.001, 1.0)) + rs.randn(n) * amp * rs.uniform(0, 0.5), -32768, 32767).astype(np.int64)
+        if i == 0:
+            x = np.where((np.arange(n) // 50) % 2 == 0, 32767, -32768)                        # full-scale square wave: long Rice code words
+        if i == 1:
+            x = (x >> 3) << 3                                                              # wasted bits
+        data = flac_enc.encode(x, kind=kinds[i % len(kinds)], porder=int(rs.randint(0, 5)), method=int(rs.randint(0, 2)),
+                               blocksize=int(rs.choice([192, 576, 1024, 4096, 4608, 333])), escape_partitions=(1,) if i % 7 == 3 else ())
+        scans.append(sls.scan_flac_bytes(data, 64600, sample_rate=None))
+        refs.append(sls.decode_flac_bytes(data, 64600, sample_rate=None))
+        assert np.array_equal(refs[-1], x[:64600].astype(np.int16))
+    d, fr, tot, off, lens = sls.pack_flac_batch(scans, 64600)
+    host_pcm, host_st = sls.decode_flac_frames_host(d, fr, tot)
+    bytes_dev = torch.zeros(d.size + 8, dtype=torch.uint8, device=cuda)
+    bytes_dev[:d.size] = torch.from_numpy(d).to(cuda)
+    frames_dev = torch.from_numpy(fr.view(np.uint8).reshape(-1).copy()).to(cuda)
+    pcm_dev = torch.zeros(tot, dtype=torch.int16, device=cuda)
+    st_dev = torch.zeros(len(fr), dtype=torch.int32, device=cuda)
+    assert lib.slsb_flac_decode_frames(P(bytes_dev), P(frames_dev), len(fr), P(pcm_dev), P(st_dev), stream()) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(st_dev.cpu().numpy(), host_st) and (host_st > 0).all()
+    got = pcm_dev.cpu().numpy()
+    assert np.array_equal(got, host_pcm)
+    for o, n, r in zip(off.tolist(), lens.tolist(), refs):
+        assert np.array_equal(got[o:o + n], r)
+    # files -> scores: decode on the device == decode on the host, bit for bit; a stereo file makes its batch take the host path
+    _, m = _small(sls, "sae")
+    paths = []
+    clips = [(rs.randn(n) * 2000).astype(np.int64) for n in (70000, 12345, 64600, 300, 40000, 64601, 9, 20000, 33333)]
+    for i, c in enumerate(clips):
+        paths.append(str(tmp_path / f"c{i}.flac"))
+        with open(paths[-1], "wb") as f:
+            f.write(flac_enc.encode(c, kind="lpc8" if i % 2 else "fixed2", porder=2, rate=16000))
+    ref_scores = sls.score_audio_files(m, paths, batch=4, workers=2)
+    stats = {}
+    dev_scores = sls.score_flac_files_device(m, paths, batch=4, workers=2, stats=stats)
+    assert torch.equal(dev_scores, ref_scores) and stats["device_batches"] == 3 and stats["host_batches"] == 0
+    assert 0 < stats["flac_bytes"] < stats["pcm_bytes"]
+    stereo = str(tmp_path / "st.flac")
+    with open(stereo, "wb") as f:
+        f.write(flac_enc.encode(np.stack([clips[1], clips[1] // 2], 1), kind="fixed2", stereo=10, rate=16000))
+    mixed = paths[:3] + [stereo] + paths[3:5]
+    stats = {}
+    mixed_scores = sls.score_flac_files_device(m, mixed, batch=4, workers=2, stats=stats)
+    assert torch.equal(mixed_scores, sls.score_audio_files(m, mixed, batch=4, workers=2)) and stats["host_batches"] == 1 and stats["device_batches"] == 1

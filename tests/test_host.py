@@ -980,3 +980,103 @@ def test_flac_decoder_roundtrip_property(lib):
         assert np.array_equal(pcm if stereo is not None else pcm[:, 0], x)
 
     check()
+
+
+# ---------------------------------------------------------------------------------------------- device FLAC decoder: host side
+def _frame_core(sls, data, max_samples=64600):
+    """scan -> frame jobs -> the frame core compiled for the host (csrc/flac_frame.h, the code the GPU runs one thread per frame)."""
+    sc = sls.scan_flac_bytes(data, max_samples, sample_rate=None)
+    d, fr, tot, off, lens = sls.pack_flac_batch([sc], max_samples)
+    pcm, st = sls.decode_flac_frames_host(d, fr, tot)
+    return sc, pcm, st, fr
+
+
+def test_flac_frame_core_matches_host_decoder_on_every_syntax_element(sls, lib):
+    """The frame core of the device decoder (flac_frame.h: streamed Rice decode + predictor restore, word-wise bit reader) equals
+    flac_decode.cpp sample for sample on CONSTANT / VERBATIM / FIXED 0-4 / LPC 1-32, both Rice methods, partition orders 0-4,
+    escape partitions, wasted bits, odd block sizes, two-byte frame numbers - for whole clips and for heads that end inside a frame."""
+    import flac_enc
+    rs = np.random.RandomState(5)
+    t = np.arange(20000)
+    mono = (8000 * np.sin(t * 0.05) + rs.randn(t.size) * 300).astype(np.int64)
+    sq = np.where((t // 50) % 2 == 0, 32767, -32768)
+    cases = [(mono, dict(kind="verbatim")), (mono, dict(kind="fixed0")), (mono, dict(kind="fixed1", porder=1)), (mono, dict(kind="fixed2", porder=3)),
+             (mono, dict(kind="fixed3", porder=4, method=1)), (mono, dict(kind="fixed4", porder=2, escape_partitions=(1, 3))),
+             (mono, dict(kind="lpc8", porder=2)), (mono, dict(kind="lpc12", porder=3)), (mono, dict(kind="lpc13", porder=1)),
+             (mono, dict(kind="lpc32", porder=1, blocksize=1152)), (mono, dict(kind="fixed2", blocksize=777)),
+             (mono[:3000], dict(kind="fixed2", blocksize=16, extra_metadata=False)), (mono, dict(kind="lpc4", with_md5=False)),
+             (sq, dict(kind="fixed1", porder=2)), (np.zeros(5000, np.int64), dict(kind="constant")), ((mono >> 3) << 3, dict(kind="fixed2")),
+             (mono, dict(kind="lpc1", blocksize=192)), (mono, dict(kind="lpc5", blocksize=4608, porder=2))]
+    for x, kw in cases:
+        data = flac_enc.encode(x, **kw)
+        for cut in (64600, 5000, 1):
+            ref = sls.decode_flac_bytes(data, cut, sample_rate=None)
+            sc, pcm, st, fr = _frame_core(sls, data, cut)
+            assert sc.device_ok and (st > 0).all(), (kw, cut, st)
+            assert st.tolist() == sc.blocks.tolist()                      # the status of a decoded frame is its block size
+            assert np.array_equal(pcm, ref) and np.array_equal(ref, x[:cut].astype(np.int16)), (kw, cut)
+            assert int(fr["keep"].sum()) == ref.size
+
+
+def test_flac_scan_frame_table_and_rejections(sls, lib):
+    """slsb_flac_scan: frame boundaries are exact (offsets chain, the lengths cover the audio part of the file), the RFC 9639 example
+    files scan and decode, streams the device decoder does not take are flagged, damaged streams are refused."""
+    import flac_enc
+    rs = np.random.RandomState(6)
+    x = (5000 * np.sin(np.arange(30000) * 0.02) + rs.randn(30000) * 500).astype(np.int64)
+    data = flac_enc.encode(x, kind="lpc8", porder=3, blocksize=1024)
+    sc = sls.scan_flac_bytes(data, None, sample_rate=None)
+    assert len(sc.off) == 30 and sc.samples == 30000 and sc.total == 30000 and sc.blocks.tolist() == [1024] * 29 + [30000 - 29 * 1024]
+    assert np.array_equal(sc.off[1:], sc.off[:-1] + sc.len[:-1]) and int(sc.off[-1] + sc.len[-1]) == len(data)
+    head = sls.scan_flac_bytes(data, 2500, sample_rate=None)                  # the head needs 3 frames
+    assert len(head.off) == 3 and head.samples == 2500
+    # a sync code planted inside a frame (0xFF 0xF8 ...) must not split it: raw 16-bit samples that spell sync codes
+    evil = np.tile(np.array([-8, -1, -7, -2], dtype=np.int64), 3000)          # 0xFFF8 0xFFFF 0xFFF9 0xFFFE as verbatim samples
+    data2 = flac_enc.encode(evil, kind="verbatim", blocksize=4096)
+    sc2, pcm2, st2, _ = _frame_core(sls, data2)
+    assert len(sc2.off) == 3 and (st2 > 0).all() and np.array_equal(pcm2, evil.astype(np.int16))
+    # RFC 9639 appendix D: example 1 (mono... if 16-bit mono) decodes through the frame core; stereo examples are flagged, not decoded
+    for name, (hexs, rate, ch, bps, want) in RFC9639_EXAMPLES.items():
+        raw = bytes.fromhex(hexs.replace(" ", ""))
+        s3 = sls.scan_flac_bytes(raw, None, sample_rate=None)
+        assert (s3.rate, s3.channels, s3.bps) == (rate, ch, bps) and s3.samples == len(want), name
+        assert s3.device_ok == (ch == 1 and bps == 16), name
+        if s3.device_ok:
+            _, pcm3, st3, _ = _frame_core(sls, raw, None)
+            assert (st3 > 0).all() and pcm3.tolist() == [w[0] for w in want], name
+    stereo = flac_enc.encode(np.stack([x, x // 2], 1), kind="fixed2", stereo=10)
+    assert not sls.scan_flac_bytes(stereo, 64600, sample_rate=None).device_ok
+    assert not sls.scan_flac_bytes(flac_enc.encode(x >> 8, bps=8), 64600, sample_rate=None).device_ok
+    with pytest.raises(sls.AudioFormatError):
+        sls.scan_flac_bytes(flac_enc.encode(x, rate=44100), 64600)             # wrong rate, as the host path
+    bad = bytearray(data)
+    bad[len(bad) // 2] ^= 0x04                                                 # payload damage: some frame's CRC-16 no longer matches
+    with pytest.raises(sls.AudioFormatError):
+        sls.scan_flac_bytes(bytes(bad), None, sample_rate=None)
+    with pytest.raises(sls.AudioFormatError):
+        sls.scan_flac_bytes(data[:len(data) // 2], None, sample_rate=None)     # truncated
+    # the frame core refuses what it is not built for instead of guessing (status -9), the caller then decodes on the host
+    d, fr, tot, off, lens = sls.pack_flac_batch([sls.scan_flac_bytes(stereo, 64600, sample_rate=None)], 64600)
+    _, st = sls.decode_flac_frames_host(d, fr, tot)
+    assert (st == -9).all()
+
+
+def test_flac_frame_core_property_random_streams(sls):
+    """decode_frames(scan(encode(x))) == x over random signals, predictors, Rice settings and block sizes; several clips per batch."""
+    import flac_enc
+    rs = np.random.RandomState(7)
+    scans, refs = [], []
+    for i in range(24):
+        n = int(rs.randint(1, 9000))
+        amp = float(rs.choice([3, 300, 12000]))
+        x = np.clip(amp * np.sin(np.arange(n) * rs.uniform(0.001, 1.0)) + rs.randn(n) * amp * rs.uniform(0, 0.5), -32768, 32767).astype(np.int64)
+        kind = str(rs.choice(["verbatim", "constant" if False else "fixed0", "fixed1", "fixed2", "fixed3", "fixed4", "lpc2", "lpc8", "lpc12", "lpc20"]))
+        data = flac_enc.encode(x, kind=kind, porder=int(rs.randint(0, 5)), method=int(rs.randint(0, 2)), blocksize=int(rs.choice([192, 576, 1024, 4096, 333])))
+        cut = int(rs.choice([64600, max(1, n // 2), max(1, n - 1)]))
+        scans.append(sls.scan_flac_bytes(data, cut, sample_rate=None))
+        refs.append(x[:cut].astype(np.int16))
+    d, fr, tot, off, lens = sls.pack_flac_batch(scans, 64600)
+    pcm, st = sls.decode_flac_frames_host(d, fr, tot)
+    assert (st > 0).all() and tot == sum(r.size for r in refs)
+    for o, n, r in zip(off.tolist(), lens.tolist(), refs):
+        assert n == r.size and np.array_equal(pcm[o:o + n], r)

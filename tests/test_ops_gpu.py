@@ -373,3 +373,86 @@ def test_topk_matches_canonical_rule(lib, cuda, D, k):
     assert torch.equal(enc, ref)     # bit-exact selection, canonical lowest-index tie rule
     assert torch.equal(thr, x.gather(-1, order[:, -1:]).squeeze(-1))
     assert int((enc[6] != 0).nonzero().max()) == k - 1
+
+
+# ------------------------------------------------------------------------------------------ fused select + pool
+def _canonical_topk_mask(x, k):
+    """Keep mask of the canonical rule: k largest per row, ties at the threshold go to the lowest indices."""
+    order = torch.sort(x, dim=-1, descending=True, stable=True).indices[..., :k]
+    return torch.zeros_like(x, dtype=torch.bool).scatter_(-1, order, True)
+
+
+def _canonical_pool(kept_acts, lens, chunk=8):
+    """Mean over the valid frames in the kernels' summation order: frames of a chunk in order, chunk partials in order
+    (fp32 adds are exact IEEE operations, so a torch loop in the same order gives the same bits)."""
+    B, T, D = kept_acts.shape
+    total = torch.zeros(B, D, device=kept_acts.device)
+    for c0 in range(0, T, chunk):
+        part = torch.zeros(B, D, device=kept_acts.device)
+        for t in range(c0, min(c0 + chunk, T)):
+            valid = (t < lens).to(kept_acts.dtype)[:, None]
+            part = part + kept_acts[:, t] * valid
+        total = total + part
+    return total / lens.to(torch.float32)[:, None]
+
+
+@pytest.mark.parametrize("B,T,D,k,with_lens", [(3, 201, 4096, 128, False), (4, 50, 4096, 128, True), (2, 9, 1024, 64, True), (2, 33, 2048, 7, False)])
+def test_topk_pool_fused_is_bit_exact(lib, cuda, B, T, D, k, with_lens):
+    """H-SAE scoring path (model.py:68-79 + :245): per-frame top-k + masked mean pool in one kernel, activations read once."""
+    x = F.relu(_rand((B, T, D), 71))
+    x[0, 3] = 0.0                               # all-zero frame
+    x[1, 2, :] = 0.5                            # all-equal frame: lowest k indices win
+    x[0, 5, : D // 2] = x[0, 5, D // 2:]        # real ties at the threshold
+    lens = torch.tensor([T - 3 * i for i in range(B)], dtype=torch.int32, device=cuda) if with_lens else None
+    nc = lib.slsb_op_pool_chunks(T)
+    assert nc == (T + 7) // 8
+    thr = torch.empty(B * T, device=cuda); cut = torch.empty(B * T, device=cuda, dtype=torch.int32)
+    partial = torch.empty(B, nc, D, device=cuda); pooled = torch.empty(B, D, device=cuda)
+    ok(lib, lib.slsb_op_topk_pool(P(x), B, T, D, k, P(lens), P(thr), P(cut), P(partial), P(pooled), stream()), "topk_pool")
+    mask = _canonical_topk_mask(x, k)
+    full = torch.full((B,), T, device=cuda, dtype=torch.int32)
+    ref = _canonical_pool(x * mask, lens if with_lens else full)
+    assert torch.equal(pooled, ref)
+    # thr / cut agree with the stand-alone selection kernel (what the dense / compact code consumers read)
+    thr2 = torch.empty(B * T, device=cuda); cut2 = torch.empty(B * T, device=cuda, dtype=torch.int32)
+    ok(lib, lib.slsb_op_topk(P(x), B * T, D, k, P(thr2), P(cut2), None, stream()), "topk")
+    assert torch.equal(thr, thr2) and torch.equal(cut, cut2)
+    # selection only (no pooling buffers)
+    thr3 = torch.empty(B * T, device=cuda); cut3 = torch.empty(B * T, device=cuda, dtype=torch.int32)
+    ok(lib, lib.slsb_op_topk_pool(P(x), B, T, D, k, None, P(thr3), P(cut3), None, None, stream()), "topk_pool select only")
+    assert torch.equal(thr, thr3) and torch.equal(cut, cut3)
+
+
+@pytest.mark.parametrize("B,T,D,k,window,ties", [(2, 201, 4096, 128, 8, False), (3, 37, 4096, 128, 8, True), (2, 20, 1024, 64, 4, True), (2, 11, 2048, 9, 2, False)])
+def test_window_pool_fused_is_bit_exact(lib, cuda, B, T, D, k, window, ties):
+    """H-WIN scoring path (model_window_topk.py:118-203): window sums -> per-window top-k -> votes -> per-frame top-k -> pooled kept
+    activations, with the window sums and votes held in registers; against a torch restatement with the canonical tie rule."""
+    x = F.relu(_rand((B, T, D), 72))
+    if ties:
+        x[0, :, 100:] = 0.0                     # fewer than k positive features: zeros tie at the threshold in every window
+        x[1, 4] = 0.0
+    stride = max(1, window // 2)
+    nw = (T - window) // stride + 1
+    sums = torch.zeros(B, nw, D, device=cuda)
+    for j in range(window):                     # frame order, as the kernel and the reference's sum over the window
+        sums = sums + torch.stack([x[:, w * stride + j] for w in range(nw)], 1)
+    wmask_ref = _canonical_topk_mask(sums, k)
+    votes_ref = torch.zeros(B, T, D, device=cuda)
+    for w in range(nw):                         # ascending window order (:175-185)
+        sl = slice(w * stride, w * stride + window)
+        votes_ref[:, sl] = votes_ref[:, sl] + x[:, sl] * wmask_ref[:, w:w + 1]
+    keep = _canonical_topk_mask(votes_ref, k)
+    full = torch.full((B,), T, device=cuda, dtype=torch.int32)
+    pooled_ref = _canonical_pool(x * keep, full)
+    nc = lib.slsb_op_pool_chunks(T)
+    wmask = torch.empty(B, nw, 256, device=cuda, dtype=torch.int32)
+    for want_votes in (True, False):
+        thr = torch.empty(B * T, device=cuda); cut = torch.empty(B * T, device=cuda, dtype=torch.int32)
+        votes = torch.empty(B, T, D, device=cuda) if want_votes else None
+        partial = torch.empty(B, nc, D, device=cuda); pooled = torch.empty(B, D, device=cuda)
+        ok(lib, lib.slsb_op_window_pool(P(x), B, T, D, k, window, P(wmask), P(thr), P(cut), P(votes), P(partial), P(pooled), stream()), "window_pool")
+        assert torch.equal(pooled, pooled_ref)
+        if want_votes:
+            assert torch.equal(votes, votes_ref)
+            kth = torch.sort(votes_ref, dim=-1, descending=True, stable=True).values[..., k - 1].reshape(-1)
+            assert torch.equal(thr, kth)

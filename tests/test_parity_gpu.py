@@ -81,19 +81,23 @@ def test_logprob_parity_and_taps(sls, cuda, clips, case, precision):
     assert torch.isfinite(out).all()
     assert err <= TOL[precision], f"{head}/{precision}: {err} > {TOL[precision]}"
     assert torch.equal(out.argmax(-1), ref.argmax(-1))
-    lim = 2e-5 if precision == "fp32" else 3e-2
+    lim = 5e-6 if precision == "fp32" else 1.5e-2              # 2 x the observed 2.3e-6 / 7.5e-3 (profiles/r02 parity logs)
     assert x_rel <= lim and all(r <= lim for _, r in layer_rel), (x_rel, layer_rel)
     # committed golden fixture (minted in the build container by oracle/make_golden.py)
     fx = np.load(os.path.join(GOLDEN, f"xlsr300m_{head}_b2.npz"))
     assert float(np.abs(out.numpy() - fx["logprob"]).max()) <= TOL[precision]
     got_tap = eng.get_tensor("x", (B, T, D)).cpu()[:, ::25, ::64].numpy()
-    assert np.abs(got_tap - fx["x_tap"]).max() <= (1e-4 if precision == "fp32" else 0.15)
+    tap_err = float(np.abs(got_tap - fx["x_tap"]).max())
+    print(f"[{head}/{precision}] x_tap max|err|={tap_err:.3e}")
+    assert tap_err <= (1e-4 if precision == "fp32" else 0.15)
     if head != "sls" and precision == "fp32":
         pooled = eng.get_tensor("pooled", (B, 4096)).cpu()
         assert float((pooled - taps["pooled"]).abs().max()) <= 1e-4
         enc = eng.get_tensor("encoded", (B, T, 4096)).cpu()
         nnz = (enc > 0).sum(-1)
-        assert int((nnz != (taps["encoded"] > 0).sum(-1)).sum()) <= 2       # selection agrees frame by frame
+        nnz_diff = int((nnz != (taps["encoded"] > 0).sum(-1)).sum())
+        print(f"[{head}/{precision}] frames whose kept count differs from the oracle: {nnz_diff}; pooled max|err|={float((pooled - taps['pooled']).abs().max()):.3e}")
+        assert nnz_diff <= 2                                                # selection agrees frame by frame
         if head == "sae":
             assert int(nnz.max()) <= 128
 
