@@ -23,7 +23,7 @@
 
 namespace flacf {
 
-enum { FLACF_OK = 0, FLACF_TRUNC = -3, FLACF_HEADER = -4, FLACF_RESERVED = -7, FLACF_UNSUPPORTED = -9, FLACF_LENGTH = -12 };
+enum { FLACF_OK = 0, FLACF_TRUNC = -3, FLACF_HEADER = -4, FLACF_RESERVED = -7, FLACF_UNSUPPORTED = -9, FLACF_LENGTH = -12, FLACF_RANGE = -13 };
 
 // MSB-first bit reader over 32-bit words of an arbitrarily aligned byte range; the buffer must stay readable up to the next
 // 4-byte boundary after the range (the callers pad their buffers by 8 bytes).
@@ -116,29 +116,34 @@ struct Bits {
     FLACF_HD void align() { const int r = cnt & 7; win <<= r; cnt -= r; }                    // `left` is a multiple of 8
 };
 
-constexpr int kMaxOrd = 12;       // predictor orders up to 12 (every libFLAC preset) run on the register shift chain
-
 // Sink of decoded samples: applies the wasted-bits shift and stores the first `keep` as int16.
 struct Out16 {
     int16_t* out; int keep; int wasted; int i;
-    FLACF_HD void put(int64_t v) {
-        if (i < keep) out[i] = (int16_t)(int32_t)((uint64_t)v << wasted);
+    FLACF_HD void put(int32_t v) {
+        if (i < keep) out[i] = (int16_t)(int32_t)((uint32_t)v << wasted);
         ++i;
     }
 };
 
-// Residual partitions + predictor, streamed.  `hist[0]` is the most recent sample; coefficients beyond `order` are zero.
-// Orders 13..32 take the generic path with the history in a small local array.
-template <int ORD>
-FLACF_HD int decode_predicted(Bits& br, Out16& o, int blocksize, int order, const int32_t* coef_in, int shift, const int64_t* warm) {
-    int64_t hist[ORD];
-    int64_t coef[ORD];
+// Residual partitions + predictor, streamed: ONE loop over the samples of the block (partition headers are read when the running
+// count reaches zero), so the 32 frames a warp decodes walk the same trip count whatever their partition orders are.
+// `hist[0]` is the most recent sample; coefficients beyond `order` are zero, so TAPS only has to be >= order.
+// 32-bit datapath: samples, coefficients and the prediction sum are int32 - what libFLAC itself does when
+// bps + precision + log2(order) <= 32 (every 16-bit stream an encoder produces).  `maxabs` tracks the largest |sample| so the caller
+// can PROVE afterwards that no 32-bit sum wrapped (sum |coef| * maxabs < 2^31); a stream where it might have is handed to the
+// host decoder (64-bit sums), so the device never returns a sample that differs from flac_decode.cpp.
+template <int TAPS>
+FLACF_HD int decode_predicted(Bits& br, Out16& o, int blocksize, int order, const int32_t* coef_in, int shift, const int32_t* warm,
+                              uint32_t& maxabs) {
+    int32_t hist[TAPS], coef[TAPS];
 #pragma unroll
-    for (int j = 0; j < ORD; ++j) { hist[j] = 0; coef[j] = j < order ? (int64_t)coef_in[j] : 0; }
+    for (int j = 0; j < TAPS; ++j) { hist[j] = 0; coef[j] = j < order ? coef_in[j] : 0; }
     for (int i = 0; i < order; ++i) {                 // warm-up samples, oldest first
 #pragma unroll
-        for (int j = ORD - 1; j > 0; --j) hist[j] = hist[j - 1];
+        for (int j = TAPS - 1; j > 0; --j) hist[j] = hist[j - 1];
         hist[0] = warm[i];
+        const uint32_t a = (uint32_t)(warm[i] < 0 ? -(int64_t)warm[i] : warm[i]);
+        maxabs = a > maxabs ? a : maxabs;
         o.put(warm[i]);
     }
     const uint32_t method = br.get(2);
@@ -147,35 +152,54 @@ FLACF_HD int decode_predicted(Bits& br, Out16& o, int blocksize, int order, cons
     const int porder = (int)br.get(4);
     const int parts = 1 << porder;
     if (porder > 0 && ((blocksize >> porder) << porder) != blocksize) return FLACF_HEADER;
-    for (int p = 0; p < parts; ++p) {
-        const int count = (blocksize >> porder) - (p == 0 ? order : 0);
-        if (count < 0) return FLACF_HEADER;
-        const int k = (int)br.get(pbits);
-        const bool escape = k == esc;
-        const int raw = escape ? (int)br.get(5) : 0;
-        for (int n = 0; n < count; ++n) {
-            int32_t r;
-            if (escape) {
-                r = raw ? br.sget(raw) : 0;
-            } else {
-                const uint32_t u = br.rice(k);
-                r = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);             // zig-zag
-            }
-            uint64_t acc = 0;
-#pragma unroll
-            for (int j = 0; j < ORD; ++j) acc += (uint64_t)coef[j] * (uint64_t)hist[j];
-            const int64_t v = (int64_t)((uint64_t)((int64_t)acc >> shift) + (uint64_t)(int64_t)r);
-#pragma unroll
-            for (int j = ORD - 1; j > 0; --j) hist[j] = hist[j - 1];
-            hist[0] = v;
-            o.put(v);
+    if ((blocksize >> porder) < order) return FLACF_HEADER;
+    int part = 0, remaining = 0, k = 0, raw = 0;
+    bool escape = false;
+    for (int i = order; i < blocksize; ++i) {
+        while (remaining == 0) {                       // next partition header (a partition may be empty: order == its length)
+            if (part == parts) return FLACF_HEADER;
+            remaining = (blocksize >> porder) - (part == 0 ? order : 0);
+            k = (int)br.get(pbits);
+            escape = k == esc;
+            raw = escape ? (int)br.get(5) : 0;
+            ++part;
         }
-        if (br.fail) return FLACF_TRUNC;
+        --remaining;
+        int32_t r;
+        if (escape) {
+            r = raw ? br.sget(raw) : 0;
+        } else {
+            const uint32_t u = br.rice(k);
+            r = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);                 // zig-zag
+        }
+        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;                       // four partial sums (wrapping): shorter dependency chains
+#pragma unroll
+        for (int j = 0; j < TAPS; j += 4) {
+            a0 += (uint32_t)coef[j] * (uint32_t)hist[j];
+            if (j + 1 < TAPS) a1 += (uint32_t)coef[j + 1] * (uint32_t)hist[j + 1];
+            if (j + 2 < TAPS) a2 += (uint32_t)coef[j + 2] * (uint32_t)hist[j + 2];
+            if (j + 3 < TAPS) a3 += (uint32_t)coef[j + 3] * (uint32_t)hist[j + 3];
+        }
+        const int32_t sum = (int32_t)((a0 + a1) + (a2 + a3));
+        const int32_t v = (int32_t)((uint32_t)(sum >> shift) + (uint32_t)r);
+#pragma unroll
+        for (int j = TAPS - 1; j > 0; --j) hist[j] = hist[j - 1];
+        hist[0] = v;
+        const uint32_t a = (uint32_t)(v < 0 ? -(int64_t)v : v);
+        maxabs = a > maxabs ? a : maxabs;
+        o.put(v);
     }
-    return FLACF_OK;
+    if (br.fail) return FLACF_TRUNC;
+    while (part < parts) {                             // trailing empty partitions still carry their headers
+        if ((blocksize >> porder) - (part == 0 ? order : 0) != 0) return FLACF_HEADER;
+        const int kk = (int)br.get(pbits);
+        if (kk == esc) br.get(5);
+        ++part;
+    }
+    return br.fail ? FLACF_TRUNC : FLACF_OK;
 }
 
-// One mono subframe of `bps` bits -> o
+// One mono subframe of `bps` (<= 17) bits -> o
 FLACF_HD int decode_subframe(Bits& br, Out16& o, int blocksize, int bps) {
     if (br.get(1)) return FLACF_RESERVED;
     const int type = (int)br.get(6);
@@ -186,7 +210,7 @@ FLACF_HD int decode_subframe(Bits& br, Out16& o, int blocksize, int bps) {
     if (bps < 1) return FLACF_HEADER;
     o.wasted = wasted;
     if (type == 0) {                                        // CONSTANT
-        const int64_t v = br.sget(bps);
+        const int32_t v = br.sget(bps);
         for (int i = 0; i < blocksize; ++i) o.put(v);
     } else if (type == 1) {                                 // VERBATIM
         for (int i = 0; i < blocksize; ++i) o.put(br.sget(bps));
@@ -194,7 +218,7 @@ FLACF_HD int decode_subframe(Bits& br, Out16& o, int blocksize, int bps) {
         const bool lpc = type >= 32;
         const int order = lpc ? (type & 31) + 1 : type - 8;
         if (order > blocksize) return FLACF_HEADER;
-        int64_t warm[32];
+        int32_t warm[32];
         for (int i = 0; i < order; ++i) warm[i] = br.sget(bps);
         int32_t coef[32];
         int shift = 0;
@@ -209,11 +233,17 @@ FLACF_HD int decode_subframe(Bits& br, Out16& o, int blocksize, int bps) {
             for (int i = 0; i < order; ++i) coef[i] = fixed[order][i];
         }
         if (br.fail) return FLACF_TRUNC;
+        uint64_t sumabs = 0;
+        for (int i = 0; i < order; ++i) sumabs += (uint64_t)(coef[i] < 0 ? -(int64_t)coef[i] : coef[i]);
+        uint32_t maxabs = 0;
         int rc;
-        if (order <= 4) rc = decode_predicted<4>(br, o, blocksize, order, coef, shift, warm);
-        else if (order <= kMaxOrd) rc = decode_predicted<kMaxOrd>(br, o, blocksize, order, coef, shift, warm);
-        else rc = decode_predicted<32>(br, o, blocksize, order, coef, shift, warm);
+        if (order <= 4) rc = decode_predicted<4>(br, o, blocksize, order, coef, shift, warm, maxabs);
+        else if (order <= 8) rc = decode_predicted<8>(br, o, blocksize, order, coef, shift, warm, maxabs);
+        else if (order <= 12) rc = decode_predicted<12>(br, o, blocksize, order, coef, shift, warm, maxabs);
+        else rc = decode_predicted<32>(br, o, blocksize, order, coef, shift, warm, maxabs);
         if (rc != FLACF_OK) return rc;
+        // proof that the 32-bit sums never wrapped and every sample stayed an int32: otherwise the host decoder takes the clip
+        if (sumabs * (uint64_t)maxabs >= (1ull << 31) || maxabs >= (1u << 30)) return FLACF_RANGE;
     } else {
         return FLACF_RESERVED;
     }
