@@ -26,8 +26,9 @@ t0 = int(tr[0, 9]) if int(tr[0, 9]) else int(tr[tr > 0].min())
 names = ["S_iss", "S_com", "P_seen", "PV_com", "S_seen", "max_dn", "P_pub", "O_seen", "epi_dn", "st_free", "ld_land"]
 print("unit " + " ".join(f"{n:>8s}" for n in names) + " | S_lat softmax(p1,p2) PVwake PV_lat epi period")
 prev = {}
-for u in range(16):
+NW = int(os.environ.get("SLSB_ATTN_NW", "4"))
+for u in range(24):
     r = [int(tr[u, e]) - t0 if int(tr[u, e]) else -1 for e in range(11)]
     s_lat = r[4] - r[1]; p1 = r[5] - r[4]; p2 = r[6] - r[5]; pvw = r[2] - r[6]; pv_lat = r[7] - r[3]; epi = r[8] - r[7]
-    per = r[8] - prev.get(u % 2, r[8]); prev[u % 2] = r[8]
+    per = r[8] - prev.get(u % NW, r[8]); prev[u % NW] = r[8]
     print(f"{u:4d} " + " ".join(f"{v:8d}" for v in r) + f" | {s_lat:5d} {p1:5d} {p2:5d} {pvw:6d} {pv_lat:6d} {epi:5d} {per:6d}")
