@@ -616,278 +616,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     }
 }
 
-
-// =================================================================================================
-// tcgen05, FOUR units in flight per SM (T in (128, 256]: two query tiles per item)
-//
-// The two-half kernel above keeps two 128-query units resident (S needs Tp <= 256 fp32 columns next to the 64 of O) and the two
-// softmax warpgroups walk the same phases in step: while they wait for S, for the row maxima's TMEM loads or for P V, all four
-// schedulers idle (~45 % of the kernel, profiles/r01_attention_notes.md).  Here TMEM is cut into four 128-column regions
-// (S block at [0, 64), O at [64, 128)) and every unit runs the key-block schedule of the wide kernel:
-//   round 1: S is formed in blocks of <= 128 keys (O's columns are still free) only for the row maxima,
-//   round 2: S is formed again in blocks of <= 64 keys, exponentiated against the GLOBAL row max, written back in place as
-//            packed bf16 and multiplied into O (A operand from tensor memory).
-// QK^T costs 4 MMAs per block on a tensor pipe that idles, so forming it twice is the cheap way to fit four units, whose
-// latencies then hide behind each other's exponentials.  16 softmax warps (4 warpgroups, thread == query row == TMEM lane),
-// warp 16 = TMA producer, warps 17..20 = one MMA issuer per region.  Units u, u + 4, ... belong to region u % 4; the two units
-// of an item sit on regions {0, 1} or {2, 3} and share a {2 Q tiles, K, V} stage.  The output tile of a unit is staged in the
-// unit's own (dead) Q tile, so a stage is released by 2 MMA commits + 2 "store has read the tile" arrivals.
-// =================================================================================================
-constexpr int R4_THREADS = 768;               // 16 softmax warps + 8 service warps (producer, 4 issuers, 3 idle)
-constexpr int R4_REGS_SERVICE = 48, R4_REGS_SOFTMAX = 96;      // setmaxnreg moves registers inside the pool the CTA got at launch (768 x 80)
-static_assert(512 * R4_REGS_SOFTMAX + 256 * R4_REGS_SERVICE <= R4_THREADS * 80, "register budget of the six warpgroups");
-constexpr int R4_REGION = 128, R4_OCOL = 64;
-struct Attn4Geo {
-    static constexpr int STAGES = 2;
-    static constexpr int SQ = 2 * AQ * 128, SK = 256 * 128, SV = 256 * 128;
-    static constexpr int STAGE = SQ + SK + SV;            // 96 KB
-    static constexpr int BAR_OFFSET = STAGES * STAGE;
-    static constexpr int SMEM = BAR_OFFSET + 256;
-};
-// key block kb of a balanced partition of g sixteen-key groups into nkb blocks
-__device__ __forceinline__ void key_block(int g, int nkb, int kb, int& kb0, int& wk) {
-    const int base = g / nkb, rem = g - base * nkb;
-    kb0 = 16 * (kb * base + min(kb, rem));
-    wk = 16 * (base + (kb < rem ? 1 : 0));
-}
-
-__global__ void __launch_bounds__(R4_THREADS, 1)
-attn_tc4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_out,
-                int Tn, int Tp, int H, int n_items, int nkb1, int nkb2, const int* __restrict__ lens, int stagger, long long* __restrict__ trace) {
-    using G = Attn4Geo;
-    constexpr int n_qt = 2;
-    extern __shared__ __align__(1024) uint8_t smem[];
-    if ((smem_u32(smem) & 1023u) != 0) { if (threadIdx.x == 0) printf("slsb: dynamic smem base not 1024-aligned\n"); __trap(); }
-#define ATT_TRACE(unit, ev) do { if (trace != nullptr && blockIdx.x == 0 && (unit) < 64) trace[(unit) * 16 + (ev)] = clock64(); } while (0)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G::BAR_OFFSET);
-    uint64_t* full = bars;                    // [2] loads landed
-    uint64_t* stage_free = bars + 2;          // [2] MMAs of both units done (2 commits) + both output stores have read their tile (2 arrivals)
-    uint64_t* s_ready = bars + 4;             // [4] S block complete in region w
-    uint64_t* p_ready = bars + 8;             // [4] S block consumed / P written (4 warp arrivals)
-    uint64_t* o_ready = bars + 12;            // [4] O complete (once per unit)
-    uint64_t* tmem_free = bars + 16;          // [4] O read out of region w (4 warp arrivals)
-    uint64_t* pv_done = bars + 20;            // [4] P_kb V_kb complete
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 24);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int D = H * HD;
-    const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int my_units = my_items * n_qt;
-    const int nph = nkb1 + nkb2;
-    const int g16 = Tp / 16;
-
-    griddep_launch();
-    if (warp == 16 && lane == 0) {
-        tma_prefetch_desc(&tm_q);
-        tma_prefetch_desc(&tm_kv);
-        tma_prefetch_desc(&tm_out);
-        for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 1); mbar_init(&stage_free[i], 2 * n_qt); }
-        for (int i = 0; i < 4; ++i) {
-            mbar_init(&s_ready[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_ready[i], 1); mbar_init(&tmem_free[i], 4); mbar_init(&pv_done[i], 1);
-        }
-        mbar_fence_init();
-    }
-    if (warp == 17) tmem_alloc<512>(tmem_ptr);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_ptr;
-    griddep_wait();
-
-    if (warp >= 16) {
-        reg_dealloc<R4_REGS_SERVICE>();
-        if (warp == 16) {
-            // ===================== TMA producer =====================
-            if (lane == 0) {
-                const uint32_t tx = (uint32_t)(n_qt * AQ * 128 + 2 * Tp * 128);
-                for (int n = 0; n < my_items; ++n) {
-                    const int item = blockIdx.x + n * gridDim.x;
-                    const int b = item / H, h = item - b * H;
-                    const int st = n & 1;
-                    mbar_wait(&stage_free[st], ((n >> 1) & 1) ^ 1);
-                    ATT_TRACE(n * n_qt, 9);
-                    uint8_t* base = smem + st * G::STAGE;
-                    mbar_expect_tx(&full[st], tx);
-                    for (int qt = 0; qt < n_qt; ++qt) tma_load_2d(base + qt * (AQ * 128), &tm_q, &full[st], h * HD, b * Tn + qt * AQ);
-                    tma_load_2d(base + G::SQ, &tm_kv, &full[st], D + h * HD, b * Tn);
-                    tma_load_2d(base + G::SQ + G::SK, &tm_kv, &full[st], 2 * D + h * HD, b * Tn);
-                }
-            }
-        } else if (warp <= 20) {
-            // ===================== MMA issuers: warp 17 + w serves region w =====================
-            if (lane == 0) {
-                const int w = warp - 17;
-                const uint32_t idesc_o = make_idesc_bf16(AQ, HD, 0, 1);
-                const uint32_t th = tmem + w * R4_REGION;
-                uint32_t ph = 0, pvn = 0;
-                for (int u = w, k = 0; u < my_units; u += 4, ++k) {
-                    const int n = u >> 1, qt = u & 1, st = n & 1;
-                    mbar_wait(&full[st], (n >> 1) & 1);
-                    ATT_TRACE(u, 10);
-                    if (k == 0 && w >= 2 && stagger > 0) { const long long t0 = clock64(); while (clock64() - t0 < stagger) { } }   // regions {2, 3} run out of phase with {0, 1}
-                    mbar_wait(&tmem_free[w], (k & 1) ^ 1);
-                    tc_fence_after();
-                    ATT_TRACE(u, 0);
-                    const uint32_t sq = smem_u32(smem + st * G::STAGE + qt * (AQ * 128));
-                    const uint32_t sk = smem_u32(smem + st * G::STAGE + G::SQ);
-                    const uint32_t sv = smem_u32(smem + st * G::STAGE + G::SQ + G::SK);
-                    const uint64_t da = make_smem_desc_sw128(sq, 0, 1024);
-                    for (int p = 0; p < nph; ++p) {
-                        const bool do_pv = p >= nkb1;
-                        const int kb = do_pv ? p - nkb1 : p;
-                        int kb0, wk;
-                        key_block(g16, do_pv ? nkb2 : nkb1, kb, kb0, wk);
-                        const uint32_t idesc_s = make_idesc_bf16(AQ, wk);
-                        const uint64_t dk = make_smem_desc_sw128(sk + kb0 * 128, 0, 1024);
-#pragma unroll
-                        for (int kk = 0; kk < HD / 16; ++kk) tc_mma_f16(th, da + uint64_t(2 * kk), dk + uint64_t(2 * kk), idesc_s, kk != 0);
-                        tc_commit(&s_ready[w]);
-                        if (p == 0) ATT_TRACE(u, 1);
-                        mbar_wait(&p_ready[w], ph & 1); ++ph;
-                        tc_fence_after();
-                        if (!do_pv) continue;
-                        if (p + 1 == nph) ATT_TRACE(u, 2);
-                        uint64_t db = make_smem_desc_sw128(sv + kb0 * 128, 32768, 1024);
-                        for (int kk = 0; kk < wk / 16; ++kk) {
-                            tc_mma_f16_ts(th + R4_OCOL, th + kk * 8, db, idesc_o, (kb | kk) != 0);
-                            db += 2048 >> 4;
-                        }
-                        if (p + 1 < nph) {               // the next S block overwrites the P columns this product reads
-                            tc_commit(&pv_done[w]);
-                            mbar_wait(&pv_done[w], pvn & 1); ++pvn;
-                            tc_fence_after();
-                        }
-                    }
-                    tc_commit(&o_ready[w]);
-                    tc_commit(&stage_free[st]);
-                    ATT_TRACE(u, 3);
-                }
-            }
-        }
-    } else {
-        reg_alloc<R4_REGS_SOFTMAX>();
-        // ===================== softmax + epilogue warpgroups =====================
-        const int w = warp >> 2, q = warp & 3;
-        const int r = q * 32 + lane;
-        const uint32_t trow = tmem + (uint32_t(q * 32) << 16) + w * R4_REGION;
-        const int bar_id = 1 + w;
-        const bool issuer = r == 0;
-        constexpr float kLog2e = 1.4426950408889634f;
-        uint32_t ph = 0;
-        for (int u = w, k = 0; u < my_units; u += 4, ++k) {
-            const int n = u >> 1, qt = u & 1, st = n & 1;
-            const int item = blockIdx.x + n * gridDim.x;
-            const int b = item / H, h = item - b * H;
-            const int len = lens ? min(lens[b], Tn) : Tn;
-            const int rows_valid = min(AQ, Tn - qt * AQ);
-            const bool active = q * 32 < rows_valid;
-            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-            float mxl = 0.f;
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-            for (int p = 0; p < nph; ++p) {
-                const bool do_exp = p >= nkb1;
-                int kb0, wk;
-                key_block(g16, do_exp ? nkb2 : nkb1, do_exp ? p - nkb1 : p, kb0, wk);
-                const int lim = min(len - kb0, wk);
-                mbar_wait(&s_ready[w], ph & 1); ++ph;
-                tc_fence_after();
-                if (issuer && p == 0) ATT_TRACE(u, 4);
-                if (active) {
-                    if (!do_exp) {
-                        const int npiece = (wk + 31) / 32;
-                        uint32_t a[2][32];
-#pragma unroll 1
-                        for (int c = 0; c < npiece; c += 2) {
-                            tmem_ld_32x32b_x32(trow + c * 32, a[0]);
-                            if (c + 1 < npiece) tmem_ld_32x32b_x32(trow + (c + 1) * 32, a[1]);
-                            tmem_ld_wait();
-                            max32(a[0], c * 32, lim, mx4);
-                            if (c + 1 < npiece) max32(a[1], (c + 1) * 32, lim, mx4);
-                        }
-                        if (issuer && p + 1 == nkb1) ATT_TRACE(u, 5);
-                    } else {
-                        if (p == nkb1) mxl = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * kLog2e;   // key 0 is valid: finite
-                        // no register double-buffering here: four warps per scheduler (one of each region) cover the TMEM load latency
-                        auto exp16 = [&](const uint32_t* cur, int col0, uint32_t* pk) {
-                            float pe[16];
-                            if (col0 + 16 <= lim) {
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) pe[j] = ex2_approx(fmaf(__uint_as_float(cur[j]), kLog2e, -mxl));
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) pe[j] = col0 + j < lim ? ex2_approx(fmaf(__uint_as_float(cur[j]), kLog2e, -mxl)) : 0.f;
-                            }
-                            s0 += (pe[0] + pe[4]) + (pe[8] + pe[12]); s1 += (pe[1] + pe[5]) + (pe[9] + pe[13]);
-                            s2 += (pe[2] + pe[6]) + (pe[10] + pe[14]); s3 += (pe[3] + pe[7]) + (pe[11] + pe[15]);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(pe[2 * j], pe[2 * j + 1]);
-                        };
-#pragma unroll 1
-                        for (int c0 = 0; c0 < wk; c0 += 16) {
-                            uint32_t a[16], pk[8];
-                            tmem_ld_32x32b_x16(trow + c0, a);
-                            tmem_ld_wait();
-                            exp16(a, c0, pk);
-                            tmem_st_32x32b_x8(trow + (c0 >> 1), pk);
-                        }
-                        tmem_st_wait();
-                    }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&p_ready[w]);
-            }
-            const float inv = 1.0f / ((s0 + s1) + (s2 + s3));
-            if (issuer) ATT_TRACE(u, 6);
-            // ---- epilogue: O / sum -> bf16 -> the unit's own Q tile (dead: every S MMA has completed) -> TMA store
-            mbar_wait(&o_ready[w], k & 1);
-            tc_fence_after();
-            if (issuer) ATT_TRACE(u, 7);
-            uint8_t* tile = smem + st * G::STAGE + qt * (AQ * 128);
-            uint8_t* srow = tile + r * 128;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t o[32];                                  // unconditional (an idle quadrant reads stale columns; its rows are clipped by the store)
-                tmem_ld_32x32b_x32(trow + R4_OCOL + half * 32, o);
-                tmem_ld_wait();
-                if (half == 1) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_free[w]);      // the issuer may start S(u + 4)
-                    if (issuer) ATT_TRACE(u, 8);
-                }
-                {
-#pragma unroll
-                    for (int c8 = 0; c8 < 4; ++c8) {
-                        uint4 wv;
-                        wv.x = pack_bf16x2(__uint_as_float(o[8 * c8 + 0]) * inv, __uint_as_float(o[8 * c8 + 1]) * inv);
-                        wv.y = pack_bf16x2(__uint_as_float(o[8 * c8 + 2]) * inv, __uint_as_float(o[8 * c8 + 3]) * inv);
-                        wv.z = pack_bf16x2(__uint_as_float(o[8 * c8 + 4]) * inv, __uint_as_float(o[8 * c8 + 5]) * inv);
-                        wv.w = pack_bf16x2(__uint_as_float(o[8 * c8 + 6]) * inv, __uint_as_float(o[8 * c8 + 7]) * inv);
-                        *reinterpret_cast<uint4*>(srow + (((half * 4 + c8) ^ (r & 7)) << 4)) = wv;
-                    }
-                }
-            }
-            fence_proxy_async_smem();
-            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-            if (issuer) {
-                tma_store_3d(&tm_out, tile, h * HD, qt * AQ, b);     // rows t >= Tn fall outside the (d, t, b) tensor: clipped
-                tma_store_commit();
-                tma_store_wait_read<0>();                            // the tile goes back to the producer with the stage
-                mbar_arrive(&stage_free[st]);
-            }
-        }
-        if (issuer) tma_store_wait<0>();
-    }
-#undef ATT_TRACE
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 17) {
-        tc_fence_after();
-        tmem_dealloc<512>(tmem);
-    }
-}
-
 }  // namespace
 
 int attention_simt(const void* qkv, void* out, int io_bf16, int B, int T, int H, const int* lens, cudaStream_t stream) {
@@ -961,20 +689,6 @@ int attention_tc(const void* qkv, void* out, int B, int T, int H, const int* len
     const int grid = n_items < num_sms ? n_items : num_sms;
     static int stagger = -1;
     if (stagger < 0) { const char* sv = getenv("SLSB_ATTN_STAGGER"); stagger = sv ? atoi(sv) : 0; }
-    // two query tiles per item: four units in flight per SM (attn_tc4_kernel); SLSB_ATTN_NW=2 keeps the two-half kernel (A/B)
-    static int nw = -1;
-    if (nw < 0) { const char* v = getenv("SLSB_ATTN_NW"); nw = v ? atoi(v) : 4; }
-    if (!wide && n_qt == 2 && nw == 4) {
-        static bool configured4 = false;
-        if (!configured4) {
-            SLSB_CUDA_CHECK(cudaFuncSetAttribute(attn_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Geo::SMEM));
-            configured4 = true;
-        }
-        const int nkb1 = (Tp + R4_REGION - 1) / R4_REGION, nkb2 = (Tp + R4_OCOL - 1) / R4_OCOL;
-        SLSB_CUDA_CHECK(launch_pdl(attn_tc4_kernel, dim3(grid), dim3(R4_THREADS), Attn4Geo::SMEM, stream, tq, tkv, to, T, Tp, H, n_items, nkb1, nkb2,
-                                   lens, stagger, trace));
-        return 0;
-    }
     if (wide)
         SLSB_CUDA_CHECK(launch_pdl(attn_tc_kernel<true>, dim3(grid), dim3(P_THREADS), AttnGeo<true>::SMEM, stream, tq, tkv, to, T, Tp, H, n_items, n_qt,
                                    kvbox, nkb, kbw, lens, stagger, trace));

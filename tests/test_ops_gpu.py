@@ -341,10 +341,10 @@ def test_attention_tc_key_blocks(lib, cuda, B, T, lens):
 
 @pytest.mark.parametrize("B,T,lens", [(5, 201, [201, 130, 64, 17, 1]), (64, 201, None), (3, 129, None), (7, 255, [255, 200, 129, 128, 100, 50, 2]),
                                       (19, 240, None), (9, 144, [144, 143, 97, 96, 95, 49, 48, 47, 16])])
-def test_attention_tc_four_units(lib, cuda, B, T, lens):
-    """129 <= T <= 256 (two query tiles per item): the four-units-in-flight kernel (TMEM in four 128-column regions, max round over
-    <= 128-key blocks, exp round over <= 64-key blocks, output staged in the unit's own Q tile); odd item counts per CTA, padding
-    masks that end inside / at the edge of / before a key block, bit-stability, vs the fp32 torch reference and the CUDA-core kernel."""
+def test_attention_tc_two_tiles(lib, cuda, B, T, lens):
+    """129 <= T <= 256 (two query tiles per item, the 4-s clips of the headline config): odd item counts per CTA, padding masks
+    that end inside / at the edge of / before a 16-key group, rows of the last tile past T, bit-stability over three launches into
+    NaN-filled outputs, vs the fp32 torch reference and the CUDA-core kernel."""
     H = 16
     qkv = _rand((B, T, 3 * H * 64), 65, 0.5)
     qkv[..., :H * 64] *= 0.5
@@ -354,7 +354,7 @@ def test_attention_tc_four_units(lib, cuda, B, T, lens):
     outs = []
     for _ in range(3):
         out = torch.full((B, T, H * 64), float("nan"), device=cuda, dtype=torch.bfloat16)
-        ok(lib, lib.slsb_op_attention(2, 1, P(qkv), P(out), B, T, H, P(lens_t), stream()), "attention four units")
+        ok(lib, lib.slsb_op_attention(2, 1, P(qkv), P(out), B, T, H, P(lens_t), stream()), "attention two tiles")
         outs.append(out)
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])      # bit-stable
     out = outs[0].clone()
@@ -367,8 +367,8 @@ def test_attention_tc_four_units(lib, cuda, B, T, lens):
             out[i, n:] = 0
             ref[i, n:] = 0
             simt[i, n:] = 0
-    report(f"attention tc4 T={T}", out, ref, atol=1.5e-2, rtol=1e-2)
-    report(f"attention tc4 vs simt T={T}", out, simt, atol=1.5e-2, rtol=1e-2)
+    report(f"attention tc two tiles T={T}", out, ref, atol=1.5e-2, rtol=1e-2)
+    report(f"attention tc two tiles vs simt T={T}", out, simt, atol=1.5e-2, rtol=1e-2)
 
 
 def test_attention_tc_rejects_T_above_512(lib, cuda):
