@@ -21,3 +21,10 @@ echo "hbm capture rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:"sls_fuse_pool" -s 1 -c 1 -o gpurun_out/prof_pool -f $P > gpurun_out/ncu_pool.log 2>&1
 echo "pool capture rc=$?"
 # then, in the repo: python tools/ncu_summarize.py --round rNN  (writes profiles/)
+# head kernels of the heads main.py builds (H-SAE / H-WIN): fused select+pool
+PS="python tools/prof_step.py --steps 1 --warmup 1 --head sae"
+$PS > gpurun_out/prof_sae_plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"topk_pool_kernel|pool_finish_kernel" -s 2 -c 2 -o gpurun_out/prof_sae -f $PS > gpurun_out/ncu_sae.log 2>&1
+echo "sae head capture rc=$?"
+PW="python tools/prof_step.py --steps 1 --warmup 1 --head window"
+$PW > gpurun_out/prof_win_plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"window_select_kernel|window_vote_pool_kernel" -s 2 -c 2 -o gpurun_out/prof_win -f $PW > gpurun_out/ncu_win.log 2>&1
+echo "window head capture rc=$?"

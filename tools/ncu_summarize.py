@@ -119,7 +119,8 @@ def main():
         launch_list(ll, a.round, out_dir)
     traffic = {"_source": "ncu --set full --clock-control none captures (profiles/%s_ncu_*_summary.csv): dram__bytes_read.sum + "
                           "dram__bytes_write.sum per launch, bytes" % a.round}
-    for rep, tag in (("prof_gemm", "gemm"), ("prof_ln2", "conv_pair"), ("prof_hbm", "hbm_kernels"), ("prof_pool", "sls_pool")):
+    for rep, tag in (("prof_gemm", "gemm"), ("prof_ln2", "conv_pair"), ("prof_hbm", "hbm_kernels"), ("prof_pool", "sls_pool"),
+                     ("prof_sae", "sae_head"), ("prof_win", "window_head")):
         path = os.path.join(a.src, rep + ".ncu-rep")
         if not os.path.exists(path):
             continue
