@@ -210,6 +210,11 @@ int slsb_op_conv_ln_gelu(const void* x, const void* W, const float* bias, const 
 /* conv0 (raw audio, k = 10, stride 5) on tensor cores via a hi/lo bf16 split; scratch >= 64 KB + B*L0*128 bytes; out bf16 */
 int slsb_op_conv0_tc(const float* wav, const float* w, const float* bias, const float* ln_w, const float* ln_b, void* out,
                      void* scratch, int B, int S, void* stream);
+/* conv0 as ONE kernel (csrc/conv0_tc.cu; replaces the first block of wav2vec2.py:785-822): A tiles (hi/lo split of the audio window, bias
+ * in spare K columns) built in shared memory, LayerNorm statistics from the 11 x 11 Gram matrix of [w | b], weights resident, 16 epilogue
+ * warps; scratch >= 64 KB + 2 KB; out bf16 [B*L0, 512] */
+int slsb_op_conv0_fused(const float* wav, const float* w, const float* bias, const float* ln_w, const float* ln_b, void* out,
+                        void* scratch, int B, int S, void* stream);
 /* grouped positional conv + GELU + residual: x fp32 [B,T,D]; W [D, K*64] (per out channel: tap-major, 64 in-channels) */
 int slsb_op_posconv(int precision, const float* x, const void* W, const float* bias, float* out, void* scratch,
                     int B, int T, int D, int K, const int32_t* frame_lens_dev, void* stream);

@@ -67,6 +67,7 @@ _SIGNATURES = {
     "slsb_op_conv": (C.c_int, [C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "slsb_op_conv_ln_gelu": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "slsb_op_conv0_tc": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "slsb_op_conv0_fused": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "slsb_op_posconv": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "slsb_op_conv0": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "slsb_op_layernorm": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _P]),

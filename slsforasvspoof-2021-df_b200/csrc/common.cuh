@@ -67,10 +67,11 @@ __device__ __forceinline__ float tanh_approx(float x) {
     return y;
 }
 __device__ __forceinline__ float gelu_fast(float x) {
-    const float xc = fminf(fmaxf(x, -6.0f), 6.0f);
-    const float x2 = xc * xc;
+    // the polynomial is only monotone up to |x| ~ 7.2: clamp x^2 (one FMNMX) instead of x (two); past |x| = 6 the argument is
+    // 1.674 |x| > 10, where tanh.approx returns exactly +-1, the same value the clamped-x form produced (bit-identical outputs)
+    const float x2 = fminf(x * x, 36.0f);
     const float p = fmaf(x2, fmaf(x2, -0.00035151677629392575f, 0.03700564581269318f), 0.7975078480466281f);
-    const float t = tanh_approx(xc * p);
+    const float t = tanh_approx(x * p);
     const float hx = 0.5f * x;
     return fmaf(hx, t, hx);
 }
@@ -330,5 +331,7 @@ int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t
 // SWIZZLE_64B variant (inner box extent 64 bytes = 16 fp32): 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3)
 int encode_tmap_f32_sw64(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                          const uint32_t* box);
+int encode_tmap_bf16_sw64(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                          const uint32_t* box);
 
 }  // namespace slsb

@@ -73,6 +73,10 @@ int encode_tmap_f32_sw64(CUtensorMap* out, const void* base, int rank, const uin
     return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box, false, true);
 }
 
+int encode_tmap_bf16_sw64(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+    return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, false, true);
+}
+
 bool pdl_enabled() {
     static int on = -1;
     if (on < 0) { const char* v = getenv("SLSB_NO_PDL"); on = (v && atoi(v) != 0) ? 0 : 1; }
@@ -132,7 +136,7 @@ struct slsb_engine {
     int64_t launches = 0;
     // workspace
     Buf fe[2], lnbuf, qkv, attn, ffn, xmid, xfinal, xc, xpad, acts, encoded, sums, votes, thr, cut, thr_w, cut_w, pool_part, wmask, flac_bytes, flac_frames, flac_status, pooled, logprob,
-        sls_w, sls_in, sls_part, sls_dots, zeros, scratch, flens, wav_stage[2], lens_stage[2], score_stage[4], recon, tmp_bf16, im2col, conv0_w64, ybuf, pcm_stage, off_stage;
+        sls_w, sls_in, sls_part, sls_dots, zeros, scratch, flens, wav_stage[2], lens_stage[2], score_stage[4], recon, tmp_bf16, im2col, conv0_w64, conv0_wb64, conv0_gram, ybuf, pcm_stage, off_stage;
     // pipelined host scoring (slsb_score_submit / slsb_score_wait): uploads run on a private copy stream into two staging
     // slots so the H2D copy of batch i+1 overlaps the forward of batch i; up to 4 submissions may be in flight
     cudaStream_t copy_stream = nullptr;
@@ -340,6 +344,16 @@ static int attention(slsb_engine* e, bool bf, const void* qkv, void* out, int B,
 // epilogue behind the next tile's MMAs (measured conv1..6: 1208 us vs 1571 us per 64-clip batch).  K = 64 (conv0) has no
 // mainloop to hide anything behind and pays the pair's statistics exchange on every tile (722 us vs 515 us): it stays on the
 // one-CTA-per-row-block kernel.  SLSB_LN_GEMM_V1=1 / =2 force the old / the pair kernel everywhere (A/B measurements).
+#ifndef SLSB_CONV0_V1_DEFAULT
+#define SLSB_CONV0_V1_DEFAULT 0      // 1: im2col + tc_gemm_ln_kernel (round-1 conv0) unless SLSB_CONV0_V1=0
+#endif
+// conv0: the one-kernel form (conv0_tc.cu) for the XLS-R geometry; SLSB_CONV0_V1=1 selects im2col + tc_gemm_ln_kernel (A/B)
+static bool conv0_one_kernel(const slsb_config& c) {
+    static int v1 = -1;
+    if (v1 < 0) { const char* v = getenv("SLSB_CONV0_V1"); v1 = v ? (atoi(v) != 0 ? 1 : 0) : SLSB_CONV0_V1_DEFAULT; }
+    return !v1 && c.conv_dim == 512 && c.conv_kernel[0] >= 1 && c.conv_kernel[0] <= 15;
+}
+
 static int ln_gemm_dispatch(const TcLnGemmArgs& g, int num_sms, cudaStream_t st) {
     static int force = -1;
     if (force < 0) { const char* v = getenv("SLSB_LN_GEMM_V1"); force = v ? atoi(v) : 0; }
@@ -415,9 +429,13 @@ static int run_trunk(slsb_engine* e, const float* wav, const int* slens, int B, 
     const bool fused_ln = bf && c.reserved[0] == 0;     // reserved[0] = 1 disables the fused conv+LN+GELU tensor-core kernel
     if (fused_ln) {
         // bf16: every layer is one tcgen05 kernel with the LayerNorm + GELU in its epilogue
-        if (e->im2col.reserve((size_t)B * L[0] * 64 * 2)) return -1;
-        LAUNCH(conv0_im2col(wav, e->im2col.p, B, S, L[0], c.conv_kernel[0], c.conv_stride[0], st));
-        {
+        if (conv0_one_kernel(c)) {
+            ProfScope ps(e, st, PK_CONV_GEMM, 2.0 * (double)B * L[0] * C * c.conv_kernel[0]);
+            LAUNCH(conv0_tc(wav, e->conv0_wb64.p, e->conv0_gram.as<float>(), W32("conv0.ln.w"), W32("conv0.ln.b"), e->fe[0].p, B, S, L[0],
+                            c.conv_kernel[0], c.conv_stride[0], 1e-5f, e->num_sms, st));
+        } else {
+            if (e->im2col.reserve((size_t)B * L[0] * 64 * 2)) return -1;
+            LAUNCH(conv0_im2col(wav, e->im2col.p, B, S, L[0], c.conv_kernel[0], c.conv_stride[0], st));
             ProfScope ps(e, st, PK_CONV_GEMM, 2.0 * (double)B * L[0] * C * c.conv_kernel[0]);
             TcLnGemmArgs g;
             g.a_mode = A_PLAIN; g.A = e->im2col.p; g.lda = 64; g.W = e->conv0_w64.p; g.M = B * L[0]; g.K = 64; g.batches = 1;
@@ -745,7 +763,7 @@ int slsb_destroy(slsb_engine* e) {
     Buf* bufs[] = {&e->fe[0], &e->fe[1], &e->lnbuf, &e->qkv, &e->attn, &e->ffn, &e->xmid, &e->xfinal, &e->xc, &e->xpad, &e->acts, &e->encoded,
                    &e->sums, &e->votes, &e->thr, &e->cut, &e->thr_w, &e->cut_w, &e->pool_part, &e->wmask, &e->flac_bytes, &e->flac_frames, &e->flac_status, &e->pooled, &e->logprob, &e->sls_w, &e->sls_in, &e->sls_part, &e->sls_dots,
                    &e->zeros, &e->scratch, &e->flens, &e->wav_stage[0], &e->wav_stage[1], &e->lens_stage[0], &e->lens_stage[1], &e->score_stage[0],
-                   &e->score_stage[1], &e->score_stage[2], &e->score_stage[3], &e->recon, &e->tmp_bf16, &e->im2col, &e->conv0_w64, &e->ybuf,
+                   &e->score_stage[1], &e->score_stage[2], &e->score_stage[3], &e->recon, &e->tmp_bf16, &e->im2col, &e->conv0_w64, &e->conv0_wb64, &e->conv0_gram, &e->ybuf,
                    &e->pcm_stage, &e->off_stage};
     for (Buf* b : bufs) b->release();
     for (int i = 0; i < 2; ++i) { if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]); if (e->ev_slot_free[i]) cudaEventDestroy(e->ev_slot_free[i]); }
@@ -785,6 +803,11 @@ int slsb_finalize_weights(slsb_engine* e, void* stream) {
     }
     if (e->conv0_w64.reserve((size_t)e->cfg.conv_dim * 64 * 2)) return -1;
     LAUNCH(conv0_pack_weights(e->w.at("conv0.w").f32, e->conv0_w64.p, e->cfg.conv_dim, e->cfg.conv_kernel[0], static_cast<cudaStream_t>(stream)));
+    if (conv0_one_kernel(e->cfg)) {
+        if (e->conv0_wb64.reserve((size_t)e->cfg.conv_dim * 64 * 2) || e->conv0_gram.reserve((16 + 256) * 4)) return -1;
+        LAUNCH(conv0_tc_pack(e->w.at("conv0.w").f32, e->w.at("conv0.b").f32, e->conv0_wb64.p, e->conv0_gram.as<float>(), e->cfg.conv_dim,
+                             e->cfg.conv_kernel[0], static_cast<cudaStream_t>(stream)));
+    }
     e->finalized = true;
     return 0;
 }
@@ -1164,6 +1187,16 @@ int slsb_op_conv0_tc(const float* wav, const float* w, const float* bias, const 
     g.a_mode = A_PLAIN; g.A = cols; g.lda = 64; g.W = w64; g.M = B * L0; g.K = 64; g.batches = 1;
     g.out = out; g.bias = bias; g.ln_w = ln_w; g.ln_b = ln_b;
     return ln_gemm_dispatch(g, device_sms(), st);
+}
+
+int slsb_op_conv0_fused(const float* wav, const float* w, const float* bias, const float* ln_w, const float* ln_b, void* out, void* scratch,
+                        int B, int S, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int L0 = (S - 10) / 5 + 1;
+    char* w64 = static_cast<char*>(scratch);                       // [512, 64] bf16
+    float* gram = reinterpret_cast<float*>(w64 + 512 * 64 * 2);    // 272 floats
+    if (conv0_tc_pack(w, bias, w64, gram, 512, 10, st)) return -1;
+    return conv0_tc(wav, w64, gram, ln_w, ln_b, out, B, S, L0, 10, 5, 1e-5f, device_sms(), st);
 }
 
 int slsb_op_posconv(int precision, const float* x, const void* W, const float* bias, float* out, void* scratch, int B, int T, int D, int K,

@@ -49,6 +49,12 @@ int tc_gemm_ln_gelu_pair(const TcLnGemmArgs& g, int num_sms, cudaStream_t stream
 // conv0 on tensor cores: raw audio -> hi/lo-split bf16 im2col rows [B*L0, 64]; weights [C, k] -> [C, 64] (hi | lo | hi | 0)
 int conv0_im2col(const float* wav, void* out, int B, int S, int L0, int k, int stride, cudaStream_t stream);
 int conv0_pack_weights(const float* w, void* out, int C, int k, cudaStream_t stream);
+// conv0 as one kernel (conv0_tc.cu): audio -> bf16 [B*L0, 512]; row statistics from the (k+1) x (k+1) Gram matrix of [w | b], bias in
+// spare K columns, weights resident in shared memory, A tiles built in shared memory (no im2col buffer).
+// w64: [512, 64] bf16; gram: 272 floats (s[16] | G[16][16])
+int conv0_tc_pack(const float* w, const float* bias, void* w64, float* gram, int C, int k, cudaStream_t stream);
+int conv0_tc(const float* wav, const void* w64, const float* gram, const float* ln_w, const float* ln_b, void* out, int B, int S, int L0, int k,
+             int stride, float eps, int num_sms, cudaStream_t stream);
 
 // ---------------------------------------------------------------- fp32 SIMT GEMM (gemm_simt.cu)
 // C[z][m][n] = act(sum_k A[z][m][k] * W[zw][n][k] + bias[n_off + n]) (+ residual); A/W/out element types selectable.

@@ -859,6 +859,8 @@ def test_library_sass_is_blackwell_native(sls):
     wide = rows["attn_tc_kernel<true>"]                                                # T in (256, 512]: same tcgen05 structure
     assert wide["UTCHMMA"] > 0 and wide["STTM"] > 0 and wide["UTMALDG"] > 0
     assert ln2["UTCHMMA"] > 0 and ln2["UTMASTG"] > 0 and lns["UBLKCP"] > 0
+    c0 = rows["conv0_tc_kernel"]                                                       # conv0: audio -> tcgen05 -> LN + GELU -> TMA store
+    assert c0["UTCHMMA"] > 0 and c0["LDTM"] > 0 and c0["UTMASTG"] > 0 and c0["MUFU.TANH"] > 0
     assert all(v["HMMA"] == 0 for v in rows.values())
 
 

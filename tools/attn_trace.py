@@ -26,7 +26,7 @@ t0 = int(tr[0, 9]) if int(tr[0, 9]) else int(tr[tr > 0].min())
 names = ["S_iss", "S_com", "P_seen", "PV_com", "S_seen", "max_dn", "P_pub", "O_seen", "epi_dn", "st_free", "ld_land"]
 print("unit " + " ".join(f"{n:>8s}" for n in names) + " | S_lat softmax(p1,p2) PVwake PV_lat epi period")
 prev = {}
-NW = int(os.environ.get("SLSB_ATTN_NW", "4"))
+NW = int(os.environ.get("SLSB_ATTN_NW", "2"))
 for u in range(24):
     r = [int(tr[u, e]) - t0 if int(tr[u, e]) else -1 for e in range(11)]
     s_lat = r[4] - r[1]; p1 = r[5] - r[4]; p2 = r[6] - r[5]; pvw = r[2] - r[6]; pv_lat = r[7] - r[3]; epi = r[8] - r[7]
