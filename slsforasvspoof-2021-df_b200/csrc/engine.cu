@@ -354,10 +354,17 @@ static bool conv0_one_kernel(const slsb_config& c) {
     return !v1 && c.conv_dim == 512 && c.conv_kernel[0] >= 1 && c.conv_kernel[0] <= 15;
 }
 
+#ifndef SLSB_LN_GEMM_EPI8_DEFAULT
+#define SLSB_LN_GEMM_EPI8_DEFAULT 0      // 1: conv1..6 on the 8-epilogue-warp pair kernel unless SLSB_LN_GEMM_EPI8=0
+#endif
 static int ln_gemm_dispatch(const TcLnGemmArgs& g, int num_sms, cudaStream_t st) {
     static int force = -1;
     if (force < 0) { const char* v = getenv("SLSB_LN_GEMM_V1"); force = v ? atoi(v) : 0; }
     const bool pair = force == 2 || (force != 1 && g.K >= 256);
+    // SLSB_LN_GEMM_EPI8=1: the pair kernel with 8 epilogue warps (gemm_tc_ln2.cu) instead of 16 (gemm_tc_ln2x.cu)
+    static int epi8 = -1;
+    if (epi8 < 0) { const char* v = getenv("SLSB_LN_GEMM_EPI8"); epi8 = v ? (atoi(v) != 0 ? 1 : 0) : SLSB_LN_GEMM_EPI8_DEFAULT; }
+    if (pair && !epi8) return tc_gemm_ln_gelu_pair16(g, num_sms, st);
     return pair ? tc_gemm_ln_gelu_pair(g, num_sms, st) : tc_gemm_ln_gelu(g, num_sms, st);
 }
 

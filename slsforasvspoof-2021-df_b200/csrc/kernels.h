@@ -46,6 +46,8 @@ int tc_gemm_ln_gelu(const TcLnGemmArgs& g, int num_sms, cudaStream_t stream);
 // CTA-pair version (gemm_tc_ln2.cu): each CTA of a 2-CTA cluster owns 256 of the 512 channels, row statistics are exchanged
 // through distributed shared memory, so two accumulators fit in TMEM and the epilogue overlaps the next tile's MMAs
 int tc_gemm_ln_gelu_pair(const TcLnGemmArgs& g, int num_sms, cudaStream_t stream);
+// the same with 16 epilogue warps of 64 columns each (gemm_tc_ln2x.cu): the 8-warp epilogue, not the operand feed, bounded the pair kernel
+int tc_gemm_ln_gelu_pair16(const TcLnGemmArgs& g, int num_sms, cudaStream_t stream);
 // conv0 on tensor cores: raw audio -> hi/lo-split bf16 im2col rows [B*L0, 64]; weights [C, k] -> [C, 64] (hi | lo | hi | 0)
 int conv0_im2col(const float* wav, void* out, int B, int S, int L0, int k, int stride, cudaStream_t stream);
 int conv0_pack_weights(const float* w, void* out, int C, int k, cudaStream_t stream);

@@ -853,7 +853,7 @@ def test_library_sass_is_blackwell_native(sls):
     assert r.returncode == 0, r.stderr[-1500:]
     rows = {ln.split('",')[0].strip('"'): dict(zip(r.stdout.splitlines()[0].split(",")[1:], map(int, ln.split('",')[1].split(","))))
             for ln in r.stdout.splitlines()[1:]}
-    pair, attn, ln2, lns = rows["tc_gemm_pair_kernel"], rows["attn_tc_kernel<false>"], rows["tc_gemm_ln2_kernel<1>"], rows["ln_stream_kernel<true>"]
+    pair, attn, ln2, lns = rows["tc_gemm_pair_kernel"], rows["attn_tc_kernel<false>"], rows["tc_gemm_ln2x_kernel<1>"], rows["ln_stream_kernel<true>"]
     assert pair["UTCHMMA"] > 0 and pair["LDTM"] > 0 and pair["UTMALDG"] > 0 and pair["UTMASTG"] > 0 and pair["UTMAREDG"] > 0
     assert attn["UTCHMMA"] > 0 and attn["STTM"] > 0 and attn["UTMALDG"] > 0           # P written back into tensor memory
     wide = rows["attn_tc_kernel<true>"]                                                # T in (256, 512]: same tcgen05 structure
