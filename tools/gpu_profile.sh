@@ -14,7 +14,7 @@ $P > gpurun_out/prof_plain.log 2>&1 || { echo "plain prof_step failed"; exit 1; 
 # launch order inside a step: ... LN, qkv GEMM, attention, out GEMM, LN, fc1, fc2 ... : skip the first step (warm-up) entirely
 ncu --set full --clock-control none --import-source on -k regex:tc_gemm_pair_kernel -s 100 -c 4 -o gpurun_out/prof_gemm -f $P > gpurun_out/ncu_gemm.log 2>&1
 echo "gemm capture rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:tc_gemm_ln2_kernel -s 6 -c 2 -o gpurun_out/prof_ln2 -f $P > gpurun_out/ncu_ln2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"tc_gemm_ln2x_kernel|conv0_tc_kernel" -s 7 -c 3 -o gpurun_out/prof_ln2 -f $P > gpurun_out/ncu_ln2.log 2>&1
 echo "ln2 capture rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:"ln_stream_kernel|attn_tc_kernel" -s 80 -c 4 -o gpurun_out/prof_hbm -f $P > gpurun_out/ncu_hbm.log 2>&1
 echo "hbm capture rc=$?"
