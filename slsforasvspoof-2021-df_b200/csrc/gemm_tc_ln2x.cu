@@ -3,17 +3,22 @@
 //
 // Mainloop, cluster layout and statistics exchange are those of gemm_tc_ln2.cu (CTA r of a 2-CTA cluster owns channels
 // [256 r, 256 r + 256) of a 128-row block, two 128 x 256 accumulators in TMEM, (sum, sum of squares) exchanged through distributed
-// shared memory).  That kernel was EPILOGUE-bound, not feed-bound: with 8 epilogue warps (2 per scheduler, 128 columns per thread,
-// ~2 150 instructions per thread and tile at 0.33 IPC) the LayerNorm + GELU of a tile took ~20 k cycles against 13 k cycles of
-// MMAs (conv1, K = 1536), i.e. 64 % tensor-pipe activity; halving the operand traffic per SM (multicast A tile; a four-CTA
-// cta_group::2 version) changed nothing.  Here 16 epilogue warps (4 per scheduler) take 64 columns each:
+// shared memory).  Here 16 epilogue warps (4 per scheduler) take 64 columns each instead of 8 warps with 128:
 //   * pass 1: (sum, sum of squares) over 64 columns, 16-column TMEM loads double-buffered; the four column groups of a row combine
 //     through 4 KB of scratch borrowed from column group 0's staging buffer, then the pair exchange as before;
 //   * pass 2: normalise + affine + one-MUFU GELU -> bf16 -> 8 KB SWIZZLE_64B staging buffer per column group (32 columns at a time)
 //     -> TMA store.
+// Measured (SLSB_LN2_TRACE=1 python tools/conv_trace.py, conv1: K = 1536, 24 k-blocks per tile): the epilogue of a tile takes ~11 k
+// cycles (pass 1 1.5 k, statistics exchange 2.7 k, pass 2 7 k) and hides completely behind the next tile's mainloop, which runs
+// 783 clocks per k-block against 542 at the tensor peak: the 128 x 256 x 64 cta_group::1 step moves 48 KB INTO shared memory (TMA)
+// and reads 48 KB out of it (MMA operands), 96 KB per k-block at 128 B/clk = 750 clocks - the kernel sits on the shared-memory
+// bandwidth of this MMA shape (65 % tensor-pipe activity in ncu), not on the L2 feed (a multicast A tile changed nothing), not on
+// the epilogue (8 -> 16 warps: 573 -> 561 us for conv1) and a four-CTA cta_group::2 variant (80 KB per k-block and SM) lost more
+// to cluster placement and 256-row tiles than it gained.
 // 640 threads, 96 registers.  SLSB_LN_GEMM_EPI8=1 selects the 8-warp kernel (A/B).
 #include "common.cuh"
 #include "kernels.h"
+#include <cstdio>
 #include <cstdlib>
 
 namespace slsb {
@@ -37,6 +42,7 @@ struct Ln2xDev {
     int conv_cin, conv_stride;
     const float* bias; const float* ln_w; const float* ln_b;
     float eps;
+    long long* trace;   // SLSB_LN2_TRACE=1 (tuning only): clock64 stamps of pair 0 / CTA 0, trace[it * 8 + event]
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -97,6 +103,9 @@ tc_gemm_ln2x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
     const int num_tiles = p.batches * p.m_tiles;
     const int num_kb = p.K / BLOCK_K;
+    // events: 0 accumulator free (MMA), 1 first k-block landed, 2 last MMA issued, 3 accumulator complete seen by the epilogue,
+    // 4 pass 1 done, 5 peer statistics received, 6 epilogue done, 7 first load of the tile issued
+#define LN2_TRACE(it_, ev_) do { if (p.trace != nullptr && pair == 0 && rank == 0 && (it_) < 64) p.trace[(it_) * 8 + (ev_)] = clock64(); } while (0)
 
     griddep_launch();
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); tma_prefetch_desc(&tmap_out); }
@@ -117,10 +126,12 @@ tc_gemm_ln2x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+            int itp = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs, ++itp) {
                 const int m_blk = tile % p.m_tiles, b = tile / p.m_tiles;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (kb == 0) LN2_TRACE(itp, 7);
                     uint8_t* sa = smem + stage * kStage;
                     uint8_t* sb = sa + kStageA;
                     mbar_expect_tx(&full_bar[stage], kStage);
@@ -146,10 +157,12 @@ tc_gemm_ln2x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const int acc = it & 1;
                 mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
+                LN2_TRACE(it, 0);
                 const uint32_t d_tmem = tmem_base + acc * NHALF;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
+                    if (kb == 0) LN2_TRACE(it, 1);
                     const uint32_t sa = smem_u32(smem + stage * kStage);
                     const uint64_t da = make_smem_desc_sw128(sa, 0, 1024);
                     const uint64_t db = make_smem_desc_sw128(sa + kStageA, 0, 1024);
@@ -160,6 +173,7 @@ tc_gemm_ln2x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(&tmem_full[acc]);
+                LN2_TRACE(it, 2);
             }
         }
     } else if (warp >= 4) {
@@ -184,6 +198,7 @@ tc_gemm_ln2x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * NHALF + cg * 64;
             mbar_wait(&tmem_full[acc], (it >> 1) & 1);
             tc_fence_after();
+            if (warp == 4 && lane == 0) LN2_TRACE(it, 3);
             // ---- pass 1: (sum, sum of squares) over this thread's 64 columns; 16-column TMEM loads double-buffered in registers
             float s = 0.f, ss = 0.f;
             {
@@ -203,6 +218,7 @@ tc_gemm_ln2x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
                 }
             }
+            if (warp == 4 && lane == 0) LN2_TRACE(it, 4);
             // ---- combine the four column groups inside the CTA (fixed order 0, 1, 2, 3), then exchange the 256-channel partial with the peer
             if (cg == 0 && issuer) tma_store_wait_read<0>();          // group 0's last store no longer reads the buffer the scratch borrows
             asm volatile("bar.sync 1, 512;" ::: "memory");            // (the 16 epilogue warps only)
@@ -217,6 +233,7 @@ tc_gemm_ln2x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if (lane == 0) mbar_arrive_peer(peer_bar + (uint32_t)buf * 8u);
             }
             mbar_wait_cluster(&xch_full[buf], (it >> 1) & 1);
+            if (warp == 4 && lane == 0) LN2_TRACE(it, 5);
             const float2 px = xch[buf * 128 + r];
             const float mean = (cs + px.x) * (1.0f / NCH);
             const float var = fmaxf((css + px.y) * (1.0f / NCH) - mean * mean, 0.0f);
@@ -264,9 +281,11 @@ tc_gemm_ln2x_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
                 }
             }
+            if (warp == 4 && lane == 0) LN2_TRACE(it, 6);
         }
         if (issuer) tma_store_wait<0>();
     }
+#undef LN2_TRACE
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                 // the peer may still be writing into this CTA's exchange buffer until it is done too
@@ -293,6 +312,29 @@ int launch_ln2x(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     }
     const int tiles = dp.batches * dp.m_tiles;
     const int pairs = tiles < max_pairs ? tiles : max_pairs;
+    static const bool trace_on = getenv("SLSB_LN2_TRACE") && atoi(getenv("SLSB_LN2_TRACE")) != 0;
+    if (trace_on) {   // tuning aid: timeline of pair 0, printed after a stream sync (never on in production)
+        Ln2xDev q = dp;
+        static long long tr_buf[64 * 8];
+        long long* tr_dev = nullptr;
+        SLSB_CUDA_CHECK(cudaMalloc(&tr_dev, sizeof(tr_buf)));
+        SLSB_CUDA_CHECK(cudaMemsetAsync(tr_dev, 0, sizeof(tr_buf), stream));
+        q.trace = tr_dev;
+        SLSB_CUDA_CHECK(launch_pdl(kern, dim3(2 * pairs), dim3(kThreads), kSmemBytes, stream, ta, tb, to, q));
+        SLSB_CUDA_CHECK(cudaMemcpyAsync(tr_buf, tr_dev, sizeof(tr_buf), cudaMemcpyDeviceToHost, stream));
+        SLSB_CUDA_CHECK(cudaStreamSynchronize(stream));
+        long long t0 = 0;
+        for (int i = 0; i < 64 * 8; ++i) if (tr_buf[i] && (!t0 || tr_buf[i] < t0)) t0 = tr_buf[i];
+        fprintf(stderr, "ln2x_trace M=%d K=%d batches=%d pairs=%d tiles=%d\n", dp.M, dp.K, dp.batches, pairs, tiles);
+        for (int it = 0; it < 12; ++it) {
+            if (!tr_buf[it * 8 + 0]) break;
+            fprintf(stderr, "  it %2d: load_first %7lld | acc_free %7lld first_kb %7lld mma_done_issue %7lld | acc_ready %7lld pass1 %7lld stats %7lld epi_done %7lld\n", it,
+                    tr_buf[it * 8 + 7] - t0, tr_buf[it * 8 + 0] - t0, tr_buf[it * 8 + 1] - t0, tr_buf[it * 8 + 2] - t0, tr_buf[it * 8 + 3] - t0,
+                    tr_buf[it * 8 + 4] - t0, tr_buf[it * 8 + 5] - t0, tr_buf[it * 8 + 6] - t0);
+        }
+        cudaFree(tr_dev);
+        return 0;
+    }
     SLSB_CUDA_CHECK(launch_pdl(kern, dim3(2 * pairs), dim3(kThreads), kSmemBytes, stream, ta, tb, to, dp));
     return 0;
 }
