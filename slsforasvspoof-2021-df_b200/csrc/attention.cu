@@ -621,11 +621,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 int attention_simt(const void* qkv, void* out, int io_bf16, int B, int T, int H, const int* lens, cudaStream_t stream) {
     dim3 grid((T + SQ_ROWS - 1) / SQ_ROWS, H, B);
     constexpr int kSmem = (SQ_ROWS * HD + SK_TILE * (HD + 1) + SK_TILE * HD + 8 * SK_TILE * 4) * (int)sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured_on = 0;       // bit d: function attributes set on device d (they are per device)
+    if (first_use_on_device(&configured_on)) {
         SLSB_CUDA_CHECK(cudaFuncSetAttribute(attn_simt_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
         SLSB_CUDA_CHECK(cudaFuncSetAttribute(attn_simt_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-        configured = true;
     }
     if (io_bf16) attn_simt_kernel<bf16><<<grid, 256, kSmem, stream>>>(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), T, H, lens);
     else attn_simt_kernel<float><<<grid, 256, kSmem, stream>>>(static_cast<const float*>(qkv), static_cast<float*>(out), T, H, lens);
@@ -644,10 +643,9 @@ int attention_tc_v1(const void* qkv, void* out, int B, int T, int H, const int* 
     uint32_t boxq[2] = {HD, AQ}, boxkv[2] = {HD, (uint32_t)Tp};
     if (encode_tmap_bf16(&tq, qkv, 2, dims, strides, boxq)) return -1;
     if (encode_tmap_bf16(&tkv, qkv, 2, dims, strides, boxkv)) return -1;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured_on = 0;       // bit d: function attributes set on device d (they are per device)
+    if (first_use_on_device(&configured_on)) {
         SLSB_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-        configured = true;
     }
     dim3 grid((T + AQ - 1) / AQ, H, B);
     attn_tc_v1_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(tq, tkv, static_cast<bf16*>(out), T, Tp, H, lens);
@@ -679,11 +677,10 @@ int attention_tc(const void* qkv, void* out, int B, int T, int H, const int* len
     uint64_t ostrides[2] = {(uint64_t)D * 2, (uint64_t)T * D * 2};
     uint32_t obox[3] = {HD, AQ, 1};
     if (encode_tmap_bf16(&to, out, 3, odims, ostrides, obox)) return -1;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured_on = 0;       // bit d: function attributes set on device d (they are per device)
+    if (first_use_on_device(&configured_on)) {
         SLSB_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnGeo<false>::SMEM));
         SLSB_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnGeo<true>::SMEM));
-        configured = true;
     }
     const int n_items = B * H, n_qt = (T + AQ - 1) / AQ;
     const int grid = n_items < num_sms ? n_items : num_sms;

@@ -311,6 +311,15 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // host: launch with the programmatic-stream-serialization attribute (kernels that call griddep_wait() only);
 // SLSB_NO_PDL=1 turns the attribute off (A/B measurements)
 bool pdl_enabled();
+// cudaFuncSetAttribute (dynamic shared memory size) is per DEVICE: launchers keep one bit per device instead of a process-wide flag,
+// so an engine created on cuda:1 after one on cuda:0 configures its kernels too.  Returns true on the first call for the current device.
+inline bool first_use_on_device(unsigned long long* mask) {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    if ((*mask >> d) & 1ull) return false;
+    *mask |= 1ull << d;
+    return true;
+}
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

@@ -328,10 +328,9 @@ int conv0_tc(const float* wav, const void* w64, const float* gram, const float* 
         uint32_t box[2] = {32, C0_BLOCK_M};
         if (encode_tmap_bf16_sw64(&to, out, 2, dims, strides, box)) return -1;
     }
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured_on = 0;       // bit d: function attributes set on device d (they are per device)
+    if (first_use_on_device(&configured_on)) {
         SLSB_CUDA_CHECK(cudaFuncSetAttribute(conv0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C0_SMEM));
-        configured = true;
     }
     const int grid = dp.m_tiles < num_sms ? dp.m_tiles : num_sms;
     SLSB_CUDA_CHECK(launch_pdl(conv0_tc_kernel, dim3(grid), dim3(C0_THREADS), C0_SMEM, stream, tw, to, dp));

@@ -296,7 +296,8 @@ static bool ln_stream_enabled() {
 
 static int ln_stream_launch(const LnArgs& a, cudaStream_t stream) {
     static int num_sms = 0;
-    if (!num_sms) {
+    static unsigned long long configured_on = 0;       // bit d: function attributes set on device d (they are per device)
+    if (first_use_on_device(&configured_on)) {
         int dev = 0;
         SLSB_CUDA_CHECK(cudaGetDevice(&dev));
         SLSB_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));

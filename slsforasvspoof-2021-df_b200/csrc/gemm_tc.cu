@@ -869,16 +869,15 @@ int pair_tail_split(int tiles, int pairs) {
 
 int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr, const DevParams& dp, int num_sms,
                 cudaStream_t stream) {
-    static bool configured = false;
+    static unsigned long long configured_on = 0;       // bit d: function attributes set on device d (they are per device)
     static int max_pairs = 0;
-    if (!configured) {
+    if (first_use_on_device(&configured_on)) {
         SLSB_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan2::kBytes));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(num_sms & ~1); cfg.blockDim = dim3(kNumThreads); cfg.dynamicSmemBytes = Plan2::kBytes;
         int n = 0;
         if (cudaOccupancyMaxActiveClusters(&n, tc_gemm_pair_kernel, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms / 2; }
         max_pairs = n < num_sms / 2 ? n : num_sms / 2;
-        configured = true;
     }
     const int tiles = ((dp.M + 255) / 256) * dp.n_tiles;
     const int pairs = tiles < max_pairs ? tiles : max_pairs;
@@ -926,11 +925,10 @@ bool epilogue_supported(int act, int out_bf16, bool has_res) {
 template <int BLOCK_N, int A_MODE>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr, const DevParams& dp, int num_sms, cudaStream_t stream) {
     using Plan = SmemPlan<BLOCK_N>;
-    static bool configured = false;
+    static unsigned long long configured_on = 0;       // bit d: function attributes set on device d (they are per device)
     auto kern = tc_gemm_kernel<BLOCK_N, A_MODE>;
-    if (!configured) {
+    if (first_use_on_device(&configured_on)) {
         SLSB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::kBytes));
-        configured = true;
     }
     const int tiles = dp.batches * dp.m_tiles * dp.n_tiles;
     const int grid = tiles < num_sms ? tiles : num_sms;

@@ -220,11 +220,10 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
 template <int A_MODE>
 int launch_ln(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const LnDev& dp, int num_sms, cudaStream_t stream) {
-    static bool configured = false;
+    static unsigned long long configured_on = 0;       // bit d: function attributes set on device d (they are per device)
     auto kern = tc_gemm_ln_kernel<A_MODE>;
-    if (!configured) {
+    if (first_use_on_device(&configured_on)) {
         SLSB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        configured = true;
     }
     const int tiles = dp.batches * dp.m_tiles;
     SLSB_CUDA_CHECK(launch_pdl(kern, dim3(tiles < num_sms ? tiles : num_sms), dim3(kThreads), kSmemBytes, stream, ta, tb, to, dp));

@@ -276,10 +276,10 @@ tc_gemm_ln2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
 template <int A_MODE>
 int launch_ln2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const Ln2Dev& dp, int num_sms, cudaStream_t stream) {
-    static bool configured = false;
+    static unsigned long long configured_on = 0;       // bit d: function attributes set on device d (they are per device)
     static int max_pairs = 0;
     auto kern = tc_gemm_ln2_kernel<A_MODE>;
-    if (!configured) {
+    if (first_use_on_device(&configured_on)) {
         SLSB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         // persistent grid = as many 2-CTA clusters as can be co-resident (a GPC with an odd SM count leaves one SM unpaired)
         cudaLaunchConfig_t cfg = {};
@@ -287,7 +287,6 @@ int launch_ln2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& 
         int n = 0;
         if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms / 2; }
         max_pairs = n < num_sms / 2 ? n : num_sms / 2;
-        configured = true;
     }
     const int tiles = dp.batches * dp.m_tiles;
     const int pairs = tiles < max_pairs ? tiles : max_pairs;

@@ -836,11 +836,10 @@ int sls_fuse_pool(const void* const* layers, int layers_bf16, int n_layers, cons
     static const int vec8 = getenv("SLSB_POOL_VEC") ? atoi(getenv("SLSB_POOL_VEC")) == 8 : 0;
     static const int pool_tma = getenv("SLSB_POOL_TMA") ? atoi(getenv("SLSB_POOL_TMA")) : 1;   // default since round 2: 0.135 vs 0.165 ms (0.72 vs 0.59 of the copy bandwidth), parity green
     if (layers_bf16 && pool_tma && D == kPtD) {
-        static bool configured = false;
-        if (!configured) {
+        static unsigned long long configured_on = 0;       // bit d: function attributes set on device d (they are per device)
+        if (first_use_on_device(&configured_on)) {
             SLSB_CUDA_CHECK(cudaFuncSetAttribute(sls_fuse_pool_tma_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPtSmem));
             SLSB_CUDA_CHECK(cudaFuncSetAttribute(sls_fuse_pool_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPtSmem));
-            configured = true;
         }
         if (out_bf16) sls_fuse_pool_tma_kernel<bf16><<<grid, 160, kPtSmem, stream>>>(L, n_layers, layer_w, T, bn, bn_eps, static_cast<bf16*>(out), ldo);
         else sls_fuse_pool_tma_kernel<float><<<grid, 160, kPtSmem, stream>>>(L, n_layers, layer_w, T, bn, bn_eps, static_cast<float*>(out), ldo);
