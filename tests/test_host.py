@@ -347,6 +347,45 @@ def test_reference_main_py_runs_on_the_shim(sls, tmp_path, window):
     assert not out.exists() or out.read_text() == ""                                  # the stale score file was removed (main.py:646-647)
 
 
+def test_conv0_layernorm_statistics_from_the_gram_matrix():
+    """The identity csrc/conv0_tc.cu is built on (host arithmetic only, fp32 like the kernel): with a = [x_0..x_9, 1] and
+    W' = [w | b], the LayerNorm statistics of the 512 conv0 outputs y_n = a . W'_n are mean = a . s / 512 and
+    E[y^2] = a^T G a / 512 (s = column sums, G = W'^T W', both built in double once per weight load).  Cases: noise, a DC offset
+    30x the signal, digital silence, a bias with a large common component (mean >> std: the cancellation case)."""
+    rs = np.random.RandomState(7)
+    C, k = 512, 10
+    for kind in ("noise", "dc", "silence", "bias_offset"):
+        w = (rs.randn(C, k) * np.sqrt(2.0 / k)).astype(np.float32)
+        b = (rs.randn(C) * 0.05 + (5.0 if kind == "bias_offset" else 0.0)).astype(np.float32)
+        x = rs.randn(4000, k).astype(np.float32)
+        if kind == "dc":
+            x = (0.03 * x + 0.9).astype(np.float32)
+        elif kind == "silence":
+            x[:] = 0
+        wp = np.concatenate([w, b[:, None]], 1).astype(np.float64)
+        s32 = (wp.sum(0) / C).astype(np.float32)
+        g32 = (wp.T @ wp / C).astype(np.float32)
+        a = np.concatenate([x, np.ones((len(x), 1), np.float32)], 1)
+        mean = np.zeros(len(x), np.float32)
+        e2 = np.zeros(len(x), np.float32)
+        for i in range(k + 1):                      # the kernel's order: row i of G against a, then a_i times that, fp32 throughout
+            t = np.zeros(len(x), np.float32)
+            for j in range(k + 1):
+                t = (g32[i, j] * a[:, j] + t).astype(np.float32)
+            e2 = (a[:, i] * t + e2).astype(np.float32)
+            mean = (a[:, i] * s32[i] + mean).astype(np.float32)
+        var = np.maximum(e2 - mean * mean, 0).astype(np.float32)
+        rstd = 1.0 / np.sqrt(var + np.float32(1e-5))
+        y = a.astype(np.float64) @ wp.T             # direct: the 512 outputs, statistics over them in double
+        mean_ref, var_ref = y.mean(1), y.var(1)
+        rstd_ref = 1.0 / np.sqrt(var_ref + 1e-5)
+        assert np.abs(mean - mean_ref).max() <= 1e-6, kind                      # observed <= 3.2e-7
+        # what the epilogue applies is (y - mean) * rstd: compare the normalised outputs, not var itself
+        z = (y - mean[:, None].astype(np.float64)) * rstd[:, None].astype(np.float64)
+        z_ref = (y - mean_ref[:, None]) * rstd_ref[:, None]
+        assert np.abs(z - z_ref).max() <= (5e-5 if kind == "bias_offset" else 2e-6), (kind, float(np.abs(z - z_ref).max()))   # observed 1.7e-5 / 6.7e-7
+
+
 def test_shard_ranges_cover_exactly(sls):
     for n, w in [(611829, 8), (10, 4), (3, 8), (0, 2)]:
         r = [sls.shard_range(n, k, w) for k in range(w)]
