@@ -282,11 +282,15 @@ def leg_varlen(ctx, sls_b200, args, n_clips):
     prec = sls_b200.PRECISIONS[args.precision]
     rs = np.random.RandomState(4000 + ctx.rank)
     lens = rs.randint(16000, 160001, size=n_clips).tolist()
-    batches = sls_b200.bucket_by_frames(lens, eng.frames, bucket_frames=64, max_batch=args.batch)
+    min_rows = args.varlen_min_rows if args.varlen_min_rows > 0 else None
+    if args.varlen_buckets:
+        batches = sls_b200.bucket_by_frames(lens, eng.frames, bucket_frames=64, max_batch=args.batch, min_rows=min_rows)
+    else:
+        batches = sls_b200.batch_by_length(lens, eng.frames, max_pad_frames=64, max_batch=args.batch, min_rows=min_rows)
     dev_batches = []
     for bi, b in enumerate(batches):
         Smax = lens[b[0]]
-        wav = eng.synth_clips(ctx.rank * 100000 + bi * args.batch, len(b), Smax)
+        wav = eng.synth_clips(ctx.rank * 100000 + bi * 4 * args.batch, len(b), Smax)
         ln = torch.tensor([lens[i] for i in b], dtype=torch.int32, device=ctx.dev)
         wav *= (torch.arange(Smax, device=ctx.dev)[None, :] < ln[:, None])             # zero right-padding
         dev_batches.append((wav, ln))
@@ -301,7 +305,7 @@ def leg_varlen(ctx, sls_b200, args, n_clips):
     rec = {"value": n_clips * ctx.world / (ms * 1e-3), "unit": "utt/s", "audio_seconds_per_second": audio_s / (ms * 1e-3),
            "equivalent_4s_utt_per_s": audio_s / (64600 / 16000.0) / (ms * 1e-3), "clips": n_clips * ctx.world, "batches_per_rank": len(batches),
            "seconds": ms * 1e-3, "gpu_launches": int(launches), "frames_min_max": [min(frames), max(frames)],
-           "workload": f"{n_clips} clips per GPU, lengths U{{16000..160000}} samples (1-10 s), 64-frame buckets, batch <= {args.batch}, "
+           "workload": f"{n_clips} clips per GPU, lengths U{{16000..160000}} samples (1-10 s), {"64-frame buckets" if args.varlen_buckets else "length-sorted batches (< 64 frames of padding)"}, batch <= {args.batch} (short clips: up to {4 * args.batch}, >= {args.varlen_min_rows} frame rows per forward), "
                        "TopK-SAE head, padding masks; T > 256 runs the wide tcgen05 attention"}
     eng.close()
     del model, eng, dev_batches
@@ -466,6 +470,8 @@ def main():
                          "power-capped steady clock (a 611 829-clip job lives there); the cold-board burst is reported beside it")
     ap.add_argument("--df-eval-utts", type=int, default=611829, help="BASELINE config 3 leg: trials of the sharded DF-eval-sized run; 0 = off")
     ap.add_argument("--varlen-clips", type=int, default=1024, help="BASELINE config 4 leg: clips of 1-10 s per GPU; 0 = off")
+    ap.add_argument("--varlen-buckets", action="store_true", help="config 4 leg: fixed 64-frame buckets (round-1 batching) instead of length-sorted batches")
+    ap.add_argument("--varlen-min-rows", type=int, default=12864, help="config 4 leg: buckets of short clips take batches of up to 4 x --batch so that a forward has about this many frame rows; 0 = off")
     ap.add_argument("--ingest-clips", type=int, default=1024, help="ingest leg (PCM shard / FLAC files -> scores), N = 1 only; 0 = off")
     ap.add_argument("--legs", default="all", help="comma list out of heads,varlen,df_eval,ingest,torch_baseline (or all / none)")
     args = ap.parse_args()

@@ -15,7 +15,7 @@ from .engine import Engine, make_config, PRECISIONS, HEAD_NONE, HEAD_SAE, HEAD_W
 from .weights import TrunkGeometry, TrunkParams, pack_state_dict, load_checkpoint_tensors, load_model_checkpoint, fix_module_prefix
 from .model import Model, ModelWindowTopK, ModelSLS, SSLModel, AutoEncoderTopK, getAttenF
 from .scoring import (produce_evaluation_file, score_synthetic_shard, gather_scores, write_score_file, pad_clip,
-                      SyntheticEvalSet, shard_range, bucket_by_frames, score_variable_length, compute_eer, read_score_file,
+                      SyntheticEvalSet, shard_range, bucket_by_frames, batch_by_length, score_variable_length, compute_eer, read_score_file,
                       synth_clip_host)
 from .data_utils import genSpoof_list, pad, Dataset_ASVspoof2021_eval, Dataset_in_the_wild_eval
 from .ingest import (read_wav_pcm16, write_wav_pcm16, decode_wav_files, write_pcm_shard, wav_files_to_shard, PcmShard,
@@ -25,7 +25,7 @@ from .ingest import (read_wav_pcm16, write_wav_pcm16, decode_wav_files, write_pc
 
 __all__ = ["Model", "ModelWindowTopK", "ModelSLS", "SSLModel", "AutoEncoderTopK", "getAttenF", "Engine", "make_config",
            "TrunkGeometry", "TrunkParams", "pack_state_dict", "load_checkpoint_tensors", "load_model_checkpoint", "fix_module_prefix", "produce_evaluation_file", "score_synthetic_shard",
-           "gather_scores", "write_score_file", "pad_clip", "SyntheticEvalSet", "shard_range", "bucket_by_frames",
+           "gather_scores", "write_score_file", "pad_clip", "SyntheticEvalSet", "shard_range", "bucket_by_frames", "batch_by_length",
            "score_variable_length", "compute_eer", "read_score_file", "synth_clip_host", "SlsbError",
            "load_library", "LIB_PATH", "EXPORTED_SYMBOLS", "PRECISIONS", "HEAD_NONE", "HEAD_SAE", "HEAD_WINDOW",
            "HEAD_SLS", "HEAD_RETAIN", "PREC_FP32", "PREC_BF16", "read_wav_pcm16", "write_wav_pcm16", "decode_wav_files", "write_pcm_shard",

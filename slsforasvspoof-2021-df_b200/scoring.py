@@ -126,24 +126,58 @@ def score_synthetic_shard(model, lo: int, hi: int, batch: int = 64, samples: int
 # variable-length clips (BASELINE config 4): bucket by frame count, right-pad inside a bucket
 # ---------------------------------------------------------------------------------------------
 
-def bucket_by_frames(sample_lengths: Sequence[int], frames_of, bucket_frames: int = 64, max_batch: int = 64) -> List[List[int]]:
+def bucket_by_frames(sample_lengths: Sequence[int], frames_of, bucket_frames: int = 64, max_batch: int = 64,
+                     min_rows: Optional[int] = None) -> List[List[int]]:
     """Groups utterance indices so that every batch holds clips whose conv-stack frame counts fall into the same
     ``bucket_frames``-wide bucket (``frames_of(samples) -> frames``, e.g. ``Engine.frames``).  Inside a batch the
     indices are sorted by length (longest first: it defines the padded width); batches come out in bucket order and
-    every index appears exactly once."""
+    every index appears exactly once.  ``min_rows``: buckets of short clips take larger batches (up to 4 x ``max_batch``)
+    so that a forward still has about ``min_rows`` frame rows for the GEMMs (a batch of 64 one-second clips is only
+    3 200 rows: a quarter of the tiles 148 SMs need); scores do not depend on the batch a clip is scored in."""
     buckets = {}
     for i, n in enumerate(sample_lengths):
         buckets.setdefault((frames_of(int(n)) - 1) // bucket_frames, []).append(i)
     out: List[List[int]] = []
     for key in sorted(buckets):
         idx = sorted(buckets[key], key=lambda i: (-int(sample_lengths[i]), i))
-        out.extend(idx[j:j + max_batch] for j in range(0, len(idx), max_batch))
+        bs = max_batch
+        if min_rows:
+            bs = max(max_batch, min(4 * max_batch, int(min_rows) // ((key + 1) * bucket_frames)))
+        out.extend(idx[j:j + bs] for j in range(0, len(idx), bs))
+    return out
+
+
+def batch_by_length(sample_lengths: Sequence[int], frames_of, max_pad_frames: int = 64, max_batch: int = 64,
+                    min_rows: Optional[int] = None) -> List[List[int]]:
+    """Length-sorted batching for clips of arbitrary length (BASELINE config 4): the indices are sorted longest first and cut into
+    consecutive batches; a batch is closed when it holds ``max_batch`` clips (short clips: up to 4 x ``max_batch`` while the
+    forward has fewer than ``min_rows`` frame rows) or when the next clip would be padded by ``max_pad_frames`` frames or more.
+    Against fixed buckets (``bucket_by_frames``) there is one ragged batch per job instead of one per bucket and the padding of a
+    batch is bounded by the length spread of ITS clips.  Every index appears exactly once; scores do not depend on the batching."""
+    order = sorted(range(len(sample_lengths)), key=lambda i: (-int(sample_lengths[i]), i))
+    out: List[List[int]] = []
+    cur: List[int] = []
+    top = cap = 0
+    for i in order:
+        f = frames_of(int(sample_lengths[i]))
+        if cur and (len(cur) >= cap or top - f >= max_pad_frames):
+            out.append(cur)
+            cur = []
+        if not cur:
+            top = f
+            cap = max_batch
+            if min_rows:
+                cap = max(max_batch, min(4 * max_batch, int(min_rows) // max(top, 1)))
+        cur.append(i)
+    if cur:
+        out.append(cur)
     return out
 
 
 @torch.no_grad()
-def score_variable_length(model, clips: Sequence[torch.Tensor], bucket_frames: int = 64, max_batch: int = 64) -> torch.Tensor:
-    """Scores 1-D float32 clips of different lengths: length-bucketed batches, zero right-padding to the longest clip
+def score_variable_length(model, clips: Sequence[torch.Tensor], bucket_frames: int = 64, max_batch: int = 64,
+                          min_rows: Optional[int] = None) -> torch.Tensor:
+    """Scores 1-D float32 clips of different lengths: length-sorted batches (``batch_by_length``, at most ``bucket_frames`` frames of padding), zero right-padding to the longest clip
     of the batch, sample lengths passed down so that padded frames are masked (wav2vec2.py:567-586).  Returns the
     scores in the order of ``clips`` (CPU float32)."""
     m = model.module if hasattr(model, "module") else model
@@ -151,7 +185,7 @@ def score_variable_length(model, clips: Sequence[torch.Tensor], bucket_frames: i
     head, prec = (m._head() if hasattr(m, "_head") else 3), m._prec()
     lens = [int(c.numel()) for c in clips]
     scores = torch.empty(len(clips), dtype=torch.float32)
-    for batch in bucket_by_frames(lens, eng.frames, bucket_frames, max_batch):
+    for batch in batch_by_length(lens, eng.frames, bucket_frames, max_batch, min_rows):
         S = lens[batch[0]]
         wav = torch.zeros(len(batch), S, dtype=torch.float32, pin_memory=True)
         for j, i in enumerate(batch):

@@ -159,6 +159,28 @@ def test_bucket_by_frames_partitions_and_bounds(sls):
     assert sls.bucket_by_frames([], _frames) == []
 
 
+def test_batch_by_length_partitions_and_bounds(sls):
+    """Length-sorted batching (config 4): every index once, longest first inside and across batches, padding of a batch below
+    max_pad_frames, size <= max_batch (up to 4 x for short clips when min_rows asks for it), one ragged batch at most per closing rule."""
+    rs = np.random.RandomState(5)
+    lens = rs.randint(16000, 160001, size=700).tolist()
+    for min_rows in (None, 12864):
+        batches = sls.batch_by_length(lens, _frames, max_pad_frames=64, max_batch=32, min_rows=min_rows)
+        flat = [i for b in batches for i in b]
+        assert sorted(flat) == list(range(700))
+        assert [lens[i] for i in flat] == sorted(lens, reverse=True)
+        for b in batches:
+            fr = [_frames(lens[i]) for i in b]
+            assert fr[0] - fr[-1] < 64
+            cap = 32 if not min_rows else max(32, min(128, min_rows // fr[0]))
+            assert 1 <= len(b) <= cap
+        if min_rows:
+            assert max(len(b) for b in batches) > 32                       # one-second clips really get the larger batches
+    assert sls.batch_by_length([], _frames) == []
+    # three clips of very different lengths are not padded into one batch
+    assert [len(b) for b in sls.batch_by_length([160000, 16000, 80000], _frames)] == [1, 1, 1]
+
+
 def _frames(n):
     for k, s in [(10, 5), (3, 2), (3, 2), (3, 2), (3, 2), (2, 2), (2, 2)]:
         n = (n - k) // s + 1
