@@ -408,6 +408,34 @@ def test_conv0_layernorm_statistics_from_the_gram_matrix():
         assert np.abs(z - z_ref).max() <= (5e-5 if kind == "bias_offset" else 2e-6), (kind, float(np.abs(z - z_ref).max()))   # observed 1.7e-5 / 6.7e-7
 
 
+def test_conv0_hi_lo_split_arithmetic():
+    """The operand layout csrc/conv0_tc.cu builds in shared memory, restated in numpy: A row = [x_hi | x_hi | x_lo | 1 1 0..],
+    W row = [w_hi | w_lo | w_hi | b_hi b_lo 0..] (bf16 parts, fp32 accumulation), so that A . W = x_hi w_hi + x_hi w_lo + x_lo w_hi
+    + b_hi + b_lo.  Against the exact fp32 conv + bias the dropped x_lo w_lo term and the bf16 rounding of the lo parts leave a
+    relative error of ~2^-16 of the operand magnitudes - three orders of magnitude below the bf16 rounding of the output."""
+    bf = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).bfloat16().float().numpy()
+    rs = np.random.RandomState(11)
+    k, C = 10, 512
+    x = rs.randn(3000, k).astype(np.float32) * 0.3
+    w = (rs.randn(C, k) * np.sqrt(2.0 / k)).astype(np.float32)
+    b = (rs.randn(C) * 0.05).astype(np.float32)
+    x_hi = bf(x); x_lo = bf(x - x_hi)
+    w_hi = bf(w); w_lo = bf(w - w_hi)
+    b_hi = bf(b); b_lo = bf(b - b_hi)
+    A = np.zeros((len(x), 64), np.float32)
+    A[:, 0:k] = x_hi; A[:, 16:16 + k] = x_hi; A[:, 32:32 + k] = x_lo; A[:, 48] = 1.0; A[:, 49] = 1.0
+    W = np.zeros((C, 64), np.float32)
+    W[:, 0:k] = w_hi; W[:, 16:16 + k] = w_lo; W[:, 32:32 + k] = w_hi; W[:, 48] = b_hi; W[:, 49] = b_lo
+    assert np.array_equal(bf(A), A) and np.array_equal(bf(W), W)          # every operand element is exactly representable in bf16
+    got = A.astype(np.float64) @ W.astype(np.float64).T                   # the tensor core accumulates exact bf16 products in fp32
+    ref = x.astype(np.float64) @ w.astype(np.float64).T + b.astype(np.float64)
+    scale = (np.abs(x).astype(np.float64) @ np.abs(w).astype(np.float64).T + np.abs(b))
+    rel = np.abs(got - ref) / scale
+    assert rel.max() <= 2.0 ** -15, float(rel.max())                      # observed ~1e-5; bf16 output rounding is 2^-9
+    plain = bf(x).astype(np.float64) @ bf(w).astype(np.float64).T + bf(b).astype(np.float64)
+    assert (np.abs(plain - ref) / scale).max() > 50 * rel.max()           # what a single-bf16 operand GEMM would give
+
+
 def test_shard_ranges_cover_exactly(sls):
     for n, w in [(611829, 8), (10, 4), (3, 8), (0, 2)]:
         r = [sls.shard_range(n, k, w) for k in range(w)]
