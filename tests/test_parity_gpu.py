@@ -89,7 +89,7 @@ def test_logprob_parity_and_taps(sls, cuda, clips, case, precision):
     got_tap = eng.get_tensor("x", (B, T, D)).cpu()[:, ::25, ::64].numpy()
     tap_err = float(np.abs(got_tap - fx["x_tap"]).max())
     print(f"[{head}/{precision}] x_tap max|err|={tap_err:.3e}")
-    assert tap_err <= (1e-4 if precision == "fp32" else 0.15)
+    assert tap_err <= (2e-5 if precision == "fp32" else 4e-2)          # observed 6.7e-6 / 1.84e-2 on every box of round 2
     if head != "sls" and precision == "fp32":
         pooled = eng.get_tensor("pooled", (B, 4096)).cpu()
         assert float((pooled - taps["pooled"]).abs().max()) <= 1e-4
@@ -97,7 +97,7 @@ def test_logprob_parity_and_taps(sls, cuda, clips, case, precision):
         nnz = (enc > 0).sum(-1)
         nnz_diff = int((nnz != (taps["encoded"] > 0).sum(-1)).sum())
         print(f"[{head}/{precision}] frames whose kept count differs from the oracle: {nnz_diff}; pooled max|err|={float((pooled - taps['pooled']).abs().max()):.3e}")
-        assert nnz_diff <= 2                                                # selection agrees frame by frame
+        assert nnz_diff == 0                                                # selection agrees frame by frame (observed 0: the fp32 path is bit-deterministic)
         if head == "sae":
             assert int(nnz.max()) <= 128
 
